@@ -1,0 +1,485 @@
+"""Random-init, diffusers-0.18-shaped SD1.5 stand-ins (UNet, VAE, tokenizer, text encoder, DDIM scheduler).
+
+`diffusers` is not installed in this image and cannot be (no network), so both the oracle (the reference's own
+modules imported unmodified, see oracle/ref_import.py) and the B200 path run on this stand-in network with
+identical seeded weights.  Only the *attribute surface* the reference touches is reproduced
+(reference `src/utils/attention.py:32-214,344-415,434-450`,
+`src/demo/model.py:124-127,232,267,291-297`), with the SD1.5 architecture constants
+(block_out_channels (320,640,1280,1280), 2 layers per block, 8 heads, cross dim 768, GEGLU x4).
+
+The arithmetic of the convolutions / norms / feed-forwards is ordinary PyTorch (library kernels) -- it is the
+part of the UNet the hot path does not touch.
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Attention (class name must be literally 'Attention': reference attention.py:434)
+# --------------------------------------------------------------------------------------------------------------
+class Attention(nn.Module):
+    def __init__(self, query_dim, cross_attention_dim=None, heads=8, dim_head=40):
+        super().__init__()
+        inner = heads * dim_head
+        cross_attention_dim = cross_attention_dim if cross_attention_dim is not None else query_dim
+        self.heads = heads
+        self.scale = dim_head ** -0.5
+        self.upcast_attention = False
+        self.upcast_softmax = False
+        self.spatial_norm = None
+        self.group_norm = None
+        self.norm_cross = None
+        self.norm_encoder_hidden_states = None
+        self.residual_connection = False
+        self.rescale_output_factor = 1.0
+        self.to_q = nn.Linear(query_dim, inner, bias=False)
+        self.to_k = nn.Linear(cross_attention_dim, inner, bias=False)
+        self.to_v = nn.Linear(cross_attention_dim, inner, bias=False)
+        self.to_out = nn.ModuleList([nn.Linear(inner, query_dim), nn.Dropout(0.0)])
+
+    def prepare_attention_mask(self, attention_mask, target_length, batch_size=None):
+        return attention_mask
+
+    def head_to_batch_dim(self, tensor):
+        b, s, c = tensor.shape
+        h = self.heads
+        return tensor.reshape(b, s, h, c // h).permute(0, 2, 1, 3).reshape(b * h, s, c // h)
+
+    def batch_to_head_dim(self, tensor):
+        bh, s, d = tensor.shape
+        h = self.heads
+        return tensor.reshape(bh // h, h, s, d).permute(0, 2, 1, 3).reshape(bh // h, s, d * h)
+
+    def get_attention_scores(self, query, key, attention_mask=None):
+        scores = torch.bmm(query, key.transpose(-1, -2)) * self.scale
+        if attention_mask is not None:
+            scores = scores + attention_mask
+        return scores.softmax(dim=-1).to(query.dtype)
+
+    def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None):
+        ctx = hidden_states if encoder_hidden_states is None else encoder_hidden_states
+        q = self.head_to_batch_dim(self.to_q(hidden_states))
+        k = self.head_to_batch_dim(self.to_k(ctx))
+        v = self.head_to_batch_dim(self.to_v(ctx))
+        probs = self.get_attention_scores(q, k, attention_mask)
+        out = self.batch_to_head_dim(torch.bmm(probs, v))
+        return self.to_out[0](out)
+
+
+class GEGLU(nn.Module):
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+    def forward(self, x):
+        x, gate = self.proj(x).chunk(2, dim=-1)
+        return x * F.gelu(gate)
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim, mult=4):
+        super().__init__()
+        self.net = nn.ModuleList([GEGLU(dim, dim * mult), nn.Dropout(0.0), nn.Linear(dim * mult, dim)])
+
+    def forward(self, x):
+        for m in self.net:
+            x = m(x)
+        return x
+
+
+class BasicTransformerBlock(nn.Module):
+    def __init__(self, dim, heads, dim_head, cross_attention_dim):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn1 = Attention(dim, None, heads, dim_head)
+        self.norm2 = nn.LayerNorm(dim)
+        self.attn2 = Attention(dim, cross_attention_dim, heads, dim_head)
+        self.norm3 = nn.LayerNorm(dim)
+        self.ff = FeedForward(dim)
+
+    def forward(self, x, encoder_hidden_states=None):
+        x = self.attn1(self.norm1(x)) + x
+        x = self.attn2(self.norm2(x), encoder_hidden_states=encoder_hidden_states) + x
+        x = self.ff(self.norm3(x)) + x
+        return x
+
+
+class Transformer2DModel(nn.Module):
+    def __init__(self, channels, heads, cross_attention_dim, groups):
+        super().__init__()
+        self.norm = nn.GroupNorm(groups, channels, eps=1e-6)
+        self.proj_in = nn.Conv2d(channels, channels, 1)
+        self.transformer_blocks = nn.ModuleList(
+            [BasicTransformerBlock(channels, heads, channels // heads, cross_attention_dim)])
+        self.proj_out = nn.Conv2d(channels, channels, 1)
+
+    def forward(self, x, encoder_hidden_states=None):
+        b, c, h, w = x.shape
+        res = x
+        x = self.proj_in(self.norm(x))
+        x = x.permute(0, 2, 3, 1).reshape(b, h * w, c)
+        for blk in self.transformer_blocks:
+            x = blk(x, encoder_hidden_states=encoder_hidden_states)
+        x = x.reshape(b, h, w, c).permute(0, 3, 1, 2).contiguous()
+        return self.proj_out(x) + res
+
+
+class ResnetBlock2D(nn.Module):
+    def __init__(self, cin, cout, temb_ch, groups):
+        super().__init__()
+        self.norm1 = nn.GroupNorm(groups, cin, eps=1e-5)
+        self.conv1 = nn.Conv2d(cin, cout, 3, padding=1)
+        self.time_emb_proj = nn.Linear(temb_ch, cout)
+        self.norm2 = nn.GroupNorm(groups, cout, eps=1e-5)
+        self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
+        self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
+
+    def forward(self, x, temb):
+        h = self.conv1(F.silu(self.norm1(x)))
+        h = h + self.time_emb_proj(F.silu(temb))[:, :, None, None]
+        h = self.conv2(F.silu(self.norm2(h)))
+        if self.conv_shortcut is not None:
+            x = self.conv_shortcut(x)
+        return x + h
+
+
+class Downsample2D(nn.Module):
+    def __init__(self, ch):
+        super().__init__()
+        self.conv = nn.Conv2d(ch, ch, 3, stride=2, padding=1)
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+class Upsample2D(nn.Module):
+    def __init__(self, ch):
+        super().__init__()
+        self.conv = nn.Conv2d(ch, ch, 3, padding=1)
+
+    def forward(self, x, output_size=None):
+        if output_size is None:
+            x = F.interpolate(x, scale_factor=2.0, mode="nearest")
+        else:
+            x = F.interpolate(x, size=tuple(output_size), mode="nearest")
+        return self.conv(x)
+
+
+class CrossAttnDownBlock2D(nn.Module):
+    has_cross_attention = True
+
+    def __init__(self, cin, cout, temb_ch, heads, cross_dim, groups, add_downsample, layers=2):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(cin if i == 0 else cout, cout, temb_ch, groups) for i in range(layers)])
+        self.attentions = nn.ModuleList([Transformer2DModel(cout, heads, cross_dim, groups) for _ in range(layers)])
+        self.downsamplers = nn.ModuleList([Downsample2D(cout)]) if add_downsample else None
+
+    def forward(self, hidden_states, temb=None, encoder_hidden_states=None, attention_mask=None,
+                cross_attention_kwargs=None):
+        outs = ()
+        for r, a in zip(self.resnets, self.attentions):
+            hidden_states = r(hidden_states, temb)
+            hidden_states = a(hidden_states, encoder_hidden_states=encoder_hidden_states)
+            outs += (hidden_states,)
+        if self.downsamplers is not None:
+            for d in self.downsamplers:
+                hidden_states = d(hidden_states)
+            outs += (hidden_states,)
+        return hidden_states, outs
+
+
+class DownBlock2D(nn.Module):
+    has_cross_attention = False
+
+    def __init__(self, cin, cout, temb_ch, groups, add_downsample, layers=2):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(cin if i == 0 else cout, cout, temb_ch, groups) for i in range(layers)])
+        self.downsamplers = nn.ModuleList([Downsample2D(cout)]) if add_downsample else None
+
+    def forward(self, hidden_states, temb=None):
+        outs = ()
+        for r in self.resnets:
+            hidden_states = r(hidden_states, temb)
+            outs += (hidden_states,)
+        if self.downsamplers is not None:
+            for d in self.downsamplers:
+                hidden_states = d(hidden_states)
+            outs += (hidden_states,)
+        return hidden_states, outs
+
+
+class UNetMidBlock2DCrossAttn(nn.Module):
+    has_cross_attention = True
+
+    def __init__(self, ch, temb_ch, heads, cross_dim, groups):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(ch, ch, temb_ch, groups), ResnetBlock2D(ch, ch, temb_ch, groups)])
+        self.attentions = nn.ModuleList([Transformer2DModel(ch, heads, cross_dim, groups)])
+
+    def forward(self, hidden_states, temb=None, encoder_hidden_states=None, attention_mask=None,
+                cross_attention_kwargs=None):
+        hidden_states = self.resnets[0](hidden_states, temb)
+        hidden_states = self.attentions[0](hidden_states, encoder_hidden_states=encoder_hidden_states)
+        return self.resnets[1](hidden_states, temb)
+
+
+class UpBlock2D(nn.Module):
+    has_cross_attention = False
+
+    def __init__(self, cin, cout, prev_out, temb_ch, groups, add_upsample, layers=3):
+        super().__init__()
+        rs = []
+        for i in range(layers):
+            skip = cin if i == layers - 1 else cout
+            rin = prev_out if i == 0 else cout
+            rs.append(ResnetBlock2D(rin + skip, cout, temb_ch, groups))
+        self.resnets = nn.ModuleList(rs)
+        self.upsamplers = nn.ModuleList([Upsample2D(cout)]) if add_upsample else None
+
+    def forward(self, hidden_states, res_hidden_states_tuple, temb=None, upsample_size=None):
+        for r in self.resnets:
+            res = res_hidden_states_tuple[-1]
+            res_hidden_states_tuple = res_hidden_states_tuple[:-1]
+            hidden_states = r(torch.cat([hidden_states, res], dim=1), temb)
+        if self.upsamplers is not None:
+            for u in self.upsamplers:
+                hidden_states = u(hidden_states, upsample_size)
+        return hidden_states
+
+
+class CrossAttnUpBlock2D(nn.Module):
+    has_cross_attention = True
+
+    def __init__(self, cin, cout, prev_out, temb_ch, heads, cross_dim, groups, add_upsample, layers=3):
+        super().__init__()
+        rs = []
+        for i in range(layers):
+            skip = cin if i == layers - 1 else cout
+            rin = prev_out if i == 0 else cout
+            rs.append(ResnetBlock2D(rin + skip, cout, temb_ch, groups))
+        self.resnets = nn.ModuleList(rs)
+        self.attentions = nn.ModuleList([Transformer2DModel(cout, heads, cross_dim, groups) for _ in range(layers)])
+        self.upsamplers = nn.ModuleList([Upsample2D(cout)]) if add_upsample else None
+
+    def forward(self, hidden_states, res_hidden_states_tuple, temb=None, encoder_hidden_states=None,
+                cross_attention_kwargs=None, upsample_size=None, attention_mask=None):
+        for r, a in zip(self.resnets, self.attentions):
+            res = res_hidden_states_tuple[-1]
+            res_hidden_states_tuple = res_hidden_states_tuple[:-1]
+            hidden_states = r(torch.cat([hidden_states, res], dim=1), temb)
+            hidden_states = a(hidden_states, encoder_hidden_states=encoder_hidden_states)
+        if self.upsamplers is not None:
+            for u in self.upsamplers:
+                hidden_states = u(hidden_states, upsample_size)
+        return hidden_states
+
+
+class Timesteps(nn.Module):
+    """Sinusoidal embedding (flip_sin_to_cos=True, freq_shift=0: SD1.5 config)."""
+
+    def __init__(self, ch):
+        super().__init__()
+        self.ch = ch
+
+    def forward(self, timesteps):
+        half = self.ch // 2
+        exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32, device=timesteps.device) / half
+        emb = timesteps[:, None].float() * torch.exp(exponent)[None, :]
+        return torch.cat([torch.cos(emb), torch.sin(emb)], dim=-1)
+
+
+class TimestepEmbedding(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.linear_1 = nn.Linear(cin, cout)
+        self.linear_2 = nn.Linear(cout, cout)
+
+    def forward(self, sample, condition=None):
+        return self.linear_2(F.silu(self.linear_1(sample)))
+
+
+class UNet2DConditionModel(nn.Module):
+    """SD1.5-shaped UNet: 16 transformer blocks = 32 `Attention` modules in the order down(6)/mid(1)/up(9)."""
+
+    def __init__(self, block_out_channels=(320, 640, 1280, 1280), heads=8, cross_attention_dim=768,
+                 norm_num_groups=32, in_channels=4, out_channels=4):
+        super().__init__()
+        ch = list(block_out_channels)
+        temb_ch = ch[0] * 4
+        self.config = SimpleNamespace(center_input_sample=False, class_embed_type=None, addition_embed_type=None,
+                                      class_embeddings_concat=False, in_channels=in_channels,
+                                      block_out_channels=tuple(ch), attention_head_dim=heads,
+                                      cross_attention_dim=cross_attention_dim)
+        self.in_channels = in_channels
+        self.conv_in = nn.Conv2d(in_channels, ch[0], 3, padding=1)
+        self.time_proj = Timesteps(ch[0])
+        self.time_embedding = TimestepEmbedding(ch[0], temb_ch)
+        self.class_embedding = None
+        self.time_embed_act = None
+        self.encoder_hid_proj = None
+        g = norm_num_groups
+        downs = []
+        cout = ch[0]
+        for i in range(4):
+            cin, cout = cout, ch[i]
+            last = i == 3
+            if i < 3:
+                downs.append(CrossAttnDownBlock2D(cin, cout, temb_ch, heads, cross_attention_dim, g, not last))
+            else:
+                downs.append(DownBlock2D(cin, cout, temb_ch, g, not last))
+        self.down_blocks = nn.ModuleList(downs)
+        self.mid_block = UNetMidBlock2DCrossAttn(ch[-1], temb_ch, heads, cross_attention_dim, g)
+        rev = list(reversed(ch))
+        ups = []
+        cout = rev[0]
+        self.num_upsamplers = 0
+        for i in range(4):
+            prev = cout
+            cout = rev[i]
+            cin = rev[min(i + 1, 3)]
+            last = i == 3
+            if not last:
+                self.num_upsamplers += 1
+            if i == 0:
+                ups.append(UpBlock2D(cin, cout, prev, temb_ch, g, not last))
+            else:
+                ups.append(CrossAttnUpBlock2D(cin, cout, prev, temb_ch, heads, cross_attention_dim, g, not last))
+        self.up_blocks = nn.ModuleList(ups)
+        self.conv_norm_out = nn.GroupNorm(g, ch[0], eps=1e-5)
+        self.conv_act = nn.SiLU()
+        self.conv_out = nn.Conv2d(ch[0], out_channels, 3, padding=1)
+
+    @property
+    def dtype(self):
+        return next(self.parameters()).dtype
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def forward(self, sample, timestep, encoder_hidden_states):
+        """Plain forward (same dataflow as reference attention.py:13-223 with all optional inputs None)."""
+        timesteps = timestep
+        if not torch.is_tensor(timesteps):
+            timesteps = torch.tensor([timesteps], dtype=torch.int64, device=sample.device)
+        elif timesteps.ndim == 0:
+            timesteps = timesteps[None].to(sample.device)
+        timesteps = timesteps.expand(sample.shape[0])
+        emb = self.time_embedding(self.time_proj(timesteps).to(self.dtype))
+        sample = self.conv_in(sample)
+        res = (sample,)
+        for blk in self.down_blocks:
+            if blk.has_cross_attention:
+                sample, r = blk(hidden_states=sample, temb=emb, encoder_hidden_states=encoder_hidden_states)
+            else:
+                sample, r = blk(hidden_states=sample, temb=emb)
+            res += r
+        sample = self.mid_block(sample, emb, encoder_hidden_states=encoder_hidden_states)
+        for blk in self.up_blocks:
+            n = len(blk.resnets)
+            r, res = res[-n:], res[:-n]
+            if blk.has_cross_attention:
+                sample = blk(hidden_states=sample, temb=emb, res_hidden_states_tuple=r,
+                             encoder_hidden_states=encoder_hidden_states)
+            else:
+                sample = blk(hidden_states=sample, temb=emb, res_hidden_states_tuple=r)
+        return self.conv_out(self.conv_act(self.conv_norm_out(sample)))
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Scheduler / VAE / tokenizer / text encoder stubs
+# --------------------------------------------------------------------------------------------------------------
+class DDIMSchedulerStandin:
+    """alphas_cumprod of SD1.5 (scaled-linear beta 0.00085->0.012, T=1000, steps_offset=1, set_alpha_to_one=False)."""
+
+    def __init__(self):
+        betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=torch.float32) ** 2
+        self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
+        self.final_alpha_cumprod = self.alphas_cumprod[0]
+        self.config = SimpleNamespace(num_train_timesteps=1000, steps_offset=1)
+        self.num_inference_steps = None
+        self.timesteps = None
+
+    def set_timesteps(self, n, device=None):
+        self.num_inference_steps = n
+        ratio = 1000 // n
+        ts = (torch.arange(0, n) * ratio).flip(0).to(torch.int64) + 1
+        self.timesteps = ts
+
+
+class _LatentDist:
+    def __init__(self, mean):
+        self.mean = mean
+
+
+class VAEStandin(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.enc = nn.Conv2d(3, 4, 1)
+        self.dec = nn.Conv2d(4, 3, 1)
+
+    @property
+    def dtype(self):
+        return self.enc.weight.dtype
+
+    def encode(self, x):
+        return {"latent_dist": _LatentDist(self.enc(F.avg_pool2d(x, 8)))}
+
+    def decode(self, z):
+        return {"sample": F.interpolate(self.dec(z), scale_factor=8.0, mode="nearest")}
+
+
+class TokenizerStandin:
+    vocab = 1024
+
+    def __call__(self, prompt, padding="max_length", max_length=77, return_tensors="pt", **kw):
+        if isinstance(prompt, str):
+            prompt = [prompt]
+        ids = torch.zeros(len(prompt), max_length, dtype=torch.int64)
+        for i, p in enumerate(prompt):
+            ids[i, 0] = 1
+            for j, ch in enumerate(p[: max_length - 2]):
+                ids[i, j + 1] = 2 + (ord(ch) * 31 + j) % (self.vocab - 2)
+        return SimpleNamespace(input_ids=ids)
+
+
+class TextEncoderStandin(nn.Module):
+    def __init__(self, dim=768):
+        super().__init__()
+        self.tok = nn.Embedding(TokenizerStandin.vocab, dim)
+        self.pos = nn.Parameter(torch.zeros(77, dim))
+
+    def forward(self, ids):
+        return (self.tok(ids) + self.pos[None, : ids.shape[1]],)
+
+
+UNET_PRESETS = {
+    # full SD1.5 shape: d = 40/80/160/160 at 8 heads
+    "sd15": dict(block_out_channels=(320, 640, 1280, 1280), heads=8, cross_attention_dim=768, norm_num_groups=32),
+    # test-size: same head dims (40/80/160/160) with 2 heads, so the sm_100a kernels see the real d
+    "tiny": dict(block_out_channels=(80, 160, 320, 320), heads=2, cross_attention_dim=64, norm_num_groups=16),
+}
+
+
+def build_standin(preset="sd15", seed=0, device="cpu", dtype=torch.float32):
+    """Seeded, CPU-initialised (so weights are identical on every box), then moved to `device`."""
+    cfg = UNET_PRESETS[preset]
+    g = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    unet = UNet2DConditionModel(**cfg)
+    vae = VAEStandin()
+    text = TextEncoderStandin(cfg["cross_attention_dim"])
+    with torch.no_grad():
+        text.pos.normal_(0, 0.02)
+    torch.random.set_rng_state(g)
+    for m in (unet, vae, text):
+        m.eval().requires_grad_(False)
+    return SimpleNamespace(unet=unet.to(device=device, dtype=dtype), vae=vae.to(device=device, dtype=dtype),
+                           text_encoder=text.to(device=device, dtype=dtype), tokenizer=TokenizerStandin(),
+                           scheduler=DDIMSchedulerStandin())

@@ -1,0 +1,91 @@
+"""TEST INFRASTRUCTURE ONLY -- seeded input generators shared by oracle/make_golden.py and tests/.
+
+Every case is fully determined by its name (seeds are explicit) so that the fixture generator (run in the build
+container against the unmodified reference) and the parity tests (run anywhere) see identical inputs.  Inputs
+are ALSO stored inside the fixtures, so a change in a library RNG cannot silently unpin the goldens.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def blob_mask(res: int, seed: int, frac=(0.15, 0.3), dtype=np.uint8) -> np.ndarray:
+    """Filled ellipse, uint8 0/1 (SURVEY.md 8d synthetic source mask)."""
+    rng = np.random.default_rng(seed)
+    cy, cx = rng.uniform(0.3 * res, 0.7 * res, 2)
+    ay, ax = rng.uniform(frac[0] * res, frac[1] * res, 2)
+    yy, xx = np.mgrid[0:res, 0:res]
+    return ((((yy - cy) / ay) ** 2 + ((xx - cx) / ax) ** 2) <= 1.0).astype(dtype)
+
+
+def qkv(streams: int, S: int, C: int, seed: int, sk: int | None = None, logit_scale: float = 3.0, kstreams=None):
+    """q,k,v [B,S,C] fp32 with |logit| of a few units (random-init nets give near-uniform softmax: too easy)."""
+    g = torch.Generator().manual_seed(seed)
+    sk = S if sk is None else sk
+    kstreams = streams if kstreams is None else kstreams
+    q = torch.randn(streams, S, C, generator=g) * logit_scale
+    k = torch.randn(kstreams, sk, C, generator=g)
+    v = torch.randn(kstreams, sk, C, generator=g)
+    return q, k, v
+
+
+# name -> dict(kind=..., params)
+ATTN_CASES = {
+    # (kind, method, heads, d, res(full mask), S, cg, src_mode)
+    "tca_h8_s256":        dict(kind="edit", method="tca",  heads=8, d=8,  res=128, S=256, cg=0.6, src="blob", seed=11),
+    "mmsa_h8_s256":       dict(kind="edit", method="mmsa", heads=8, d=8,  res=128, S=256, cg=None, src="blob", seed=12),
+    "tca_h2_s64_d40":     dict(kind="edit", method="tca",  heads=2, d=40, res=64,  S=64,  cg=0.25, src="blob", seed=13),
+    "tca_h8_s64_empty":   dict(kind="edit", method="tca",  heads=8, d=8,  res=64,  S=64,  cg=1.0, src="empty", seed=14),
+    "tca_h8_s64_full":    dict(kind="edit", method="tca",  heads=8, d=8,  res=64,  S=64,  cg=0.5, src="full", seed=15),
+    "tca_h8_s64_onekey":  dict(kind="edit", method="tca",  heads=8, d=8,  res=64,  S=64,  cg=0.9, src="one", seed=16),
+    "bg_tca_h8_s256":     dict(kind="bg",   method="tca",  heads=8, d=8,  res=128, S=256, cg=0.7, src="blob", seed=17),
+    "bg_mmsa_h8_s64":     dict(kind="bg",   method="mmsa", heads=8, d=8,  res=64,  S=64,  cg=None, src="blob", seed=18),
+    "tca_h8_s256_res256": dict(kind="edit", method="tca", heads=8, d=8,  res=256, S=256, cg=0.4, src="blob", seed=19),
+}
+
+
+def attn_case_inputs(name: str):
+    c = ATTN_CASES[name]
+    C = c["heads"] * c["d"]
+    q, k, v = qkv(4, c["S"], C, c["seed"])
+    res = c["res"]
+    tgt = blob_mask(res, c["seed"] + 100)
+    if c["src"] == "blob":
+        src = blob_mask(res, c["seed"] + 200)
+    elif c["src"] == "empty":
+        src = np.zeros((res, res), np.uint8)
+    elif c["src"] == "full":
+        src = np.ones((res, res), np.uint8)
+    else:
+        src = np.zeros((res, res), np.uint8)
+        src[res // 2, res // 2] = 1          # survives nearest down-sampling only if on the sampling lattice
+        src[0, 0] = 1
+    out = dict(c)
+    out.update(q=q, k=k, v=v, src=torch.from_numpy(src), tgt=torch.from_numpy(tgt), scale=c["d"] ** -0.5)
+    return out
+
+
+def step_case_inputs(seed: int, h=16, w=16):
+    g = torch.Generator().manual_seed(seed)
+    eps4 = torch.randn(4, 4, h, w, generator=g)
+    x = torch.randn(2, 4, h, w, generator=g)
+    noise = torch.randn(2, 4, h, w, generator=g)
+    rng = np.random.default_rng(seed)
+    cfg_mask = torch.from_numpy(rng.integers(0, 3, (h, w)).astype(np.uint8))     # {0,1,2}: quirk Q1
+    var_mask = torch.from_numpy(rng.integers(0, 3, (h, w)).astype(np.uint8))
+    return eps4, x, noise, cfg_mask, var_mask
+
+
+def warp_case_inputs(seed: int, N=1, C=8, H=32, W=32):  # reference wrapAffine_tensor only supports N=1 (theta.unsqueeze(0))
+    rng = np.random.default_rng(seed)
+    src = rng.standard_normal((N, C, H, W)).astype(np.float32)
+    bg = rng.standard_normal((N, C, H, W)).astype(np.float32)
+    mask = blob_mask(H, seed + 5)
+    ang = rng.uniform(-30, 30)
+    sc = rng.uniform(0.7, 1.3)
+    dx, dy = rng.uniform(-0.15 * W, 0.15 * W, 2)
+    cx, cy = W / 2 - 0.5, H / 2 - 0.5
+    a, b = sc * np.cos(np.deg2rad(ang)), sc * np.sin(np.deg2rad(ang))
+    M = np.array([[a, b, (1 - a) * cx - b * cy + dx], [-b, a, b * cx + (1 - a) * cy + dy]], np.float64)
+    return src, bg, mask, M

@@ -1,0 +1,630 @@
+// (a) masked, KV-injected flash attention for sm_100a: tcgen05.mma + TMEM accumulators + TMA operand staging.
+//
+// Replaces the baddbmm -> softmax -> bmm triples (x3) + mask builders + blends of
+// Attention_Modulator.Temporal_contextal_attention (src/utils/attention.py:1043-1091) and its _bg / _compose /
+// style-align / plain variants; see include/freefine_b200.h for the per-(stream,head) plan semantics.
+//
+// One CTA = one 128-row query tile of one (stream, head).  Six warps:
+//   warps 0-3  softmax + epilogue: thread t owns query row t == TMEM lane t (tcgen05.ld/st 32x32b)
+//   warp  4    TMA producer (one elected lane): Q once, then a ring of K/V tiles (128 keys x 64 channels boxes,
+//              SWIZZLE_128B, channels beyond head_dim zero-filled by the TMA bounds check), + TMEM alloc/dealloc
+//   warp  5    MMA issuer (one elected lane):  S = Q K^T  (SS, M128 N128 K16 x DPAD/16, both operands K-major)
+//                                              O += P V   (TS: P bf16 in TMEM, V MN-major straight from the K/V box)
+// Per K/V tile:  QK^T -> [s_full] -> softmax (2 sweeps over S in TMEM: max, then exp2 / row-sum / bf16 P written
+// over the S columns already consumed) -> [p_full] -> PV -> [o_done, kv_empty].  The running max is only
+// refreshed when it grows by more than 2^8 (lazy rescale: O stays in TMEM, read-modify-written only then).
+// Region masks are bit-vectors; `allowed(q,k)` is evaluated in registers on 32-bit words, nothing [S,S]-shaped
+// exists anywhere.  Every pass of a plan has its own softmax; pass results are combined as
+// sum_p weight_p*roww_p(q)*O_p/l_p in registers (DPAD<=80) or in a third TMEM region (DPAD=160).
+// Overlap of the tensor pipe with the exp-bound softmax comes from two co-resident CTAs per SM (<=256 TMEM columns
+// and <=113 KB shared memory each for head_dim<=48, the S=4096 layers that dominate).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "ff_common.cuh"
+
+namespace {
+
+constexpr int BM = 128;                 // query rows per CTA
+constexpr int BN = 128;                 // keys per tile
+constexpr int BOX_COLS = 64;            // channels per TMA box (128 bytes of bf16 = one swizzle-128B row)
+constexpr int TILE_BYTES = BN * 128;    // 16 KiB: 128 rows x 128 B
+constexpr int NUM_THREADS = 192;
+constexpr float RESCALE_THRESHOLD = 8.f;   // log2 units
+
+template <int DPAD> struct Cfg {
+  static constexpr int NKT = (DPAD + BOX_COLS - 1) / BOX_COLS;          // 64-channel boxes per operand tile
+  static constexpr int NSTAGE = DPAD <= 80 ? 2 : 1;                     // K/V ring depth
+  static constexpr bool ACC_TMEM = DPAD > 80;                           // cross-pass accumulator location
+  static constexpr int TMEM_S = 0, TMEM_O = BN, TMEM_ACC = BN + DPAD;
+  static constexpr int TMEM_USED = BN + DPAD + (ACC_TMEM ? DPAD : 0);
+  static constexpr int TMEM_COLS = TMEM_USED <= 256 ? 256 : 512;
+  static constexpr int SMEM_Q = NKT * TILE_BYTES;
+  static constexpr int SMEM_STAGE = 2 * NKT * TILE_BYTES;               // K tiles then V tiles
+  static constexpr int SMEM_BYTES = SMEM_Q + NSTAGE * SMEM_STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int MIN_CTAS = (SMEM_BYTES <= 113 * 1024 && TMEM_COLS == 256) ? 2 : 1;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000LL) {   // ~2 s: a protocol bug must fail loudly, not hang the GPU
+      printf("ff_attn: mbarrier wait timed out (block %d,%d,%d thread %d bar %u parity %u)\n", blockIdx.x,
+             blockIdx.y, blockIdx.z, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Shared-memory matrix descriptor, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor layout:
+// start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout_type=2 (128B swizzle) [61,64)).
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor kind::f16: D f32, A/B bf16, A K-major, B K-major (b_mn=0) or MN-major (b_mn=1), M=128.
+__host__ __device__ constexpr uint32_t make_idesc(int n, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(BM >> 4) << 24);
+}
+
+struct KParams {
+  const FFAttnHeadPlan* plan;
+  const uint32_t* bitmasks;
+  const int32_t* popc;
+  void* out;
+  int heads, head_dim, s_q, s_kv, mask_words, out_dtype, n_kv_streams;
+  float scale_log2;   // scale * log2(e)
+};
+
+// Pass-level decisions every role must take identically.
+struct PassInfo {
+  int kv[2];       // stream of each KV segment (-1: no such segment)
+  bool active;
+};
+__device__ __forceinline__ PassInfo pass_info(const FFAttnPass& ps, const KParams& p, int q0) {
+  PassInfo pi;
+  pi.kv[0] = ps.kv_stream;
+  pi.kv[1] = ps.kv_stream2;
+  pi.active = true;
+  if ((ps.flags & FF_PASS_ROW_WEIGHT) && ps.row_mask >= 0) {
+    // the pass contributes roww(q)=rowbit(q): skip it when no row of this tile is inside the region
+    uint32_t any = 0;
+    for (int c = 0; c < BM / 32; ++c) {
+      const int base = q0 + 32 * c;
+      if (base >= p.s_q) break;
+      uint32_t w = __ldg(p.bitmasks + (size_t)ps.row_mask * p.mask_words + (base >> 5));
+      const int rem = p.s_q - base;
+      if (rem < 32) w &= (1u << rem) - 1u;
+      any |= w;
+    }
+    pi.active = any != 0;
+  }
+  return pi;
+}
+
+template <int DPAD>
+__global__ void __launch_bounds__(NUM_THREADS, Cfg<DPAD>::MIN_CTAS)
+attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                      const __grid_constant__ CUtensorMap tm_v, const KParams p) {
+  using C = Cfg<DPAD>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B atoms are 1024-B aligned
+  const uint32_t sQ = smem_base;
+  const uint32_t sKV = smem_base + C::SMEM_Q;
+  const uint32_t bar_base = sKV + C::NSTAGE * C::SMEM_STAGE;
+  const uint32_t bar_q = bar_base, bar_s = bar_base + 8, bar_p = bar_base + 16, bar_o = bar_base + 24;
+  const uint32_t bar_kv_full = bar_base + 32, bar_kv_empty = bar_base + 32 + 8 * C::NSTAGE;
+  const uint32_t tmem_slot = bar_base + 32 + 16 * C::NSTAGE;            // u32 written by tcgen05.alloc
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BM, head = blockIdx.y, stream = blockIdx.z;
+  const FFAttnHeadPlan* plan = p.plan + (size_t)stream * p.heads + head;
+  int n_pass = __ldg(&plan->n_pass);
+  n_pass = n_pass < 0 ? 0 : (n_pass > FF_MAX_PASS ? FF_MAX_PASS : n_pass);
+  const int n_kv_tiles = (p.s_kv + BN - 1) / BN;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_q, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, BM);
+    mbar_init(bar_o, 1);
+    for (int i = 0; i < C::NSTAGE; ++i) {
+      mbar_init(bar_kv_full + 8 * i, 1);
+      mbar_init(bar_kv_empty + 8 * i, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+
+  if (warp == 4) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      mbar_expect_tx(bar_q, C::NKT * TILE_BYTES);
+      for (int kt = 0; kt < C::NKT; ++kt)
+        tma_load_4d(sQ + kt * TILE_BYTES, &tm_q, kt * BOX_COLS, head, q0, stream, bar_q);
+      int it = 0;
+      for (int ip = 0; ip < n_pass; ++ip) {
+        const FFAttnPass ps = plan->pass[ip];
+        const PassInfo pi = pass_info(ps, p, q0);
+        if (!pi.active) continue;
+        for (int seg = 0; seg < 2; ++seg) {
+          if (pi.kv[seg] < 0) continue;
+          for (int j = 0; j < n_kv_tiles; ++j, ++it) {
+            const int stage = it % C::NSTAGE, use = it / C::NSTAGE;
+            if (use > 0) mbar_wait(bar_kv_empty + 8 * stage, (use - 1) & 1);
+            const uint32_t full = bar_kv_full + 8 * stage;
+            const uint32_t sK = sKV + stage * C::SMEM_STAGE, sV = sK + C::NKT * TILE_BYTES;
+            mbar_expect_tx(full, 2 * C::NKT * TILE_BYTES);
+            for (int kt = 0; kt < C::NKT; ++kt) {
+              tma_load_4d(sK + kt * TILE_BYTES, &tm_k, kt * BOX_COLS, head, j * BN, pi.kv[seg], full);
+              tma_load_4d(sV + kt * TILE_BYTES, &tm_v, kt * BOX_COLS, head, j * BN, pi.kv[seg], full);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc(BN, 0);
+      constexpr uint32_t idesc_pv = make_idesc(DPAD, 1);
+      mbar_wait(bar_q, 0);
+      int it = 0;
+      for (int ip = 0; ip < n_pass; ++ip) {
+        const FFAttnPass ps = plan->pass[ip];
+        const PassInfo pi = pass_info(ps, p, q0);
+        if (!pi.active) continue;
+        bool first = true;
+        for (int seg = 0; seg < 2; ++seg) {
+          if (pi.kv[seg] < 0) continue;
+          for (int j = 0; j < n_kv_tiles; ++j, ++it) {
+            const int stage = it % C::NSTAGE, use = it / C::NSTAGE;
+            const uint32_t sK = sKV + stage * C::SMEM_STAGE, sV = sK + C::NKT * TILE_BYTES;
+            mbar_wait(bar_kv_full + 8 * stage, use & 1);
+            tc_fence_after();
+            // S = Q K^T.  The S/P columns are free: softmax(it-1) arrived on p_full before PV(it-1) was issued and
+            // the tensor pipe executes this thread's MMAs in issue order.
+#pragma unroll
+            for (int ks = 0; ks < DPAD / 16; ++ks) {
+              const uint32_t off = (ks >> 2) * TILE_BYTES + (ks & 3) * 32;   // 16 channels = 32 B inside the row
+              mma_ss(tmem + C::TMEM_S, smem_desc_sw128(sQ + off, 16), smem_desc_sw128(sK + off, 16), idesc_qk,
+                     ks > 0);
+            }
+            tc_commit(bar_s);
+            mbar_wait(bar_p, it & 1);
+            tc_fence_after();
+            // O (+)= P V : A = P (bf16, TMEM columns [0,64)), B = V tile, MN-major; 16 keys = 2048 B per K-step,
+            // 64-channel groups TILE_BYTES apart (LBO)
+#pragma unroll
+            for (int ks = 0; ks < BN / 16; ++ks)
+              mma_ts(tmem + C::TMEM_O, tmem + C::TMEM_S + ks * 8, smem_desc_sw128(sV + ks * 2048, TILE_BYTES),
+                     idesc_pv, (!first || ks > 0) ? 1u : 0u);
+            tc_commit(bar_kv_empty + 8 * stage);
+            tc_commit(bar_o);
+            first = false;
+          }
+        }
+      }
+    }
+  } else {
+    // ===================================== softmax + epilogue ===============================
+    const int row = q0 + threadIdx.x;
+    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    float acc[C::ACC_TMEM ? 1 : DPAD];
+    if constexpr (!C::ACC_TMEM) {
+#pragma unroll
+      for (int i = 0; i < DPAD; ++i) acc[i] = 0.f;
+    } else {
+      acc[0] = 0.f;
+    }
+    bool acc_started = false;   // ACC_TMEM: has any pass been added yet (uniform across the CTA)
+    int it = 0;
+    for (int ip = 0; ip < n_pass; ++ip) {
+      const FFAttnPass ps = plan->pass[ip];
+      const PassInfo pi = pass_info(ps, p, q0);
+      if (!pi.active) continue;
+      // ---- per-row constants of this pass
+      uint32_t rb = 0;
+      if (ps.row_mask >= 0 && row < p.s_q)
+        rb = (__ldg(p.bitmasks + (size_t)ps.row_mask * p.mask_words + (row >> 5)) >> (row & 31)) & 1u;
+      const bool row_flip = (ps.flags & FF_PASS_ROW_XOR) && rb;
+      float m_used = -INFINITY, l = 0.f;
+      bool first = true;
+      for (int seg = 0; seg < 2; ++seg) {
+        if (pi.kv[seg] < 0) continue;
+        const int kmask = seg == 0 ? ps.key_mask : ps.key_mask2;
+        const bool kinv = (ps.flags & (seg == 0 ? FF_PASS_KEY_INVERT : FF_PASS_KEY2_INVERT)) != 0;
+        const bool flip = kinv != row_flip;
+        // quirk Q4: a row whose allowed set is empty attends uniformly to every key
+        bool uniform = false;
+        if (kmask >= 0 && pi.kv[1] < 0) {
+          const int cnt = __ldg(p.popc + kmask);
+          uniform = (flip ? p.s_kv - cnt : cnt) == 0;
+        }
+        const float sc = uniform ? 0.f : p.scale_log2;
+        for (int j = 0; j < n_kv_tiles; ++j, ++it) {
+          // ---- allowed-key words of this tile for this row
+          uint32_t aw[4];
+          bool all_on = true;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int kbase = j * BN + 32 * c;
+            const int rem = p.s_kv - kbase;
+            const uint32_t valid = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+            uint32_t w = 0xffffffffu;
+            if (kmask >= 0 && !uniform && rem > 0) {
+              w = __ldg(p.bitmasks + (size_t)kmask * p.mask_words + (kbase >> 5));
+              if (flip) w = ~w;
+            }
+            aw[c] = w & valid;
+            all_on = all_on && (aw[c] == 0xffffffffu);
+          }
+          const bool fast = __all_sync(0xffffffffu, all_on);
+
+          mbar_wait(bar_s, it & 1);
+          tc_fence_after();
+          // ---- sweep 1: row max over the allowed keys (raw scores)
+          float mt = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float s[32];
+            tmem_ld32(tlane + C::TMEM_S + 32 * c, s);
+            tmem_wait_ld();
+            if (fast) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mt = fmaxf(mt, s[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mt = fmaxf(mt, (aw[c] >> i) & 1u ? s[i] : -INFINITY);
+            }
+          }
+          const float mts = uniform ? ((aw[0] | aw[1] | aw[2] | aw[3]) ? 0.f : -INFINITY) : mt * p.scale_log2;
+          // ---- running max, lazy rescale of O (TMEM read-modify-write only when the max grew by > 2^8)
+          float alpha = 1.f;
+          bool grow = false;
+          if (first || m_used == -INFINITY) {
+            m_used = mts;        // nothing accumulated for this row yet: its O row is exactly 0 (or about to be overwritten)
+          } else if (mts > m_used + RESCALE_THRESHOLD) {
+            alpha = fast_exp2(m_used - mts);
+            m_used = mts;
+            l *= alpha;
+            grow = true;
+          }
+          if (__any_sync(0xffffffffu, grow)) {
+            mbar_wait(bar_o, (it - 1) & 1);      // PV(it-1) has finished writing O
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < DPAD / 16; ++c) {
+              float o[16];
+              uint32_t ob[16];
+              tmem_ld16(tlane + C::TMEM_O + 16 * c, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) ob[i] = __float_as_uint(o[i] * alpha);
+              tmem_st16(tlane + C::TMEM_O + 16 * c, ob);
+            }
+          }
+          const float mref = m_used == -INFINITY ? 0.f : m_used;
+          // ---- sweep 2: p = 2^(s*scale*log2e - m), row sum, bf16 pairs written over S columns already consumed
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float s[32];
+            uint32_t pk[16];
+            tmem_ld32(tlane + C::TMEM_S + 32 * c, s);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float e = fast_exp2(fmaf(s[i], sc, -mref));
+              if (!fast) e = (aw[c] >> i) & 1u ? e : 0.f;
+              s[i] = e;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const __nv_bfloat162 b2 = __floats2bfloat162_rn(s[2 * i], s[2 * i + 1]);   // .x (low half) = key 2i
+              pk[i] = *reinterpret_cast<const uint32_t*>(&b2);
+              // the row sum uses the ROUNDED weights the tensor core will see: out = sum(p^ v) / sum(p^) stays a convex
+              // combination of V rows (exact when one key dominates)
+              l += __uint_as_float(pk[i] << 16) + __uint_as_float(pk[i] & 0xffff0000u);
+            }
+            tmem_st16(tlane + C::TMEM_S + 16 * c, pk);
+          }
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(bar_p);
+          first = false;
+        }
+      }
+      // ---- end of pass: acc += weight * roww / l * O
+      mbar_wait(bar_o, (it - 1) & 1);
+      tc_fence_after();
+      float coef = ps.weight;
+      if (ps.flags & FF_PASS_ROW_WEIGHT) coef = rb ? coef : 0.f;
+      coef = l > 0.f ? coef / l : 0.f;
+#pragma unroll
+      for (int c = 0; c < DPAD / 16; ++c) {
+        float o[16];
+        tmem_ld16(tlane + C::TMEM_O + 16 * c, o);
+        tmem_wait_ld();
+        if constexpr (C::ACC_TMEM) {
+          float a[16];
+          uint32_t ab[16];
+          if (acc_started) {
+            tmem_ld16(tlane + C::TMEM_ACC + 16 * c, a);
+            tmem_wait_ld();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] = 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) ab[i] = __float_as_uint(fmaf(coef, o[i], a[i]));
+          tmem_st16(tlane + C::TMEM_ACC + 16 * c, ab);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[16 * c + i] = fmaf(coef, o[i], acc[16 * c + i]);
+        }
+      }
+      if constexpr (C::ACC_TMEM) tmem_wait_st();
+      acc_started = true;
+    }
+    // ---- write the row: out[stream, row, head*d : (head+1)*d]
+    if (row < p.s_q) {
+      const size_t o_off = ((size_t)stream * p.s_q + row) * ((size_t)p.heads * p.head_dim) + (size_t)head * p.head_dim;
+#pragma unroll
+      for (int c = 0; c < DPAD / 16; ++c) {
+        float o[16];
+        if constexpr (C::ACC_TMEM) {
+          if (acc_started) {
+            tmem_ld16(tlane + C::TMEM_ACC + 16 * c, o);
+            tmem_wait_ld();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = acc[16 * c + i];
+        }
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (16 * c + 8 * g < p.head_dim) {   // head_dim % 8 == 0
+            if (p.out_dtype == FF_DT_BF16) {
+              uint4 v;
+              __nv_bfloat162 b0 = __floats2bfloat162_rn(o[8 * g + 0], o[8 * g + 1]);
+              __nv_bfloat162 b1 = __floats2bfloat162_rn(o[8 * g + 2], o[8 * g + 3]);
+              __nv_bfloat162 b2 = __floats2bfloat162_rn(o[8 * g + 4], o[8 * g + 5]);
+              __nv_bfloat162 b3 = __floats2bfloat162_rn(o[8 * g + 6], o[8 * g + 7]);
+              v.x = *reinterpret_cast<uint32_t*>(&b0);
+              v.y = *reinterpret_cast<uint32_t*>(&b1);
+              v.z = *reinterpret_cast<uint32_t*>(&b2);
+              v.w = *reinterpret_cast<uint32_t*>(&b3);
+              *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + o_off + 16 * c + 8 * g) = v;
+            } else {
+              float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + o_off + 16 * c + 8 * g);
+              dst[0] = make_float4(o[8 * g + 0], o[8 * g + 1], o[8 * g + 2], o[8 * g + 3]);
+              dst[1] = make_float4(o[8 * g + 4], o[8 * g + 5], o[8 * g + 6], o[8 * g + 7]);
+            }
+          }
+        }
+      }
+    }
+  }
+  // ---- teardown: every tcgen05 op of this CTA has completed (softmax threads waited on o_done of the last tile)
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// [streams, S, heads, d] bf16 view of a dense [streams, S, heads*d] tensor; box = 64 channels x 1 head x 128 rows.
+// Channels >= d of a box are out of bounds in dimension 0 and therefore zero-filled.
+int make_map(CUtensorMap* map, const void* base, int streams, int S, int heads, int d) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return ff::fail(FF_E_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  const cuuint64_t C = (cuuint64_t)heads * d;
+  cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)heads, (cuuint64_t)S, (cuuint64_t)streams};
+  cuuint64_t strides[3] = {(cuuint64_t)d * 2, C * 2, (cuuint64_t)S * C * 2};
+  cuuint32_t box[4] = {BOX_COLS, 1, BN, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return ff::fail(FF_E_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d) dims=[%d,%d,%d,%d]", (int)r, d, heads, S,
+                    streams);
+  return FF_OK;
+}
+
+template <int DPAD>
+int launch(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const KParams& kp, int n_streams,
+           cudaStream_t st) {
+  using C = Cfg<DPAD>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_masked_kv_kernel<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM_BYTES);
+    if (e != cudaSuccess) return ff::fail(FF_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", C::SMEM_BYTES,
+                                          cudaGetErrorString(e));
+    configured = true;
+  }
+  dim3 grid((kp.s_q + BM - 1) / BM, kp.heads, n_streams);
+  attn_masked_kv_kernel<DPAD><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(mq, mk, mv, kp);
+  return ff::check_launch("ff_attn_masked_kv");
+}
+
+}  // namespace
+
+extern "C" int ff_attn_masked_kv(const FFAttnArgs* a, void* stream) {
+  FF_REQUIRE(a != nullptr, "ff_attn_masked_kv: null args");
+  FF_REQUIRE(a->q && a->k && a->v && a->out && a->plan, "ff_attn_masked_kv: null pointer");
+  FF_REQUIRE(a->n_streams > 0 && a->n_kv_streams > 0 && a->heads > 0 && a->s_q > 0 && a->s_kv > 0,
+             "ff_attn_masked_kv: bad shape");
+  FF_REQUIRE(a->head_dim >= 8 && a->head_dim % 8 == 0, "ff_attn_masked_kv: head_dim=%d must be a multiple of 8",
+             a->head_dim);
+  if (a->head_dim > 160) return ff::fail(FF_E_UNSUPPORTED, "ff_attn_masked_kv: head_dim=%d > 160", a->head_dim);
+  FF_REQUIRE(a->heads <= 65535 && a->n_streams <= 65535, "ff_attn_masked_kv: heads / streams exceed grid limits");
+  FF_REQUIRE(ff::aligned16(a->q) && ff::aligned16(a->k) && ff::aligned16(a->v) && ff::aligned16(a->out),
+             "ff_attn_masked_kv: q/k/v/out must be 16-byte aligned");
+  FF_REQUIRE(a->out_dtype == FF_DT_BF16 || a->out_dtype == FF_DT_F32, "ff_attn_masked_kv: bad out_dtype");
+  FF_REQUIRE(a->scale > 0.f, "ff_attn_masked_kv: scale must be positive");
+  if (a->n_masks > 0) {
+    FF_REQUIRE(a->bitmasks && a->mask_popcount, "ff_attn_masked_kv: n_masks>0 but no bitmasks / popcounts");
+    const int need = ((a->s_q > a->s_kv ? a->s_q : a->s_kv) + 31) / 32;
+    FF_REQUIRE(a->mask_words >= need, "ff_attn_masked_kv: mask_words=%d < %d", a->mask_words, need);
+  }
+  int dev = 0, major = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) return ff::fail(FF_E_ARCH, "ff_attn_masked_kv: needs an sm_100 device (got sm_%d*)", major);
+
+  alignas(64) CUtensorMap mq, mk, mv;
+  int rc;
+  if ((rc = make_map(&mq, a->q, a->n_streams, a->s_q, a->heads, a->head_dim)) != FF_OK) return rc;
+  if ((rc = make_map(&mk, a->k, a->n_kv_streams, a->s_kv, a->heads, a->head_dim)) != FF_OK) return rc;
+  if ((rc = make_map(&mv, a->v, a->n_kv_streams, a->s_kv, a->heads, a->head_dim)) != FF_OK) return rc;
+
+  KParams kp;
+  kp.plan = a->plan;
+  kp.bitmasks = a->bitmasks;
+  kp.popc = a->mask_popcount;
+  kp.out = a->out;
+  kp.heads = a->heads;
+  kp.head_dim = a->head_dim;
+  kp.s_q = a->s_q;
+  kp.s_kv = a->s_kv;
+  kp.mask_words = a->mask_words;
+  kp.out_dtype = a->out_dtype;
+  kp.n_kv_streams = a->n_kv_streams;
+  kp.scale_log2 = a->scale * 1.4426950408889634f;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int d = a->head_dim;
+  if (d <= 16) return launch<16>(mq, mk, mv, kp, a->n_streams, st);
+  if (d <= 48) return launch<48>(mq, mk, mv, kp, a->n_streams, st);
+  if (d <= 80) return launch<80>(mq, mk, mv, kp, a->n_streams, st);
+  return launch<160>(mq, mk, mv, kp, a->n_streams, st);
+}

@@ -1,0 +1,228 @@
+// (b) fused affine warp + resample + mask-guided blend.
+//
+// Reference arithmetic: wrapAffine_tensor (src/utils/geo_utils.py:304-341) = F.affine_grid + F.grid_sample
+// (padding_mode='zeros', align_corners=False) for the image (bilinear) and for the mask (nearest), then the
+// np.where(mask, warped, background) blend of re_edit_2d (src/utils/vis_utils.py:252-256,272), in ONE pass:
+// the warped image, the warped mask and the blended result never make a round trip through HBM.
+//
+// Mapping: one CTA produces a 64x16 output tile for a chunk of channels.  The affine image of that tile is a
+// parallelogram; its bounding box in the source is staged in shared memory with 128-bit loads (each source texel is
+// read from HBM/L2 once per tile instead of up to 4 times, and the 4 bilinear taps become conflict-light LDS), the
+// background tile is read and the result written as 128-bit vectors.  If the bounding box does not fit (strong
+// minification) the taps go straight to global memory -- same arithmetic, same result.
+// Coordinates follow ATen's operation order in fp32 with explicit round-to-nearest ops (no FMA contraction):
+//   x_n = (2j+1)/dW - 1;  g = x_n*t00 + y_n*t01 + t02;  ix = ((g+1)*W - 1)/2;  nearest = rint (ties to even).
+#include <cuda_bf16.h>
+
+#include "ff_common.cuh"
+
+namespace {
+
+constexpr int TILE_X = 64, TILE_Y = 16, PX = 4;           // 4 consecutive output pixels per thread
+constexpr int THREADS = (TILE_X / PX) * TILE_Y;           // 256
+constexpr int STAGE_FLOATS = 5632;                        // 22 KB staging buffer per channel (x2 channels)
+constexpr int CH_PER_ITER = 2;
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> { using type = float4; };
+template <> struct Vec4<__nv_bfloat16> { using type = uint2; };
+
+struct Coord { float ix, iy; };
+
+__device__ __forceinline__ Coord src_coord(int x, int y, int dW, int dH, int W, int H, const float* t) {
+  const float xn = __fsub_rn(__fdiv_rn((float)(2 * x + 1), (float)dW), 1.f);
+  const float yn = __fsub_rn(__fdiv_rn((float)(2 * y + 1), (float)dH), 1.f);
+  const float gx = __fadd_rn(__fadd_rn(__fmul_rn(xn, t[0]), __fmul_rn(yn, t[1])), t[2]);
+  const float gy = __fadd_rn(__fadd_rn(__fmul_rn(xn, t[3]), __fmul_rn(yn, t[4])), t[5]);
+  Coord c;
+  c.ix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)W), 1.f), 2.f);
+  c.iy = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)H), 1.f), 2.f);
+  return c;
+}
+
+// Fetch functor: texel (xi, yi) of the current channel, zero outside the image.
+template <typename T> struct GlobalFetch {
+  const T* p; int W, H;
+  __device__ __forceinline__ float operator()(int xi, int yi) const {
+    return (xi >= 0 && xi < W && yi >= 0 && yi < H) ? to_f<T>(__ldg(p + (size_t)yi * W + xi)) : 0.f;
+  }
+};
+struct SmemFetch {
+  const float* s; int bx0, by0, bw, bh;   // staged box (already clipped to the image; outside = zero padding)
+  __device__ __forceinline__ float operator()(int xi, int yi) const {
+    const int u = xi - bx0, v = yi - by0;
+    return (u >= 0 && u < bw && v >= 0 && v < bh) ? s[v * bw + u] : 0.f;
+  }
+};
+
+template <typename F> __device__ __forceinline__ float sample(const F& f, Coord c, int mode) {
+  if (mode == 1) return f(__float2int_rn(c.ix), __float2int_rn(c.iy));
+  const float x0 = floorf(c.ix), y0 = floorf(c.iy);
+  const float x1 = __fadd_rn(x0, 1.f), y1 = __fadd_rn(y0, 1.f);
+  const float wx1 = __fsub_rn(x1, c.ix), wx0 = __fsub_rn(c.ix, x0);
+  const float wy1 = __fsub_rn(y1, c.iy), wy0 = __fsub_rn(c.iy, y0);
+  const int xi = (int)x0, yi = (int)y0;
+  float o = __fmul_rn(f(xi, yi), __fmul_rn(wx1, wy1));                           // nw
+  o = __fadd_rn(o, __fmul_rn(f(xi + 1, yi), __fmul_rn(wx0, wy1)));               // ne
+  o = __fadd_rn(o, __fmul_rn(f(xi, yi + 1), __fmul_rn(wx1, wy0)));               // sw
+  o = __fadd_rn(o, __fmul_rn(f(xi + 1, yi + 1), __fmul_rn(wx0, wy0)));           // se
+  return o;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(THREADS)
+warp_affine_blend_kernel(const T* __restrict__ src, const float* __restrict__ theta,
+                         const uint8_t* __restrict__ mask_src, const T* __restrict__ bg, T* __restrict__ out,
+                         uint8_t* __restrict__ mask_out, int C, int H, int W, int dH, int dW, int mode,
+                         int ch_per_cta, int tiles_x, int vec_ok) {
+  __shared__ __align__(16) float stage[CH_PER_ITER][STAGE_FLOATS];
+  __shared__ float th[6];
+  const int n = blockIdx.z;
+  const int tile = blockIdx.x;
+  const int tx0 = (tile % tiles_x) * TILE_X, ty0 = (tile / tiles_x) * TILE_Y;
+  const int c_begin = blockIdx.y * ch_per_cta;
+  const int c_end = min(C, c_begin + ch_per_cta);
+  if (threadIdx.x < 6) th[threadIdx.x] = theta[n * 6 + threadIdx.x];
+  __syncthreads();
+
+  const int lx = (threadIdx.x % (TILE_X / PX)) * PX, ly = threadIdx.x / (TILE_X / PX);
+  const int ox = tx0 + lx, oy = ty0 + ly;
+  const bool row_ok = oy < dH;
+
+  // per-thread source coordinates of its 4 pixels (shared by every channel) and the warped mask
+  Coord cd[PX];
+  bool keep[PX];          // true -> take the warped source, false -> background
+#pragma unroll
+  for (int j = 0; j < PX; ++j) {
+    cd[j] = src_coord(ox + j, oy, dW, dH, W, H, th);
+    keep[j] = true;
+  }
+  if (mask_src != nullptr) {
+    GlobalFetch<uint8_t> mf{mask_src + (size_t)n * H * W, W, H};
+#pragma unroll
+    for (int j = 0; j < PX; ++j) {
+      const bool in = row_ok && (ox + j) < dW;
+      // nearest sample of the mask: index = rint(coordinate)
+      const int xi = __float2int_rn(cd[j].ix), yi = __float2int_rn(cd[j].iy);
+      const uint8_t mv = (in && xi >= 0 && xi < W && yi >= 0 && yi < H) ? __ldg(mf.p + (size_t)yi * W + xi) : 0;
+      keep[j] = mv != 0;
+      if (in && mask_out != nullptr && blockIdx.y == 0) mask_out[((size_t)n * dH + oy) * dW + ox + j] = keep[j];
+    }
+  }
+
+  // bounding box of the tile's pre-image (affine map => extreme values at the 4 corners), +1 texel for bilinear
+  const int xe = min(tx0 + TILE_X, dW) - 1, ye = min(ty0 + TILE_Y, dH) - 1;
+  const Coord k0 = src_coord(tx0, ty0, dW, dH, W, H, th), k1 = src_coord(xe, ty0, dW, dH, W, H, th);
+  const Coord k2 = src_coord(tx0, ye, dW, dH, W, H, th), k3 = src_coord(xe, ye, dW, dH, W, H, th);
+  int bx0 = (int)floorf(fminf(fminf(k0.ix, k1.ix), fminf(k2.ix, k3.ix))) - 1;
+  int bx1 = (int)floorf(fmaxf(fmaxf(k0.ix, k1.ix), fmaxf(k2.ix, k3.ix))) + 2;
+  int by0 = (int)floorf(fminf(fminf(k0.iy, k1.iy), fminf(k2.iy, k3.iy))) - 1;
+  int by1 = (int)floorf(fmaxf(fmaxf(k0.iy, k1.iy), fmaxf(k2.iy, k3.iy))) + 2;
+  bx0 = max(bx0, 0) & ~3;                       // 16-byte aligned start for the vector loads
+  by0 = max(by0, 0);
+  bx1 = min(bx1, W - 1);
+  by1 = min(by1, H - 1);
+  int bw = bx1 - bx0 + 1, bh = by1 - by0 + 1;
+  bw = (bw + 3) & ~3;
+  if (bx0 + bw > W) bw = W - bx0;               // W % 4 != 0: ragged right edge, scalar staging
+  const bool empty_box = (bx1 < bx0) || (by1 < by0);
+  const bool staged = !empty_box && (long long)bw * bh <= STAGE_FLOATS;
+  const bool vec_stage = vec_ok && (bw % 4 == 0) && (W % 4 == 0);
+
+  for (int c0 = c_begin; c0 < c_end; c0 += CH_PER_ITER) {
+    const int nc = min(CH_PER_ITER, c_end - c0);
+    if (staged) {
+      __syncthreads();                            // previous iteration finished reading the buffers
+      for (int cc = 0; cc < nc; ++cc) {
+        const T* p = src + ((size_t)n * C + c0 + cc) * H * W;
+        if (vec_stage && sizeof(T) == 4) {
+          const int bw4 = bw >> 2;
+          for (int i = threadIdx.x; i < bw4 * bh; i += THREADS) {
+            const int v = i / bw4, u4 = i - v * bw4;
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(p + (size_t)(by0 + v) * W + bx0) + u4);
+            *reinterpret_cast<float4*>(&stage[cc][v * bw + u4 * 4]) = t4;
+          }
+        } else {
+          for (int i = threadIdx.x; i < bw * bh; i += THREADS) {
+            const int v = i / bw, u = i - v * bw;
+            stage[cc][i] = to_f<T>(__ldg(p + (size_t)(by0 + v) * W + bx0 + u));
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (!row_ok || ox >= dW) continue;            // (no barrier below this point inside the iteration)
+    for (int cc = 0; cc < nc; ++cc) {
+      const size_t obase = (((size_t)n * C + c0 + cc) * dH + oy) * dW + ox;
+      float r[PX];
+      if (empty_box) {
+#pragma unroll
+        for (int j = 0; j < PX; ++j) r[j] = 0.f;
+      } else if (staged) {
+        SmemFetch f{stage[cc], bx0, by0, bw, bh};
+#pragma unroll
+        for (int j = 0; j < PX; ++j) r[j] = sample(f, cd[j], mode);
+      } else {
+        GlobalFetch<T> f{src + ((size_t)n * C + c0 + cc) * H * W, W, H};
+#pragma unroll
+        for (int j = 0; j < PX; ++j) r[j] = sample(f, cd[j], mode);
+      }
+      if (vec_ok && ox + PX <= dW) {
+        using V = typename Vec4<T>::type;
+        T b[PX], o[PX];
+        if (mask_src != nullptr) *reinterpret_cast<V*>(b) = __ldg(reinterpret_cast<const V*>(bg + obase));
+#pragma unroll
+        for (int j = 0; j < PX; ++j) o[j] = keep[j] ? from_f<T>(r[j]) : b[j];
+        *reinterpret_cast<V*>(out + obase) = *reinterpret_cast<V*>(o);
+      } else {
+        for (int j = 0; j < PX && ox + j < dW; ++j)
+          out[obase + j] = keep[j] ? from_f<T>(r[j]) : bg[obase + j];
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int ff_warp_affine_blend(const void* src, const float* theta, const uint8_t* mask_src, const void* bg,
+                                    void* out, uint8_t* mask_out, int32_t N, int32_t C, int32_t H, int32_t W,
+                                    int32_t dH, int32_t dW, int32_t mode, int32_t dtype, void* stream) {
+  FF_REQUIRE(src && theta && out, "ff_warp_affine_blend: null pointer");
+  FF_REQUIRE(mask_src == nullptr || bg != nullptr, "ff_warp_affine_blend: mask given without a background");
+  FF_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && dH > 0 && dW > 0, "ff_warp_affine_blend: bad shape");
+  FF_REQUIRE(N <= 65535, "ff_warp_affine_blend: N=%d > 65535 (fold N into C for identical transforms)", N);
+  FF_REQUIRE(mode == 0 || mode == 1, "ff_warp_affine_blend: mode must be 0 (bilinear) or 1 (nearest)");
+  FF_REQUIRE(dtype == FF_DT_F32 || dtype == FF_DT_BF16, "ff_warp_affine_blend: dtype must be f32 or bf16");
+  const int tiles_x = (dW + TILE_X - 1) / TILE_X, tiles_y = (dH + TILE_Y - 1) / TILE_Y;
+  // channel chunks: enough CTAs to cover the 148 SMs a few times, but as few as possible so that the per-tile
+  // coordinate / mask work is amortised over many channels
+  const long long tiles = (long long)tiles_x * tiles_y * N;
+  int chunks = (int)((148LL * 8 + tiles - 1) / tiles);
+  if (chunks < 1) chunks = 1;
+  if (chunks > (C + CH_PER_ITER - 1) / CH_PER_ITER) chunks = (C + CH_PER_ITER - 1) / CH_PER_ITER;
+  int ch_per_cta = (C + chunks - 1) / chunks;
+  ch_per_cta = ((ch_per_cta + CH_PER_ITER - 1) / CH_PER_ITER) * CH_PER_ITER;
+  chunks = (C + ch_per_cta - 1) / ch_per_cta;
+  FF_REQUIRE(chunks <= 65535, "ff_warp_affine_blend: too many channel chunks");
+  const size_t es = dtype == FF_DT_F32 ? 4 : 2;
+  const int vec_ok = (dW % 4 == 0) && ff::aligned16(src) && ff::aligned16(out) && (!bg || ff::aligned16(bg)) &&
+                     ((size_t)H * W * es % 16 == 0) && ((size_t)dH * dW * es % 16 == 0);
+  dim3 grid(tiles_x * tiles_y, chunks, N);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == FF_DT_F32)
+    warp_affine_blend_kernel<float><<<grid, THREADS, 0, st>>>(
+        static_cast<const float*>(src), theta, mask_src, static_cast<const float*>(bg), static_cast<float*>(out),
+        mask_out, C, H, W, dH, dW, mode, ch_per_cta, tiles_x, vec_ok);
+  else
+    warp_affine_blend_kernel<__nv_bfloat16><<<grid, THREADS, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(src), theta, mask_src, static_cast<const __nv_bfloat16*>(bg),
+        static_cast<__nv_bfloat16*>(out), mask_out, C, H, W, dH, dW, mode, ch_per_cta, tiles_x, vec_ok);
+  return ff::check_launch("ff_warp_affine_blend");
+}

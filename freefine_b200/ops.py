@@ -1,0 +1,204 @@
+"""Torch-tensor front end of the C ABI (include/freefine_b200.h).  PyTorch is only the owner of device memory and
+streams here: every function validates its tensors, takes raw pointers and calls libfreefine_b200.so on
+torch.cuda.current_stream().  No function has a PyTorch / CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import FF_DT_BF16, FF_DT_F32
+
+_DT = {torch.float32: FF_DT_F32, torch.bfloat16: FF_DT_BF16}
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _chk(t: torch.Tensor, dtype, name: str, dims=None):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (freefine_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    if dims is not None and t.dim() != dims:
+        raise ValueError(f"{name} must have {dims} dims, got {tuple(t.shape)}")
+    return t
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# (c) DDIM / CFG steps
+# ---------------------------------------------------------------------------------------------------------------
+def ddim_cfg_step(eps4, x, noise, cfg_mask, var_mask, guidance_scale, sqrt_1m_at, sqrt_at, sqrt_ap, c_ddim, c_ddpm,
+                  sigma, want_pred_x0=False, out=None):
+    """eps4 [E,4,C,h,w] (or [4E,C,h,w]), x [E,2,C,h,w] (or [2E,C,h,w]) fp32; masks u8 [E,h,w]; returns x_prev like x
+    (and pred_x0).  See ff_ddim_cfg_step in include/freefine_b200.h; reference model.py:605-611,134-198."""
+    _chk(eps4, torch.float32, "eps4")
+    _chk(x, torch.float32, "x")
+    Cc, h, w = x.shape[-3:]
+    n_edits = x.numel() // (2 * Cc * h * w)
+    if eps4.numel() != 2 * x.numel():
+        raise ValueError(f"eps4 {tuple(eps4.shape)} must hold 4 streams per edit for x {tuple(x.shape)}")
+    _chk(var_mask, torch.uint8, "var_mask")
+    if var_mask.numel() != n_edits * h * w:
+        raise ValueError("var_mask must be [n_edits,h,w]")
+    if cfg_mask is not None:
+        _chk(cfg_mask, torch.uint8, "cfg_mask")
+        if cfg_mask.numel() != n_edits * h * w:
+            raise ValueError("cfg_mask must be [n_edits,h,w]")
+    if noise is not None:
+        _chk(noise, torch.float32, "noise")
+        if noise.numel() != x.numel():
+            raise ValueError("noise must have the shape of x")
+    x_prev = torch.empty_like(x) if out is None else _chk(out, torch.float32, "out")
+    x0 = torch.empty_like(x) if want_pred_x0 else None
+    lib = _lib.load()
+    rc = lib.ff_ddim_cfg_step(_ptr(eps4), _ptr(x), _ptr(noise), _ptr(cfg_mask), _ptr(var_mask), guidance_scale,
+                              sqrt_1m_at, sqrt_at, sqrt_ap, c_ddim, c_ddpm, sigma, _ptr(x_prev), _ptr(x0), n_edits,
+                              Cc, h, w, _stream())
+    _lib.check(rc, "ff_ddim_cfg_step")
+    return (x_prev, x0) if want_pred_x0 else x_prev
+
+
+def ddim_inv_step(eps, x, sqrt_1m_at, sqrt_at, sqrt_an, c_next, want_pred_x0=False):
+    """reference inv_step, model.py:109-132."""
+    _chk(eps, torch.float32, "eps")
+    _chk(x, torch.float32, "x")
+    if eps.shape != x.shape:
+        raise ValueError("eps and x must have the same shape")
+    x_next = torch.empty_like(x)
+    x0 = torch.empty_like(x) if want_pred_x0 else None
+    rc = _lib.load().ff_ddim_inv_step(_ptr(eps), _ptr(x), sqrt_1m_at, sqrt_at, sqrt_an, c_next, _ptr(x_next), _ptr(x0),
+                                      x.numel(), _stream())
+    _lib.check(rc, "ff_ddim_inv_step")
+    return (x_next, x0) if want_pred_x0 else x_next
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# (b) warp + blend
+# ---------------------------------------------------------------------------------------------------------------
+def warp_affine_blend(src, theta, dsize=None, mask_src=None, bg=None, mode="bilinear", want_mask=False):
+    """src [N,C,H,W] f32/bf16, theta [N,2,3] (or [2,3]) f32 normalised (param2theta), dsize (width, height).
+    With mask_src [N,H,W] u8 + bg [N,C,dH,dW]: out = warped_mask ? warped_src : bg (re_edit_2d blend)."""
+    if src.dtype not in _DT:
+        raise TypeError(f"src must be float32 or bfloat16, got {src.dtype}")
+    _chk(src, src.dtype, "src", 4)
+    N, Cc, H, W = src.shape
+    dW, dH = (W, H) if dsize is None else dsize
+    theta = theta.to(device=src.device, dtype=torch.float32)
+    if theta.dim() == 2:
+        theta = theta[None].expand(N, 2, 3)
+    theta = theta.contiguous()
+    if theta.shape != (N, 2, 3):
+        raise ValueError(f"theta must be [N,2,3], got {tuple(theta.shape)}")
+    if mask_src is not None:
+        _chk(mask_src, torch.uint8, "mask_src")
+        if mask_src.numel() != N * H * W:
+            raise ValueError("mask_src must be [N,H,W]")
+        if bg is None:
+            raise ValueError("mask_src needs a background")
+        _chk(bg, src.dtype, "bg", 4)
+        if bg.shape != (N, Cc, dH, dW):
+            raise ValueError("bg must be [N,C,dH,dW]")
+    out = torch.empty((N, Cc, dH, dW), dtype=src.dtype, device=src.device)
+    mask_out = torch.empty((N, dH, dW), dtype=torch.uint8, device=src.device) if (want_mask and mask_src is not None) else None
+    rc = _lib.load().ff_warp_affine_blend(_ptr(src), _ptr(theta), _ptr(mask_src), _ptr(bg), _ptr(out), _ptr(mask_out),
+                                          N, Cc, H, W, dH, dW, 0 if mode == "bilinear" else 1, _DT[src.dtype],
+                                          _stream())
+    _lib.check(rc, "ff_warp_affine_blend")
+    return (out, mask_out) if want_mask else out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# masks
+# ---------------------------------------------------------------------------------------------------------------
+def mask_words(S: int) -> int:
+    return (S + 31) // 32
+
+
+def mask_downsample_pack(masks, h, w, bits=None, popcount=None):
+    """masks u8 [n,H,W] -> (bits u32-as-int32 [n, words], popcount int32 [n]) at the h x w token grid
+    (process_mask_before_attention, attention.py:841-855)."""
+    _chk(masks, torch.uint8, "masks", 3)
+    n, H, W = masks.shape
+    words = mask_words(h * w)
+    if bits is None:
+        bits = torch.empty((n, words), dtype=torch.int32, device=masks.device)
+    if popcount is None:
+        popcount = torch.empty((n,), dtype=torch.int32, device=masks.device)
+    rc = _lib.load().ff_mask_downsample_pack(_ptr(masks), n, H, W, h, w, _ptr(bits), bits.shape[1], _ptr(popcount),
+                                             _stream())
+    _lib.check(rc, "ff_mask_downsample_pack")
+    return bits, popcount
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# (a) attention
+# ---------------------------------------------------------------------------------------------------------------
+def attn_masked_kv(q, k, v, plan, heads, scale, bitmasks=None, popcount=None, out_dtype=None, out=None):
+    """q [B,Sq,C], k/v [Bk,Skv,C] bf16; plan: uint8 CUDA tensor holding FFAttnHeadPlan[B*heads] (plans.to_device);
+    bitmasks int32 [n_masks, words], popcount int32 [n_masks].  Returns [B,Sq,C] in out_dtype (default bf16)."""
+    _chk(q, torch.bfloat16, "q", 3)
+    _chk(k, torch.bfloat16, "k", 3)
+    _chk(v, torch.bfloat16, "v", 3)
+    B, Sq, Cc = q.shape
+    Bk, Skv, Ck = k.shape
+    if v.shape != k.shape or Ck != Cc or Cc % heads:
+        raise ValueError(f"bad shapes q{tuple(q.shape)} k{tuple(k.shape)} v{tuple(v.shape)} heads={heads}")
+    _chk(plan, torch.uint8, "plan")
+    if plan.numel() != B * heads * _lib.PLAN_BYTES:
+        raise ValueError(f"plan holds {plan.numel()} bytes, expected {B * heads * _lib.PLAN_BYTES}")
+    out_dtype = torch.bfloat16 if out_dtype is None else out_dtype
+    if out is None:
+        out = torch.empty((B, Sq, Cc), dtype=out_dtype, device=q.device)
+    else:
+        _chk(out, out_dtype, "out", 3)
+    a = _lib.FFAttnArgs()
+    a.q, a.k, a.v, a.out, a.plan = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), plan.data_ptr()
+    if bitmasks is not None:
+        _chk(bitmasks, torch.int32, "bitmasks", 2)
+        _chk(popcount, torch.int32, "popcount", 1)
+        a.bitmasks, a.mask_popcount = bitmasks.data_ptr(), popcount.data_ptr()
+        a.n_masks, a.mask_words = bitmasks.shape[0], bitmasks.shape[1]
+    else:
+        a.bitmasks, a.mask_popcount, a.n_masks, a.mask_words = None, None, 0, 0
+    a.n_streams, a.n_kv_streams, a.heads, a.head_dim = B, Bk, heads, Cc // heads
+    a.s_q, a.s_kv = Sq, Skv
+    a.out_dtype = _DT[out_dtype]
+    a.scale = float(scale)
+    rc = _lib.load().ff_attn_masked_kv(C.byref(a), _stream())
+    _lib.check(rc, "ff_attn_masked_kv")
+    return out
+
+
+def cross_region_blend(hs, bitmasks, region_ids):
+    """hs [4E,S,C] (f32/bf16) in place: c_e <- region ? c_e : u_e, c_r <- u_r  (attention.py:1381-1383)."""
+    if hs.dtype not in _DT:
+        raise TypeError("hs must be float32 or bfloat16")
+    _chk(hs, hs.dtype, "hs", 3)
+    B, S, Cc = hs.shape
+    if B % 4:
+        raise ValueError("hs must hold 4 streams per edit")
+    _chk(bitmasks, torch.int32, "bitmasks", 2)
+    _chk(region_ids, torch.int32, "region_ids", 1)
+    rc = _lib.load().ff_cross_region_blend(_ptr(hs), _ptr(bitmasks), bitmasks.shape[1], _ptr(region_ids), B // 4, S, Cc,
+                                           _DT[hs.dtype], _stream())
+    _lib.check(rc, "ff_cross_region_blend")
+    return hs
+
+
+def to_device_bytes(arr: np.ndarray, device) -> torch.Tensor:
+    """numpy structured array -> uint8 CUDA tensor (pinned staging, asynchronous copy on the current stream)."""
+    t = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1))
+    if torch.cuda.is_available():
+        t = t.pin_memory()
+    return t.to(device, non_blocking=True)

@@ -1,0 +1,159 @@
+/* freefine_b200.h -- C ABI of libfreefine_b200.so (hand-written sm_100a CUDA; no torch types, no CPU fallback).
+ *
+ * Drop-in boundary for the denoising hot path of CIawevy/FreeFine.  The reference has no
+ * FFI -- its hot path is eager PyTorch -- so each entry point names the reference Python function(s) whose
+ * arithmetic it replaces (file:line relative to the upstream repo root).  INTEGRATION.md shows the ctypes binding
+ * a maintainer adds inside those functions.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name starts with h_ (host);
+ *   - the caller owns all buffers; the library allocates nothing on the device and never synchronises;
+ *   - `stream` is a cudaStream_t passed as void* (e.g. torch.cuda.current_stream().cuda_stream): every call is
+ *     asynchronous on it and CUDA-graph capturable;
+ *   - return value 0 = success, negative = error (FF_E_*); the message is in ff_last_error() (thread-local);
+ *   - unsupported shapes / dtypes / misaligned pointers are errors, never a silent fallback.
+ */
+#ifndef FREEFINE_B200_H_
+#define FREEFINE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FF_VERSION 100 /* 0.1.0 */
+
+enum {
+  FF_OK = 0,
+  FF_E_INVALID = -1,     /* bad argument (null pointer, shape, alignment, enum)  */
+  FF_E_UNSUPPORTED = -2, /* legal request outside what the kernels implement     */
+  FF_E_CUDA = -3,        /* a CUDA runtime / driver call failed                  */
+  FF_E_ARCH = -4         /* device is not sm_100 (tcgen05 / TMEM / TMA required) */
+};
+
+enum { FF_DT_F32 = 0, FF_DT_BF16 = 1 };
+
+int ff_version(void);
+const char* ff_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (a) masked, KV-injected flash attention  --  tcgen05 / TMEM / TMA
+ *
+ * Replaces, per attention-layer call: Attention_Modulator.Temporal_contextal_attention (src/utils/attention.py:
+ * 1043-1091), _bg (:1284-1324), _compose (:1092-1140), style_align_share_attention (:1142-1192), the plain branch
+ * of ca_forward (:395-404), get_cross_hidden_state (:808-837), together with the mask builders they call
+ * (prepare_various_attention_mask :862-889, _compose :891-906, _for_bggen :907-925, prepare_sdsa_mask :940-951) --
+ * whose [B*heads,S,S] additive masks are never materialised: the kernel reads bit-vectors of S bits.
+ *
+ * q,k,v are the UN-SPLIT projections the controller receives, bf16, logical shape [streams, S, heads*d] with the
+ * channel index contiguous (a dense PyTorch [B,S,C] tensor).  Head h of a row is channels [h*d, (h+1)*d).
+ *
+ * Every (stream, head) gets a *plan*: out(q) = sum_p  weight_p * roww_p(q) * softmax_{k in allowed_p(q)}(q.k*scale) V
+ * where pass p reads K,V of stream kv_stream (and optionally, under the SAME softmax, of kv_stream2 -- the
+ * doubled [K_self;K_ref] context of the SSA/SDSA variants) and
+ *     kb(k)       = key_mask < 0 ? 1 : bit k of bitmask row key_mask
+ *     rb(q)       = row_mask < 0 ? 0 : bit q of bitmask row row_mask
+ *     allowed(q,k)= kb(k) ^ KEY_INVERT ^ (ROW_XOR & rb(q))
+ *     roww(q)     = ROW_WEIGHT ? rb(q) : 1
+ * A row whose allowed set is EMPTY attends uniformly to every key (reference quirk Q4: the additive fill is
+ * finfo.min, not -inf, attention.py:857); the kernel derives emptiness from mask_popcount, no host sync needed.
+ * The host-side controller (freefine_b200/attention.py) encodes quirk Q0 (head-parity mask tiling,
+ * attention.py:859,881) simply by which plan it gives to which (stream, head).
+ * ------------------------------------------------------------------------------------------------------------ */
+#define FF_MAX_PASS 4
+
+enum {
+  FF_PASS_KEY_INVERT = 1u,  /* allowed = NOT keybit                                               */
+  FF_PASS_ROW_XOR = 2u,     /* allowed ^= rowbit  (rows inside the region read the complement set) */
+  FF_PASS_ROW_WEIGHT = 4u,  /* multiply the pass output by rowbit (compose: sum_i tgt_i(q) * O_i)   */
+  FF_PASS_KEY2_INVERT = 8u  /* KEY_INVERT for the second segment                                  */
+};
+
+typedef struct FFAttnPass {
+  int32_t kv_stream;  /* stream whose K,V this pass reads                          */
+  int32_t key_mask;   /* bitmask row for the keys, -1 = every key                  */
+  int32_t row_mask;   /* bitmask row for the query rows, -1 = none                 */
+  uint32_t flags;     /* FF_PASS_*                                                 */
+  float weight;       /* e.g. context_guidance, 1-context_guidance                 */
+  int32_t kv_stream2; /* second KV segment under the same softmax, -1 = none       */
+  int32_t key_mask2;  /* key bitmask row of the second segment, -1 = every key     */
+  int32_t reserved;
+} FFAttnPass;
+
+typedef struct FFAttnHeadPlan {
+  int32_t n_pass; /* 1..FF_MAX_PASS */
+  int32_t reserved[3];
+  FFAttnPass pass[FF_MAX_PASS];
+} FFAttnHeadPlan;
+
+typedef struct FFAttnArgs {
+  const void* q;              /* bf16 [n_streams, s_q,  heads*head_dim]                                   */
+  const void* k;              /* bf16 [n_kv_streams, s_kv, heads*head_dim]                                */
+  const void* v;              /* bf16 [n_kv_streams, s_kv, heads*head_dim]                                */
+  void* out;                  /* out_dtype [n_streams, s_q, heads*head_dim]                               */
+  const FFAttnHeadPlan* plan; /* DEVICE array [n_streams*heads], index stream*heads+head                  */
+  const uint32_t* bitmasks;   /* DEVICE [n_masks, mask_words] bit i of word i/32 <=> token i; may be NULL */
+  const int32_t* mask_popcount; /* DEVICE [n_masks] number of set bits among the first s_kv tokens          */
+  int32_t n_streams, n_kv_streams, heads, head_dim; /* head_dim % 8 == 0, <= 160                          */
+  int32_t s_q, s_kv;
+  int32_t n_masks, mask_words;                      /* mask_words >= ceil(max(s_q,s_kv)/32)               */
+  int32_t out_dtype;                                /* FF_DT_BF16 or FF_DT_F32                            */
+  float scale;                                      /* softmax scale (head_dim^-0.5)                      */
+} FFAttnArgs;
+
+int ff_attn_masked_kv(const FFAttnArgs* h_args, void* stream);
+
+/* Nearest-neighbour down-sample of n full-resolution uint8 masks [n,H,W] to [h,w] and bit-packing.
+ * Replaces process_mask_before_attention (attention.py:841-855) + the flatten that follows: index
+ * floor(i*H/h) in fp32 as ATen's `nearest`; if a mask's max is > 1 the reference rescales it by its max and
+ * truncates back to uint8, so only pixels EQUAL to the max survive (kept).  bit = pixel != 0 afterwards.
+ * bits: [n, words] (words >= ceil(h*w/32), padding bits written 0); popcount: [n].                          */
+int ff_mask_downsample_pack(const uint8_t* masks, int32_t n, int32_t H, int32_t W, int32_t h, int32_t w,
+                            uint32_t* bits, int32_t words, int32_t* popcount, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (b) fused affine warp + resample + mask-guided blend
+ *
+ * Replaces wrapAffine_tensor (src/utils/geo_utils.py:304-341: F.affine_grid + F.grid_sample, padding 'zeros',
+ * align_corners=False) for the image (bilinear) and the mask (nearest), and the np.where blend of re_edit_2d
+ * (src/utils/vis_utils.py:252-256,272):   out = warped_mask != 0 ? warped_src : bg.
+ * src [N,C,H,W], bg/out [N,C,dH,dW] (dtype f32 or bf16), theta [N,2,3] f32 in normalised coordinates (the output
+ * of param2theta, geo_utils.py:292-302), mask_src [N,H,W] u8 or NULL (then out = warped_src, `bg` ignored),
+ * mask_out [N,dH,dW] u8 (0/1) or NULL.  mode: 0 bilinear, 1 nearest (for src).                                  */
+int ff_warp_affine_blend(const void* src, const float* theta, const uint8_t* mask_src, const void* bg, void* out,
+                         uint8_t* mask_out, int32_t N, int32_t C, int32_t H, int32_t W, int32_t dH, int32_t dW,
+                         int32_t mode, int32_t dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (c) fused classifier-free guidance + DDIM / local-DDPM step
+ *
+ * ff_ddim_cfg_step replaces model.py:605-611 (local CFG) + ctrl_step (model.py:134-198) for n_edits edits whose
+ * UNet output is laid out [n_edits, 4, C, h, w] = [u_e, u_r, c_e, c_r] per edit (model.py:594) and whose latents
+ * are [n_edits, 2, C, h, w] = [edit, ref].  fp32, reference operation order, no FMA contraction (bit-exact with
+ * the CPU oracle).  cfg_mask / var_mask: u8 [n_edits, h, w] with uint8 wrap-around arithmetic (quirk Q1);
+ * cfg_mask NULL = plain CFG (model.py:608).  noise: [n_edits,2,C,h,w] (the randn_tensor draw of model.py:186,
+ * consumed only when sigma != 0); pred_x0 may be NULL.  Scalars are computed by the host in fp32 exactly as the
+ * reference does from alphas_cumprod:
+ *   sqrt_1m_at = (1-a_t)**.5, sqrt_at = a_t**.5, sqrt_ap = a_prev**.5, c_ddim = (1-a_prev)**.5,
+ *   c_ddpm = (1-a_prev-sigma**2)**.5, sigma = eta*variance**.5  (edit stream; the ref stream uses sigma 0).       */
+int ff_ddim_cfg_step(const float* eps4, const float* x, const float* noise, const uint8_t* cfg_mask,
+                     const uint8_t* var_mask, float guidance_scale, float sqrt_1m_at, float sqrt_at, float sqrt_ap,
+                     float c_ddim, float c_ddpm, float sigma, float* x_prev, float* pred_x0, int32_t n_edits,
+                     int32_t C, int32_t h, int32_t w, void* stream);
+
+/* ff_ddim_inv_step replaces inv_step (model.py:109-132): x_next = sqrt_an*((x - sqrt_1m_at*eps)/sqrt_at) +
+ * c_next*eps over n elements; pred_x0 may be NULL.                                                               */
+int ff_ddim_inv_step(const float* eps, const float* x, float sqrt_1m_at, float sqrt_at, float sqrt_an, float c_next,
+                     float* x_next, float* pred_x0, int64_t n, void* stream);
+
+/* Local cross-attention blend (modulate_local_cross_attn, attention.py:1381-1383, after the 77-key attention):
+ * hs [n_edits,4,S,C] (f32 or bf16) in place -> [u_e, u_r, region*c_e + (1-region)*u_e, u_r]; region: bit-vector
+ * row `region_mask` of `bitmasks` per edit ([n_edits] indices).                                                  */
+int ff_cross_region_blend(void* hs, const uint32_t* bitmasks, int32_t mask_words, const int32_t* region_mask,
+                          int32_t n_edits, int32_t S, int32_t C, int32_t dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FREEFINE_B200_H_ */

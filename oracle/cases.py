@@ -20,14 +20,16 @@ def blob_mask(res: int, seed: int, frac=(0.15, 0.3), dtype=np.uint8) -> np.ndarr
 
 
 def qkv(streams: int, S: int, C: int, seed: int, sk: int | None = None, logit_scale: float = 3.0, kstreams=None):
-    """q,k,v [B,S,C] fp32 with |logit| of a few units (random-init nets give near-uniform softmax: too easy)."""
+    """q,k,v [B,S,C] fp32 with |logit| of a few units (random-init nets give near-uniform softmax: too easy).
+    Values are rounded to the bf16 grid (still stored as fp32) so that the SAME numbers can be fed to the fp32
+    reference / oracle and, exactly, to the bf16 tensor-core kernel."""
     g = torch.Generator().manual_seed(seed)
     sk = S if sk is None else sk
     kstreams = streams if kstreams is None else kstreams
     q = torch.randn(streams, S, C, generator=g) * logit_scale
     k = torch.randn(kstreams, sk, C, generator=g)
     v = torch.randn(kstreams, sk, C, generator=g)
-    return q, k, v
+    return tuple(t.bfloat16().float() for t in (q, k, v))
 
 
 # name -> dict(kind=..., params)
@@ -42,6 +44,11 @@ ATTN_CASES = {
     "bg_tca_h8_s256":     dict(kind="bg",   method="tca",  heads=8, d=8,  res=128, S=256, cg=0.7, src="blob", seed=17),
     "bg_mmsa_h8_s64":     dict(kind="bg",   method="mmsa", heads=8, d=8,  res=64,  S=64,  cg=None, src="blob", seed=18),
     "tca_h8_s256_res256": dict(kind="edit", method="tca", heads=8, d=8,  res=256, S=256, cg=0.4, src="blob", seed=19),
+    # SD1.5 head dims (40: up3/down0, 80: up2/down1, 160: up1/mid) at small token counts
+    "tca_h8_s256_d40":    dict(kind="edit", method="tca",  heads=8, d=40,  res=128, S=256, cg=0.7, src="blob", seed=20),
+    "tca_h8_s64_d80":     dict(kind="edit", method="tca",  heads=8, d=80,  res=64,  S=64,  cg=0.35, src="blob", seed=21),
+    "mmsa_h8_s64_d160":   dict(kind="edit", method="mmsa", heads=8, d=160, res=64,  S=64,  cg=None, src="blob", seed=22),
+    "bg_tca_h8_s64_d160": dict(kind="bg",   method="tca",  heads=8, d=160, res=64,  S=64,  cg=0.5, src="blob", seed=23),
 }
 
 

@@ -1,0 +1,463 @@
+"""Host-side mirror of FreeFine's attention plugin (reference src/utils/attention.py), backed by the sm_100a kernels.
+
+Same call surface as the reference so drivers / notebooks keep working unchanged:
+
+    controller = Attention_Modulator(start_layer=10);  model.controller = controller
+    register_attention_control(model, controller)          # also: _4bggen, _compose
+    model.modify_unet_forward()
+
+* `register_attention_control*` (reference :342-452, :226-339, :454-564) replaces `.forward` of every module whose
+  class is named ``Attention`` under the UNet children named down*/mid*/up*, counts them into
+  `controller.num_att_layers`, and dispatches each call exactly like the reference's `ca_forward`.
+* `Attention_Modulator` (reference :640-1442) keeps the reference's public fields (`use_tca`, `method`, `layer_idx`,
+  `context_guidance`, `fg_retain_mask`, `fg_ref_mask`, `local_edit_region`, `src_masks`, `tgt_masks`, counters ...)
+  and methods with the signature `(query, key, value, is_cross, place_in_unet)` on UN-SPLIT `[B,S,C]` tensors.
+
+What differs is only the arithmetic engine: no `[B*heads,S,S]` mask or score tensor is ever built.  Masks become
+bit-vectors (ff_mask_downsample_pack, cached per token-grid resolution until the masks change), the mask-stack /
+head-parity semantics become a per-(stream, head) plan (freefine_b200/plans.py) and ONE launch of
+ff_attn_masked_kv produces the layer output.  Every attention of the UNet -- TCA layers, the plain layers, the
+77-key cross attention -- goes through that kernel.  Extension over the reference: the stream batch may hold E
+edits (`[4E,S,C]`, masks `[E,H,W]`); the reference hard-unpacks exactly 4 streams (:1034,:1381).
+
+There is no PyTorch fallback: CPU tensors or a missing libfreefine_b200.so raise.
+"""
+from __future__ import annotations
+
+import abc
+import math
+
+import torch
+
+from . import ops, plans
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# controller base classes (reference :565-599)
+# ---------------------------------------------------------------------------------------------------------------
+class AttentionControl(abc.ABC):
+    def step_callback(self, x_t):
+        return x_t
+
+    def between_steps(self):
+        return
+
+    @property
+    def num_uncond_att_layers(self):
+        return self.num_att_layers if self.LOW_RESOURCE else 0
+
+    @abc.abstractmethod
+    def forward(self, attn, is_cross: bool, place_in_unet: str):
+        raise NotImplementedError
+
+    def _advance(self):
+        """One attention layer done (the counter block every reference branch repeats, e.g. :1086-1090)."""
+        self.cur_att_layer += 1
+        if self.cur_att_layer == self.num_att_layers + self.num_uncond_att_layers:
+            self.cur_att_layer = 0
+            self.cur_step += 1
+            self.between_steps()
+
+    def __call__(self, attn, is_cross: bool, place_in_unet: str):
+        self._advance()
+        return attn
+
+    def reset(self):
+        self.cur_step = 0
+        self.cur_att_layer = 0
+
+    def __init__(self):
+        self.cur_step = 0
+        self.num_att_layers = -1
+        self.cur_att_layer = 0
+        self.LOW_RESOURCE = False
+
+
+def _as_u8_stack(mask: torch.Tensor) -> torch.Tensor:
+    """[H,W] or [E,H,W] mask of any dtype -> contiguous uint8 [E,H,W] on its device (no sync)."""
+    m = mask if mask.dim() == 3 else mask[None]
+    if m.dtype != torch.uint8:
+        m = m.clamp(0, 255).to(torch.uint8)
+    return m.contiguous()
+
+
+class Attention_Modulator(AttentionControl):
+    """State carrier + attention methods of the editing pipeline (reference :640-1442)."""
+
+    def __init__(self, start_layer=None):
+        super().__init__()
+        self.step_num = 0
+        self.model_type = 'Inverse'
+        self.use_cfg = False
+        self.use_style_align = False
+        self.use_tca = False
+        self.local_edit = False
+        self.fg_retain_mask = None        # rows that read source-object keys (target + completion region)
+        self.fg_retain_mask_st2 = None    # target only; computed by the reference but unused downstream (Q9)
+        self.fg_ref_mask = None           # source object in the ref image (key columns)
+        self.obj_mask = None
+        self.local_edit_region = None     # cross-attention prompt region
+        self.layer_idx = list(range(start_layer, 16)) if start_layer is not None else list(range(16))
+        self.down_sampling_shape = dict()
+        self.method = None
+        self.context_guidance = None
+        self.tca_scope = ['up']
+        self.style_align_scope = ['down', 'mid', 'up']
+        self.src_masks = None
+        self.tgt_masks = None
+        self.prompt_length = 1
+        self.heads = None
+        self.scale = None
+        self.upcast_attention = False
+        self.upcast_softmax = False
+        self.log_mask = False
+        self._tables = {}                 # (kind, S) -> (signature, bits, popcount)
+        self._plans = {}                  # key -> device plan bytes
+
+    # ---- bookkeeping ------------------------------------------------------------------------------------------
+    def forward(self, attn, is_cross: bool, place_in_unet: str):
+        return attn
+
+    def reset(self):
+        """reference :737-754"""
+        super().reset()
+        self.step_num = 0
+        self.model_type = 'Inverse'
+        self.use_cfg = False
+        self.use_tca = False
+        self.use_style_align = False
+        self.local_edit = False
+        self.down_sampling_shape = dict()
+        self.style_align = False
+        self.method = None
+        self.context_guidance = None
+        self.tca_scope = ['up']
+        self.style_align_scope = ['down', 'mid', 'up']
+        self._tables.clear()
+        self._plans.clear()
+
+    def get_down_h_w(self, d_ratio, h, w, seq):
+        """reference :713-733 (ceil-halving from h//8, cached per d_ratio until reset(): quirk Q10)."""
+        if d_ratio in self.down_sampling_shape:
+            nh, nw = self.down_sampling_shape[d_ratio]
+            assert nh * nw == seq, f'{nh} * {nw} != {seq}'
+            return nh, nw
+        r = d_ratio // 8
+        nh, nw = h // 8, w // 8
+        while r != 1:
+            r //= 2
+            nh, nw = (nh + 1) // 2, (nw + 1) // 2
+        assert nw * nh == seq
+        self.down_sampling_shape[d_ratio] = [nh, nw]
+        return nh, nw
+
+    def _grid(self, H, W, seq):
+        d_ratio = 2 ** int(math.log2((H * W // seq) ** 0.5) + 0.5)          # reference :848
+        return self.get_down_h_w(d_ratio, H, W, seq)
+
+    # ---- masks -> bit-vector tables ------------------------------------------------------------------------------
+    def _table(self, kind: str, seq: int, masks):
+        """Bit-vector table of `masks` (list of [H,W]/[E,H,W] tensors, stacked edit-major) at `seq` tokens.
+        Cached until any mask tensor is replaced or modified in place."""
+        sig = tuple((m.data_ptr(), m._version, tuple(m.shape)) for m in masks)
+        hit = self._tables.get((kind, seq))
+        if hit is not None and hit[0] == sig:
+            return hit[1], hit[2]
+        stacks = [_as_u8_stack(m) for m in masks]
+        E, H, W = stacks[0].shape
+        for s in stacks:
+            if s.shape != (E, H, W):
+                raise ValueError(f"mask shapes differ: {[tuple(x.shape) for x in stacks]}")
+            if not s.is_cuda:
+                raise RuntimeError("controller masks must live on the CUDA device (no CPU path)")
+        h, w = self._grid(H, W, seq)
+        # row id = e*len(masks) + j
+        stacked = torch.stack(stacks, dim=1).reshape(E * len(stacks), H, W)
+        bits, pop = ops.mask_downsample_pack(stacked, h, w)
+        self._tables[(kind, seq)] = (sig, bits, pop)
+        return bits, pop
+
+    def _plan(self, key, builder):
+        p = self._plans.get(key)
+        if p is None:
+            if len(self._plans) > 256:
+                self._plans.clear()
+            p = ops.to_device_bytes(builder(), self._device)
+            self._plans[key] = p
+        return p
+
+    def _attend(self, query, key, value, plan, bits=None, pop=None):
+        self._device = query.device
+        dt = query.dtype
+        if dt not in (torch.float32, torch.bfloat16):
+            query, key, value, dt = query.float(), key.float(), value.float(), torch.float32
+        q = query.to(torch.bfloat16).contiguous()
+        k = key.to(torch.bfloat16).contiguous()
+        v = value.to(torch.bfloat16).contiguous()
+        return ops.attn_masked_kv(q, k, v, plan, self.heads, self.scale, bits, pop, out_dtype=dt)
+
+    def plain_attention(self, query, key, value):
+        """Unmasked attention, every stream over its own K,V (the reference's else-branch :395-404; also the
+        77-key cross attention get_cross_hidden_state :808-837)."""
+        self._device = query.device
+        B = query.shape[0]
+        if key.shape[0] != B:
+            raise ValueError("plain attention needs one K/V stream per query stream")
+        plan = self._plan(("plain", B, self.heads), lambda: plans.plain_plan(B, self.heads))
+        return self._attend(query, key, value, plan)
+
+    # ---- self-attention variants ----------------------------------------------------------------------------------
+    def _tca_common(self, query, key, value, kind):
+        B, S, _ = query.shape
+        if self.cur_att_layer // 2 not in self.layer_idx:                     # reference :1051-1058
+            out = self.plain_attention(query, key, value)
+            self._advance()
+            return out
+        if B % 4:
+            raise ValueError(f"TCA expects 4 streams [u_e,u_r,c_e,c_r] per edit, got batch {B}")
+        if self.method not in ('tca', 'mmsa'):
+            raise ValueError(f"controller.method must be 'tca' or 'mmsa' here, got {self.method!r}")
+        E = B // 4
+        self._device = query.device
+        if kind == "edit":
+            bits, pop = self._table("edit", S, [self.fg_ref_mask, self.fg_retain_mask])
+            src_id, tgt_id = (lambda e: 2 * e), (lambda e: 2 * e + 1)
+        else:
+            bits, pop = self._table("bg", S, [self.fg_retain_mask])
+            src_id, tgt_id = (lambda e: e), (lambda e: e)
+        if bits.shape[0] not in (2 * E if kind == "edit" else E,):
+            raise ValueError(f"{E} edits in the stream batch but masks for {bits.shape[0]} rows")
+        cg = None if self.method == 'mmsa' else float(self.context_guidance)
+        plan = self._plan((kind, E, self.heads, self.method, cg),
+                          lambda: plans.tca_plan(E, self.heads, self.method, cg, src_id, tgt_id, kind=kind))
+        out = self._attend(query, key, value, plan, bits, pop)
+        self._advance()
+        return out
+
+    def Temporal_contextal_attention(self, query, key, value, is_cross, place_in_unet):
+        """reference :1043-1091 (mask semantics incl. quirk Q0: plans.tca_plan)."""
+        return self._tca_common(query, key, value, "edit")
+
+    def Temporal_contextal_attention_bg(self, query, key, value, is_cross, place_in_unet):
+        """reference :1284-1324 (keys outside the object mask for every row)."""
+        return self._tca_common(query, key, value, "bg")
+
+    def Temporal_contextal_attention_compose(self, query, key, value, is_cross, place_in_unet):
+        """reference :1092-1140: streams [u_e, r_1..r_N, c_e]."""
+        B, S, _ = query.shape
+        if self.cur_att_layer // 2 not in self.layer_idx:
+            out = self.plain_attention(query, key, value)
+            self._advance()
+            return out
+        N = B - 2
+        self._device = query.device
+        src = self.src_masks[:N] if torch.is_tensor(self.src_masks) else torch.stack(list(self.src_masks)[:N])
+        tgt = self.tgt_masks[:N] if torch.is_tensor(self.tgt_masks) else torch.stack(list(self.tgt_masks)[:N])
+        # one "edit" whose table rows are [src_0..src_{N-1}, tgt_0..tgt_{N-1}]
+        bits, pop = self._table("compose", S, [m for m in src] + [m for m in tgt])
+        cg = None if self.method == 'mmsa' else float(self.context_guidance)
+        plan = self._plan(("compose", N, self.heads, self.method, cg),
+                          lambda: plans.compose_plan(N, self.heads, self.method, cg, list(range(N)),
+                                                     list(range(N, 2 * N))))
+        out = self._attend(query, key, value, plan, bits, pop)
+        self._advance()
+        return out
+
+    def _style_align(self, query, key, value, mask):
+        B, S, _ = query.shape
+        if B % 4:
+            raise ValueError("style-align expects 4 streams per edit")
+        E = B // 4
+        self._device = query.device
+        bits = pop = None
+        src_id = None
+        if self.method == 'sdsa':
+            bits, pop = self._table("sdsa", S, [mask])
+            src_id = lambda e: e
+        plan = self._plan(("style", E, self.heads, self.method),
+                          lambda: plans.style_align_plan(E, self.heads, src_id))
+        out = self._attend(query, key, value, plan, bits, pop)
+        self._advance()
+        return out
+
+    def style_align_share_attention(self, query, key, value, is_cross, place_in_unet):
+        """reference :1142-1192 (SSA / SDSA ablations): keys/values [self ; ref] under one softmax."""
+        return self._style_align(query, key, value, self.fg_ref_mask)
+
+    def style_align_share_attention_bg(self, query, key, value, is_cross, place_in_unet):
+        """reference :1193-1238; SDSA masks the ref half by the object mask (prepare_sdsa_mask_for_bggen :926-939)."""
+        return self._style_align(query, key, value, self.fg_retain_mask)
+
+    # ---- cross-attention variants -----------------------------------------------------------------------------------
+    def modulate_local_cross_attn(self, query, key, value, is_cross, place_in_unet):
+        """reference :1360-1393: 77-key attention, then c_e <- region ? c_e : u_e and c_r <- u_r."""
+        B, S, _ = query.shape
+        if B % 4:
+            raise ValueError("local cross-attention modulation expects 4 streams per edit")
+        hs = self.plain_attention(query, key, value)
+        bits, _ = self._table("region", S, [self.local_edit_region])
+        ids = self._plans.get(("region_ids", B // 4))
+        if ids is None:
+            ids = torch.arange(B // 4, dtype=torch.int32, device=query.device)
+            self._plans[("region_ids", B // 4)] = ids
+        ops.cross_region_blend(hs, bits, ids)
+        self._advance()
+        return hs
+
+    modulate_local_cross_attn_bg = modulate_local_cross_attn          # reference :1326-1357 is identical
+
+    def modulate_local_cross_attn_compose(self, query, key, value, is_cross, place_in_unet):
+        """reference :1394-1432: q streams [u_e, r_1..r_N, c_e]; k/v carry N+1 unconditional prompts followed by
+        `prompt_length` regional prompts; c_e = sum_i tgt_i(q) * Attn(q_c, prompt_i)."""
+        Bq, S, _ = query.shape
+        self._device = query.device
+        L = len(self.tgt_masks)
+        nu = Bq - 1
+        if key.shape[0] != nu + L:
+            raise ValueError(f"expected {nu + L} prompt streams, got {key.shape[0]}")
+        tg = self.tgt_masks if torch.is_tensor(self.tgt_masks) else torch.stack(list(self.tgt_masks))
+        bits, pop = self._table("cross_compose", S, [m for m in tg])
+
+        def build():
+            p = plans._empty(Bq, self.heads)
+            for s in range(nu):
+                for h in range(self.heads):
+                    plans._add(p, s, h, s, 1.0)
+            for h in range(self.heads):
+                for i in range(L):
+                    plans._add(p, nu, h, nu + i, 1.0, row_mask=i, flags=plans.FF_PASS_ROW_WEIGHT)
+            return p
+
+        plan = self._plan(("cross_compose", Bq, L, self.heads), build)
+        out = self._attend(query, key, value, plan, bits, pop)
+        self._advance()
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# UNet forward + registration
+# ---------------------------------------------------------------------------------------------------------------
+def override_forward(unet):
+    """reference :11-225 re-states diffusers' UNet2DConditionModel.forward so that it returns the raw tensor.  The
+    UNet body (convs / norms / feed-forwards) is library code on both sides; here the module's own forward is used and
+    only the return convention is normalised (`.sample` of an output object, or the tensor itself)."""
+    inner = unet.forward
+
+    def forward(sample, timestep, encoder_hidden_states, *args, **kwargs):
+        out = inner(sample, timestep, encoder_hidden_states, *args, **kwargs)
+        if torch.is_tensor(out):
+            return out
+        return out.sample if hasattr(out, "sample") else out[0]
+
+    return forward
+
+
+class _DummyController:
+    num_att_layers = 0
+    use_tca = use_style_align = local_edit = False
+
+    def __call__(self, *args):
+        return args[0]
+
+
+def _register(model, controller, flavour: str):
+    if controller is None:
+        controller = _DummyController()
+    plain = Attention_Modulator()      # engine for the undecorated branch when the controller is a dummy
+
+    def ca_forward(self, place_in_unet):
+        to_out = self.to_out[0] if isinstance(self.to_out, torch.nn.ModuleList) else self.to_out
+
+        def forward(hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None):
+            is_cross = encoder_hidden_states is not None
+            residual = hidden_states
+            if self.spatial_norm is not None:
+                hidden_states = self.spatial_norm(hidden_states, temb)
+            input_ndim = hidden_states.ndim
+            if input_ndim == 4:
+                batch_size, channel, height, width = hidden_states.shape
+                hidden_states = hidden_states.view(batch_size, channel, height * width).transpose(1, 2)
+            if attention_mask is not None:
+                raise NotImplementedError("explicit attention_mask is not part of the FreeFine hot path")
+            if self.group_norm is not None:
+                hidden_states = self.group_norm(hidden_states.transpose(1, 2)).transpose(1, 2)
+            query = self.to_q(hidden_states)
+            if encoder_hidden_states is None:
+                encoder_hidden_states = hidden_states
+            elif self.norm_cross:
+                encoder_hidden_states = self.norm_encoder_hidden_states(encoder_hidden_states)
+            key = self.to_k(encoder_hidden_states)
+            value = self.to_v(encoder_hidden_states)
+
+            c = controller if isinstance(controller, Attention_Modulator) else plain
+            c.heads, c.scale = self.heads, self.scale
+            c.upcast_attention, c.upcast_softmax = self.upcast_attention, self.upcast_softmax
+            if flavour == "edit":                                            # reference :388-404
+                if not is_cross and controller.use_style_align and place_in_unet in controller.style_align_scope:
+                    hidden_states = controller.style_align_share_attention(query, key, value, is_cross, place_in_unet)
+                elif not is_cross and controller.use_tca and place_in_unet in controller.tca_scope:
+                    hidden_states = controller.Temporal_contextal_attention(query, key, value, is_cross, place_in_unet)
+                elif controller.local_edit and is_cross:
+                    hidden_states = controller.modulate_local_cross_attn(query, key, value, is_cross, place_in_unet)
+                else:
+                    hidden_states = c.plain_attention(query, key, value)
+                    controller(None, is_cross, place_in_unet)
+            elif flavour == "bggen":                                         # reference :273-291
+                if place_in_unet in ['up'] and not is_cross and controller.use_tca:
+                    hidden_states = controller.Temporal_contextal_attention_bg(query, key, value, is_cross, place_in_unet)
+                elif controller.local_edit and is_cross:
+                    hidden_states = controller.modulate_local_cross_attn_bg(query, key, value, is_cross, place_in_unet)
+                else:
+                    hidden_states = c.plain_attention(query, key, value)
+                    controller(None, is_cross, place_in_unet)
+            else:                                                            # compose, reference :502-516
+                if not is_cross and controller.use_tca and place_in_unet in controller.tca_scope:
+                    hidden_states = controller.Temporal_contextal_attention_compose(query, key, value, is_cross, place_in_unet)
+                elif controller.local_edit and is_cross:
+                    hidden_states = controller.modulate_local_cross_attn_compose(query, key, value, is_cross, place_in_unet)
+                else:
+                    hidden_states = c.plain_attention(query, key, value)
+                    controller(None, is_cross, place_in_unet)
+
+            hidden_states = to_out(hidden_states)
+            if input_ndim == 4:
+                hidden_states = hidden_states.transpose(-1, -2).reshape(batch_size, channel, height, width)
+            if self.residual_connection:
+                hidden_states = hidden_states + residual
+            return hidden_states / self.rescale_output_factor
+
+        return forward
+
+    def register_recr(net_, count, place_in_unet):
+        if net_.__class__.__name__ == 'Attention':
+            net_.forward = ca_forward(net_, place_in_unet)
+            return count + 1
+        if hasattr(net_, 'children'):
+            for child in net_.children():
+                count = register_recr(child, count, place_in_unet)
+        return count
+
+    n = 0
+    for name, net in model.unet.named_children():
+        if "down" in name:
+            n += register_recr(net, 0, "down")
+        elif "up" in name:
+            n += register_recr(net, 0, "up")
+        elif "mid" in name:
+            n += register_recr(net, 0, "mid")
+    controller.num_att_layers = n
+
+
+def register_attention_control(model, controller):
+    """Drop-in for reference src/utils/attention.py:342-452."""
+    _register(model, controller, "edit")
+
+
+def register_attention_control_4bggen(model, controller):
+    """Drop-in for reference :226-339 (background generation / object removal)."""
+    _register(model, controller, "bggen")
+
+
+def register_attention_control_compose(model, controller):
+    """Drop-in for reference :454-564 (cross-image composition / appearance transfer)."""
+    _register(model, controller, "compose")

@@ -13,13 +13,17 @@ struct StepCoef {
 };
 
 // one element of ctrl_step; m is the uint8 variance mask of this stream (ref stream: 1), sd its sigma
-__device__ __forceinline__ void step_elem(float eu, float ec, float x, float nz, bool has_cfg_mask, uint8_t cfgm,
+__device__ __forceinline__ void step_elem(float eu, float ec, float x, float nz, bool do_cfg, bool has_cfg_mask,
+                                          uint8_t cfgm,
                                           uint8_t m, float sd, float cd, bool has_noise, const StepCoef& k,
                                           float& x_prev, float& x0) {
   // eps = eps_u + gs*(eps_c-eps_u)*cfg_mask                                   (model.py:608 / :610-611)
-  float g = __fmul_rn(k.gs, __fsub_rn(ec, eu));
-  if (has_cfg_mask) g = __fmul_rn(g, (float)cfgm);
-  const float eps = __fadd_rn(eu, g);
+  float eps = eu;
+  if (do_cfg) {
+    float g = __fmul_rn(k.gs, __fsub_rn(ec, eu));
+    if (has_cfg_mask) g = __fmul_rn(g, (float)cfgm);
+    eps = __fadd_rn(eu, g);
+  }
   // pred_x0 = (x - (1-a_t)**.5 * eps) / a_t**.5                               (model.py:162-163)
   x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(k.sqrt_1m_at, eps)), k.sqrt_at);
   const uint8_t om = (uint8_t)(1 - m);  // uint8 wrap-around: 1-2 = 255 (quirk Q1, model.py:179-180)
@@ -34,7 +38,8 @@ template <int V>  // V = 4 (float4 path, hw % 4 == 0) or 1
 __global__ void __launch_bounds__(256)
 ddim_cfg_step_kernel(const float* __restrict__ eps4, const float* __restrict__ x, const float* __restrict__ noise,
                      const uint8_t* __restrict__ cfg_mask, const uint8_t* __restrict__ var_mask, StepCoef k,
-                     float* __restrict__ x_prev, float* __restrict__ pred_x0, int n_edits, int C, int hw) {
+                     float* __restrict__ x_prev, float* __restrict__ pred_x0, int n_edits, int C, int hw, int spe) {
+  // spe = streams per edit in eps4: 4 -> [u_e,u_r,c_e,c_r] (CFG fused here), 2 -> eps already combined [edit, ref]
   const int hwv = hw / V;
   const long long total = (long long)n_edits * 2 * C * hwv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -45,8 +50,8 @@ ddim_cfg_step_kernel(const float* __restrict__ eps4, const float* __restrict__ x
     r /= C;
     const int s = (int)(r & 1);
     const int e = (int)(r >> 1);
-    const long long off_u = (((long long)(e * 4 + s) * C + c) * hw) + (long long)p * V;
-    const long long off_c = (((long long)(e * 4 + 2 + s) * C + c) * hw) + (long long)p * V;
+    const long long off_u = (((long long)(e * spe + s) * C + c) * hw) + (long long)p * V;
+    const long long off_c = spe == 4 ? (((long long)(e * 4 + 2 + s) * C + c) * hw) + (long long)p * V : off_u;
     const long long off_x = (((long long)(e * 2 + s) * C + c) * hw) + (long long)p * V;
     const long long off_m = (long long)e * hw + (long long)p * V;
     float eu[V], ec[V], xv[V], nz[V], xp[V], x0[V];
@@ -73,8 +78,8 @@ ddim_cfg_step_kernel(const float* __restrict__ eps4, const float* __restrict__ x
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       const uint8_t m = s == 0 ? vm[j] : (uint8_t)1;
-      step_elem(eu[j], ec[j], xv[j], noise ? nz[j] : 0.f, cfg_mask != nullptr, cfg_mask ? cm[j] : (uint8_t)1, m, sd,
-                cd, noise != nullptr, k, xp[j], x0[j]);
+      step_elem(eu[j], ec[j], xv[j], noise ? nz[j] : 0.f, spe == 4, cfg_mask != nullptr, cfg_mask ? cm[j] : (uint8_t)1,
+                m, sd, cd, noise != nullptr, k, xp[j], x0[j]);
     }
     if (V == 4) {
       *reinterpret_cast<float4*>(x_prev + off_x) = *reinterpret_cast<float4*>(xp);
@@ -127,29 +132,46 @@ inline int grid_for(long long work_items, int block) {
 
 }  // namespace
 
-extern "C" int ff_ddim_cfg_step(const float* eps4, const float* x, const float* noise, const uint8_t* cfg_mask,
-                                const uint8_t* var_mask, float guidance_scale, float sqrt_1m_at, float sqrt_at,
-                                float sqrt_ap, float c_ddim, float c_ddpm, float sigma, float* x_prev,
-                                float* pred_x0, int32_t n_edits, int32_t C, int32_t h, int32_t w, void* stream) {
-  FF_REQUIRE(eps4 && x && var_mask && x_prev, "ff_ddim_cfg_step: null pointer");
-  FF_REQUIRE(n_edits > 0 && C > 0 && h > 0 && w > 0, "ff_ddim_cfg_step: bad shape %d,%d,%d,%d", n_edits, C, h, w);
+static int launch_step(const char* what, const float* eps, int spe, const float* x, const float* noise,
+                       const uint8_t* cfg_mask, const uint8_t* var_mask, const StepCoef& k, float* x_prev,
+                       float* pred_x0, int32_t n_edits, int32_t C, int32_t h, int32_t w, void* stream) {
+  if (!(eps && x && var_mask && x_prev)) return ff::fail(FF_E_INVALID, "%s: null pointer", what);
+  if (!(n_edits > 0 && C > 0 && h > 0 && w > 0))
+    return ff::fail(FF_E_INVALID, "%s: bad shape %d,%d,%d,%d", what, n_edits, C, h, w);
   const int hw = h * w;
-  StepCoef k{guidance_scale, sqrt_1m_at, sqrt_at, sqrt_ap, c_ddim, c_ddpm, sigma};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool vec = (hw % 4 == 0) && ff::aligned16(eps4) && ff::aligned16(x) && ff::aligned16(x_prev) &&
+  const bool vec = (hw % 4 == 0) && ff::aligned16(eps) && ff::aligned16(x) && ff::aligned16(x_prev) &&
                    (!noise || ff::aligned16(noise)) && (!pred_x0 || ff::aligned16(pred_x0)) &&
                    (reinterpret_cast<uintptr_t>(var_mask) % 4 == 0) &&
                    (!cfg_mask || reinterpret_cast<uintptr_t>(cfg_mask) % 4 == 0);
   if (vec) {
     const long long items = (long long)n_edits * 2 * C * (hw / 4);
-    ddim_cfg_step_kernel<4><<<grid_for(items, 256), 256, 0, st>>>(eps4, x, noise, cfg_mask, var_mask, k, x_prev,
-                                                                   pred_x0, n_edits, C, hw);
+    ddim_cfg_step_kernel<4><<<grid_for(items, 256), 256, 0, st>>>(eps, x, noise, cfg_mask, var_mask, k, x_prev,
+                                                                   pred_x0, n_edits, C, hw, spe);
   } else {
     const long long items = (long long)n_edits * 2 * C * hw;
-    ddim_cfg_step_kernel<1><<<grid_for(items, 256), 256, 0, st>>>(eps4, x, noise, cfg_mask, var_mask, k, x_prev,
-                                                                   pred_x0, n_edits, C, hw);
+    ddim_cfg_step_kernel<1><<<grid_for(items, 256), 256, 0, st>>>(eps, x, noise, cfg_mask, var_mask, k, x_prev,
+                                                                   pred_x0, n_edits, C, hw, spe);
   }
-  return ff::check_launch("ff_ddim_cfg_step");
+  return ff::check_launch(what);
+}
+
+extern "C" int ff_ddim_cfg_step(const float* eps4, const float* x, const float* noise, const uint8_t* cfg_mask,
+                                const uint8_t* var_mask, float guidance_scale, float sqrt_1m_at, float sqrt_at,
+                                float sqrt_ap, float c_ddim, float c_ddpm, float sigma, float* x_prev,
+                                float* pred_x0, int32_t n_edits, int32_t C, int32_t h, int32_t w, void* stream) {
+  StepCoef k{guidance_scale, sqrt_1m_at, sqrt_at, sqrt_ap, c_ddim, c_ddpm, sigma};
+  return launch_step("ff_ddim_cfg_step", eps4, 4, x, noise, cfg_mask, var_mask, k, x_prev, pred_x0, n_edits, C, h, w,
+                     stream);
+}
+
+extern "C" int ff_ddim_step(const float* eps2, const float* x, const float* noise, const uint8_t* var_mask,
+                            float sqrt_1m_at, float sqrt_at, float sqrt_ap, float c_ddim, float c_ddpm, float sigma,
+                            float* x_prev, float* pred_x0, int32_t n_edits, int32_t C, int32_t h, int32_t w,
+                            void* stream) {
+  StepCoef k{0.f, sqrt_1m_at, sqrt_at, sqrt_ap, c_ddim, c_ddpm, sigma};
+  return launch_step("ff_ddim_step", eps2, 2, x, noise, nullptr, var_mask, k, x_prev, pred_x0, n_edits, C, h, w,
+                     stream);
 }
 
 extern "C" int ff_ddim_inv_step(const float* eps, const float* x, float sqrt_1m_at, float sqrt_at, float sqrt_an,

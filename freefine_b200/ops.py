@@ -69,6 +69,27 @@ def ddim_cfg_step(eps4, x, noise, cfg_mask, var_mask, guidance_scale, sqrt_1m_at
     return (x_prev, x0) if want_pred_x0 else x_prev
 
 
+def ddim_step(eps2, x, noise, var_mask, sqrt_1m_at, sqrt_at, sqrt_ap, c_ddim, c_ddpm, sigma, want_pred_x0=False):
+    """ctrl_step alone (model.py:134-198) on an already guidance-combined eps2 [E,2,C,h,w]."""
+    _chk(eps2, torch.float32, "eps2")
+    _chk(x, torch.float32, "x")
+    if eps2.shape != x.shape:
+        raise ValueError("eps2 and x must have the same shape")
+    Cc, h, w = x.shape[-3:]
+    n_edits = x.numel() // (2 * Cc * h * w)
+    _chk(var_mask, torch.uint8, "var_mask")
+    if var_mask.numel() != n_edits * h * w:
+        raise ValueError("var_mask must be [n_edits,h,w]")
+    if noise is not None:
+        _chk(noise, torch.float32, "noise")
+    x_prev = torch.empty_like(x)
+    x0 = torch.empty_like(x) if want_pred_x0 else None
+    rc = _lib.load().ff_ddim_step(_ptr(eps2), _ptr(x), _ptr(noise), _ptr(var_mask), sqrt_1m_at, sqrt_at, sqrt_ap,
+                                  c_ddim, c_ddpm, sigma, _ptr(x_prev), _ptr(x0), n_edits, Cc, h, w, _stream())
+    _lib.check(rc, "ff_ddim_step")
+    return (x_prev, x0) if want_pred_x0 else x_prev
+
+
 def ddim_inv_step(eps, x, sqrt_1m_at, sqrt_at, sqrt_an, c_next, want_pred_x0=False):
     """reference inv_step, model.py:109-132."""
     _chk(eps, torch.float32, "eps")

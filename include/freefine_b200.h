@@ -142,6 +142,12 @@ int ff_ddim_cfg_step(const float* eps4, const float* x, const float* noise, cons
                      float c_ddim, float c_ddpm, float sigma, float* x_prev, float* pred_x0, int32_t n_edits,
                      int32_t C, int32_t h, int32_t w, void* stream);
 
+/* ff_ddim_step = ctrl_step (model.py:134-198) alone, for callers that already combined the guidance: eps2
+ * [n_edits, 2, C, h, w] = [edit, ref].  Same arithmetic as above from pred_x0 on.                                 */
+int ff_ddim_step(const float* eps2, const float* x, const float* noise, const uint8_t* var_mask, float sqrt_1m_at,
+                 float sqrt_at, float sqrt_ap, float c_ddim, float c_ddpm, float sigma, float* x_prev,
+                 float* pred_x0, int32_t n_edits, int32_t C, int32_t h, int32_t w, void* stream);
+
 /* ff_ddim_inv_step replaces inv_step (model.py:109-132): x_next = sqrt_an*((x - sqrt_1m_at*eps)/sqrt_at) +
  * c_next*eps over n elements; pred_x0 may be NULL.                                                               */
 int ff_ddim_inv_step(const float* eps, const float* x, float sqrt_1m_at, float sqrt_at, float sqrt_an, float c_next,

@@ -96,3 +96,44 @@ def warp_case_inputs(seed: int, N=1, C=8, H=32, W=32):  # reference wrapAffine_t
     a, b = sc * np.cos(np.deg2rad(ang)), sc * np.sin(np.deg2rad(ang))
     M = np.array([[a, b, (1 - a) * cx - b * cy + dx], [-b, a, b * cx + (1 - a) * cy + dy]], np.float64)
     return src, bg, mask, M
+
+
+def edit_case_inputs(seed: int, res: int = 128):
+    """One synthetic 2-D edit: smooth random image, elliptical object mask, a translation that keeps
+    the object inside.  Returns (image uint8 [res,res,3], ori_mask uint8 0/1 [res,res,3], edit_param 5-tuple,
+    draw_mask uint8 0/1 [res,res], cons_area uint8 0/255 [res,res])."""
+    rng = np.random.default_rng(1000 + seed)
+    img = rng.integers(0, 256, (res, res, 3)).astype(np.float32)
+    k = max(3, res // 16) | 1                     # separable box blur: smooth, non-trivial content (no cv2 needed)
+    ker = np.ones(k, np.float32) / k
+    for ax in (0, 1):
+        img = np.apply_along_axis(lambda v: np.convolve(np.pad(v, k // 2, mode="edge"), ker, mode="valid"), ax, img)
+    img = np.clip(img, 0, 255).astype(np.uint8)
+    m = blob_mask(res, 2000 + seed, (0.08, 0.16))
+    ys, xs = np.where(m)
+    lim = lambda lo, hi: (-(lo - 2), (res - 3) - hi)
+    dxl, dxh = lim(xs.min(), xs.max())
+    dyl, dyh = lim(ys.min(), ys.max())
+    dx = int(np.clip(rng.integers(-res // 5, res // 5 + 1), dxl, dxh))
+    dy = int(np.clip(rng.integers(-res // 5, res // 5 + 1), dyl, dyh))
+    if dx == 0 and dy == 0:
+        dx = int(np.clip(res // 8, dxl, dxh))
+    draw = blob_mask(res, 3000 + seed, (0.1, 0.2))
+    cons = blob_mask(res, 4000 + seed, (0.05, 0.1)) * 255
+    return img, np.repeat(m[:, :, None], 3, 2), (dx, dy, 0, 1.0, 1.0), draw, cons
+
+
+def step_noise(seed: int, k: int, shape):
+    """k-th randn_tensor draw of an edit (fed to both the reference and the B200 path)."""
+    return torch.randn(tuple(shape), generator=torch.Generator().manual_seed(42 + 1000 * seed + k))
+
+
+PIPE_CASES = {
+    # name -> kwargs of FreeFine_generation's inner calls (tiny stand-in UNet, res 128 -> 16x16 latents)
+    "quirk_free":   dict(seed=1, res=128, num_step=10, start_step=2, end_step=6, eta=1.0, gs=7.5, method="tca",
+                         use_auto_draw=False, reduce_inp_artifacts=False, end_scale=0.5, prompt="a photo of a thing"),
+    "geobench_2d":  dict(seed=2, res=128, num_step=10, start_step=4, end_step=10, eta=1.0, gs=7.5, method="tca",
+                         use_auto_draw=True, reduce_inp_artifacts=True, end_scale=0.0, prompt=""),
+    "mmsa":         dict(seed=3, res=128, num_step=8, start_step=2, end_step=8, eta=0.0, gs=5.0, method="mmsa",
+                         use_auto_draw=False, reduce_inp_artifacts=False, end_scale=0.5, prompt="a photo of a thing"),
+}

@@ -154,6 +154,43 @@ def gen_masks(ref, parts):
     np.savez_compressed(os.path.join(OUT, "masks.npz"), **out)
 
 
+def gen_pipeline(ref):
+    """Whole edits through the UNMODIFIED reference pipeline (DDIM_inversion_func -> Details_Preserving_regeneration,
+    i.e. FreeFine_generation model.py:1012-1049 without its GIF writer) on the tiny stand-in network, CPU fp32."""
+    from freefine_b200.standin import build_standin
+    out = {}
+    for name, c in cases.PIPE_CASES.items():
+        parts = build_standin("tiny")
+        pipe, controller = ref_import.make_reference_pipeline(ref, parts)
+        img, ori_mask3, edit_param, draw, cons = cases.edit_case_inputs(c["seed"], c["res"])
+        coarse, tgt_mask, _ = ref.vis_utils.re_edit_2d(img, ori_mask3, edit_param, img)
+        counter = {"k": 0}
+
+        def fake_randn(shape, generator=None, device=None, dtype=None, _c=c, _n=counter):
+            t = cases.step_noise(_c["seed"], _n["k"], shape)
+            _n["k"] += 1
+            return t
+
+        ref.model.randn_tensor = fake_randn
+        torch.manual_seed(c["seed"])
+        ori_mask = pipe.mask_reduce_dim(ori_mask3)
+        _, inv = pipe.DDIM_inversion_func(img=coarse, mask=tgt_mask, prompt="", num_step=c["num_step"],
+                                          start_step=c["start_step"], ref_img=img, verbose=True)
+        edit_img, ref_img, inter = pipe.Details_Preserving_regeneration(
+            coarse, inv, c["prompt"], tgt_mask, ori_mask, draw, num_steps=c["num_step"], start_step=c["start_step"],
+            end_step=c["end_step"], guidance_scale=c["gs"], eta=c["eta"], share_attn=True, method_type=c["method"],
+            verbose=True, local_text_edit=True, local_perturbation=True, return_intermediates=True,
+            cons_area=cons, use_auto_draw=c["use_auto_draw"], end_scale=c["end_scale"],
+            reduce_inp_artifacts=c["reduce_inp_artifacts"])
+        out[name + "/img"], out[name + "/ori_mask"], out[name + "/coarse"], out[name + "/tgt_mask"] = img, ori_mask3, coarse, tgt_mask
+        out[name + "/draw"], out[name + "/cons"] = draw, cons
+        out[name + "/inverted"] = torch.stack(inv).numpy()
+        out[name + "/latents"] = torch.stack(inter).numpy()
+        out[name + "/edit_img"], out[name + "/ref_img"] = edit_img, ref_img
+        out[name + "/n_noise"] = np.array(counter["k"])
+    np.savez_compressed(os.path.join(OUT, "pipeline.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_import.load()
@@ -164,6 +201,7 @@ def main():
     gen_steps(ref, parts)
     gen_warp(ref)
     gen_masks(ref, parts)
+    gen_pipeline(ref)
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -55,3 +55,39 @@ run("rand 4 tiles d80", 1, 512, 512, 2, 80)
 run("rand ragged d40", 1, 200, 77, 2, 40)
 run("rand d160", 1, 256, 256, 2, 160)
 run("rand big d40", 4, 1024, 1024, 8, 40)
+
+# 3) masked two-pass plans (TCA) against the oracle, per (stream, head) error map
+from oracle import cases
+
+
+def run_tca(name, heads, d, S, res, method="tca", kind="edit", cg=0.6):
+    q, k, v = cases.qkv(4, S, heads * d, 11)
+    src = O.process_mask_before_attention(torch.from_numpy(cases.blob_mask(res, 211)), S).numpy()
+    tgt = O.process_mask_before_attention(torch.from_numpy(cases.blob_mask(res, 111)), S).numpy()
+    words = ops.mask_words(S)
+    arr = np.zeros((2, words), np.uint32)
+    for i, m in enumerate((src, tgt)):
+        b = O.pack_bits(m != 0)
+        arr[i, :len(b)] = b
+    bm = torch.from_numpy(arr.view(np.int32)).to(dev)
+    pc = torch.tensor([int((src != 0).sum()), int((tgt != 0).sum())], dtype=torch.int32, device=dev)
+    plan = plans.tca_plan(1, heads, method, cg, lambda e: 0, lambda e: 1, kind=kind)
+    try:
+        out = ops.attn_masked_kv(q.to(dev).bfloat16(), k.to(dev).bfloat16(), v.to(dev).bfloat16(),
+                                 ops.to_device_bytes(plan, dev), heads, d ** -0.5, bm, pc, out_dtype=torch.float32)
+        torch.cuda.synchronize()
+    except Exception as e:
+        print(f"[{name}] FAILED: {e}")
+        return
+    ref = O.tca(q, k, v, heads, d ** -0.5, src, tgt, method, cg, kind=kind)
+    err = (out.cpu() - ref).abs().reshape(4, S, heads, d)
+    print(f"[{name}] H={heads} d={d} S={S} {method}/{kind}: max err {float(err.max()):.3e} nan={int(torch.isnan(out).sum())}")
+    if float(err.max()) > 2e-3:
+        print("  per (stream,head) max err:\n", np.array2string(err.amax((1, 3)).numpy(), precision=3))
+
+
+run_tca("tca d8", 8, 8, 256, 128)
+run_tca("tca d40", 8, 40, 256, 128)
+run_tca("mmsa d40", 8, 40, 256, 128, method="mmsa")
+run_tca("bg d80", 8, 80, 256, 128, kind="bg")
+run_tca("tca d160", 2, 160, 64, 64)

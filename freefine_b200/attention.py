@@ -182,8 +182,10 @@ class Attention_Modulator(AttentionControl):
         if p is None:
             if len(self._plans) > 256:
                 self._plans.clear()
-            p = ops.to_device_bytes(builder(), self._device)
+            host = builder()
+            p = ops.to_device_bytes(host, self._device)
             self._plans[key] = p
+            ops.PLAN_REGISTRY[p.data_ptr()] = host      # host copy for FLOP accounting (bench.py)
         return p
 
     def _attend(self, query, key, value, plan, bits=None, pop=None):

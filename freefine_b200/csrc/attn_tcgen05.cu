@@ -9,9 +9,9 @@
 //   warp  4    TMA producer (one elected lane): Q once, then a ring of K/V tiles (128 keys x 64 channels boxes,
 //              SWIZZLE_128B, channels beyond head_dim zero-filled by the TMA bounds check), + TMEM alloc/dealloc
 //   warp  5    MMA issuer (one elected lane):  S = Q K^T  (SS, M128 N128 K16 x DPAD/16, both operands K-major)
-//                                              O += P V   (TS: P bf16 in TMEM, V MN-major straight from the K/V box)
-// Per K/V tile:  QK^T -> [s_full] -> softmax (2 sweeps over S in TMEM: max, then exp2 / row-sum / bf16 P written
-// over the S columns already consumed) -> [p_full] -> PV -> [o_done, kv_empty].  The running max is only
+//                                              O += P V   (TS: P = hi+lo bf16 pair in TMEM, V MN-major from the box)
+// Per K/V tile:  QK^T -> [s_full] -> softmax (2 sweeps over S in TMEM: max, then exp2 / row-sum / P written as a
+// hi+lo bf16 pair over the S columns already consumed) -> [p_full] -> PV -> [o_done, kv_empty].  The running max is only
 // refreshed when it grows by more than 2^8 (lazy rescale: O stays in TMEM, read-modify-written only then).
 // Region masks are bit-vectors; `allowed(q,k)` is evaluated in registers on 32-bit words, nothing [S,S]-shaped
 // exists anywhere.  Every pass of a plan has its own softmax; pass results are combined as
@@ -159,6 +159,19 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, int b_mn) {
          ((uint32_t)(BM >> 4) << 24);
 }
 
+// Optional progress trace for debugging protocol stalls (ff_debug_set_trace): a host-mapped buffer the kernel writes
+// (cta, role) -> (tile counter, site) into; null in production (one predictable branch per barrier wait).
+__device__ uint32_t* g_trace = nullptr;
+__device__ __forceinline__ void trace(uint32_t* tr, int role, uint32_t it, uint32_t site) {
+  if (tr) {
+    const uint32_t cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    volatile uint32_t* t = tr + (size_t)cta * 8 + role * 2;
+    t[0] = it;
+    t[1] = site;
+    __threadfence_system();
+  }
+}
+
 struct KParams {
   const FFAttnHeadPlan* plan;
   const uint32_t* bitmasks;
@@ -239,6 +252,14 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
+#ifdef FF_ENABLE_TRACE   // build with FF_TRACE=1 (csrc/build.py); off in the product build
+  uint32_t* const tr = g_trace;
+  const int trole = warp == 4 ? 0 : (warp == 5 ? 1 : (threadIdx.x == 0 ? 2 : (threadIdx.x == 96 ? 3 : -1)));
+#define FF_TRACE(it_, site_) do { if (tr && trole >= 0 && (warp < 4 || lane == 0)) trace(tr, trole, (uint32_t)(it_), (site_)); } while (0)
+#else
+#define FF_TRACE(it_, site_) do { } while (0)
+#endif
+  FF_TRACE(0, 1);
 
   if (warp == 4) {
     // ===================================== TMA producer =====================================
@@ -255,7 +276,9 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           if (pi.kv[seg] < 0) continue;
           for (int j = 0; j < n_kv_tiles; ++j, ++it) {
             const int stage = it % C::NSTAGE, use = it / C::NSTAGE;
+            FF_TRACE(it, 10);
             if (use > 0) mbar_wait(bar_kv_empty + 8 * stage, (use - 1) & 1);
+            FF_TRACE(it, 11);
             const uint32_t full = bar_kv_full + 8 * stage;
             const uint32_t sK = sKV + stage * C::SMEM_STAGE, sV = sK + C::NKT * TILE_BYTES;
             mbar_expect_tx(full, 2 * C::NKT * TILE_BYTES);
@@ -272,6 +295,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     if (lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc(BN, 0);
       constexpr uint32_t idesc_pv = make_idesc(DPAD, 1);
+      FF_TRACE(0, 20);
       mbar_wait(bar_q, 0);
       int it = 0;
       for (int ip = 0; ip < n_pass; ++ip) {
@@ -284,7 +308,9 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           for (int j = 0; j < n_kv_tiles; ++j, ++it) {
             const int stage = it % C::NSTAGE, use = it / C::NSTAGE;
             const uint32_t sK = sKV + stage * C::SMEM_STAGE, sV = sK + C::NKT * TILE_BYTES;
+            FF_TRACE(it, 21);
             mbar_wait(bar_kv_full + 8 * stage, use & 1);
+            FF_TRACE(it, 22);
             tc_fence_after();
             // S = Q K^T.  The S/P columns are free: softmax(it-1) arrived on p_full before PV(it-1) was issued and
             // the tensor pipe executes this thread's MMAs in issue order.
@@ -295,14 +321,20 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                      ks > 0);
             }
             tc_commit(bar_s);
+            FF_TRACE(it, 23);
             mbar_wait(bar_p, it & 1);
+            FF_TRACE(it, 24);
             tc_fence_after();
-            // O (+)= P V : A = P (bf16, TMEM columns [0,64)), B = V tile, MN-major; 16 keys = 2048 B per K-step,
+            // O (+)= P_hi V + P_lo V : A = P halves (bf16 in TMEM, 8 columns per 16 keys: K-step ks keeps hi in
+            // columns [16ks,16ks+8) and lo in [16ks+8,16ks+16)), B = V tile, MN-major; 16 keys = 2048 B per K-step,
             // 64-channel groups TILE_BYTES apart (LBO)
 #pragma unroll
-            for (int ks = 0; ks < BN / 16; ++ks)
-              mma_ts(tmem + C::TMEM_O, tmem + C::TMEM_S + ks * 8, smem_desc_sw128(sV + ks * 2048, TILE_BYTES),
-                     idesc_pv, (!first || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < BN / 16; ++ks) {
+              const uint32_t a_hi = tmem + C::TMEM_S + 16 * ks;
+              const uint64_t vdesc = smem_desc_sw128(sV + ks * 2048, TILE_BYTES);
+              mma_ts(tmem + C::TMEM_O, a_hi, vdesc, idesc_pv, (!first || ks > 0) ? 1u : 0u);
+              mma_ts(tmem + C::TMEM_O, a_hi + 8, vdesc, idesc_pv, 1u);
+            }
             tc_commit(bar_kv_empty + 8 * stage);
             tc_commit(bar_o);
             first = false;
@@ -365,7 +397,9 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           }
           const bool fast = __all_sync(0xffffffffu, all_on);
 
+          FF_TRACE(it, 30);
           mbar_wait(bar_s, it & 1);
+          FF_TRACE(it, 31);
           tc_fence_after();
           // ---- sweep 1: row max over the allowed keys (raw scores)
           float mt = -INFINITY;
@@ -395,7 +429,9 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             grow = true;
           }
           if (__any_sync(0xffffffffu, grow)) {
+            FF_TRACE(it, 32);
             mbar_wait(bar_o, (it - 1) & 1);      // PV(it-1) has finished writing O
+            FF_TRACE(it, 33);
             tc_fence_after();
 #pragma unroll
             for (int c = 0; c < DPAD / 16; ++c) {
@@ -409,37 +445,47 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             }
           }
           const float mref = m_used == -INFINITY ? 0.f : m_used;
-          // ---- sweep 2: p = 2^(s*scale*log2e - m), row sum, bf16 pairs written over S columns already consumed
+          // ---- sweep 2: p = 2^(s*scale*log2e - m), row sum.  P goes to the tensor core as TWO bf16 operands,
+          // p = hi + lo (hi = truncated upper 16 bits, lo = bf16(p - hi)): 16 mantissa bits instead of 8, so the
+          // result stays within the fp32-reference tolerance; the second PV MMA rides on tensor-pipe slack (the
+          // tile is exp-bound).  The 16 keys of K-step ks (S columns [16ks,16ks+16)) are overwritten in place by
+          // hi -> [16ks,16ks+8) and lo -> [16ks+8,16ks+16): only columns this thread has already consumed.
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float s[32];
-            uint32_t pk[16];
-            tmem_ld32(tlane + C::TMEM_S + 32 * c, s);
+          for (int ks = 0; ks < BN / 16; ++ks) {
+            float s[16];
+            uint32_t hl[16];
+            tmem_ld16(tlane + C::TMEM_S + 16 * ks, s);
             tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float e = fast_exp2(fmaf(s[i], sc, -mref));
-              if (!fast) e = (aw[c] >> i) & 1u ? e : 0.f;
-              s[i] = e;
-            }
+            const uint32_t awk = aw[ks >> 1] >> (16 * (ks & 1));
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const __nv_bfloat162 b2 = __floats2bfloat162_rn(s[2 * i], s[2 * i + 1]);   // .x (low half) = key 2i
-              pk[i] = *reinterpret_cast<const uint32_t*>(&b2);
-              // the row sum uses the ROUNDED weights the tensor core will see: out = sum(p^ v) / sum(p^) stays a convex
-              // combination of V rows (exact when one key dominates)
-              l += __uint_as_float(pk[i] << 16) + __uint_as_float(pk[i] & 0xffff0000u);
+              float e = fast_exp2(fmaf(s[i], sc, -mref));
+              if (!fast) e = (awk >> i) & 1u ? e : 0.f;
+              s[i] = e;
+              l += e;
             }
-            tmem_st16(tlane + C::TMEM_S + 16 * c, pk);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t b0 = __float_as_uint(s[2 * i]), b1 = __float_as_uint(s[2 * i + 1]);
+              hl[i] = __byte_perm(b0, b1, 0x7632);                        // low half = key 2i, high half = key 2i+1
+              const float r0 = s[2 * i] - __uint_as_float(b0 & 0xffff0000u);
+              const float r1 = s[2 * i + 1] - __uint_as_float(b1 & 0xffff0000u);
+              const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
+              hl[8 + i] = *reinterpret_cast<const uint32_t*>(&l2);
+            }
+            tmem_st16(tlane + C::TMEM_S + 16 * ks, hl);
           }
           tmem_wait_st();
           tc_fence_before();
           mbar_arrive(bar_p);
+          FF_TRACE(it, 34);
           first = false;
         }
       }
       // ---- end of pass: acc += weight * roww / l * O
+      FF_TRACE(it, 35);
       mbar_wait(bar_o, (it - 1) & 1);
+      FF_TRACE(it, 36);
       tc_fence_after();
       float coef = ps.weight;
       if (ps.flags & FF_PASS_ROW_WEIGHT) coef = rb ? coef : 0.f;
@@ -470,9 +516,12 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       if constexpr (C::ACC_TMEM) tmem_wait_st();
       acc_started = true;
     }
-    // ---- write the row: out[stream, row, head*d : (head+1)*d]
-    if (row < p.s_q) {
-      const size_t o_off = ((size_t)stream * p.s_q + row) * ((size_t)p.heads * p.head_dim) + (size_t)head * p.head_dim;
+    // ---- write the row: out[stream, row, head*d : (head+1)*d].  tcgen05.ld is warp-collective (.sync.aligned):
+    // every lane executes the TMEM loads, only the global stores are predicated on row < s_q.
+    {
+      const bool row_ok = row < p.s_q;
+      const size_t o_off = ((size_t)stream * p.s_q + (row_ok ? row : 0)) * ((size_t)p.heads * p.head_dim) +
+                           (size_t)head * p.head_dim;
 #pragma unroll
       for (int c = 0; c < DPAD / 16; ++c) {
         float o[16];
@@ -490,7 +539,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         }
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-          if (16 * c + 8 * g < p.head_dim) {   // head_dim % 8 == 0
+          if (row_ok && 16 * c + 8 * g < p.head_dim) {   // head_dim % 8 == 0
             if (p.out_dtype == FF_DT_BF16) {
               uint4 v;
               __nv_bfloat162 b0 = __floats2bfloat162_rn(o[8 * g + 0], o[8 * g + 1]);
@@ -512,6 +561,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       }
     }
   }
+  FF_TRACE(0, 90);
   // ---- teardown: every tcgen05 op of this CTA has completed (softmax threads waited on o_done of the last tile)
   tc_fence_before();
   __syncthreads();
@@ -578,6 +628,17 @@ int launch(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, 
 }
 
 }  // namespace
+
+// Debug hook (not part of the product path): device-visible pointer (e.g. cudaHostAlloc'ed, mapped) that receives
+// 8 uint32 per CTA: {producer it, site, mma it, site, softmax-row0 it, site, softmax-row96 it, site}; NULL disables.
+extern "C" int ff_debug_set_trace(void* device_visible_ptr) {
+#ifndef FF_ENABLE_TRACE
+  if (device_visible_ptr) return ff::fail(FF_E_UNSUPPORTED, "ff_debug_set_trace: library built without FF_TRACE=1");
+#endif
+  cudaError_t e = cudaMemcpyToSymbol(g_trace, &device_visible_ptr, sizeof(void*));
+  if (e != cudaSuccess) return ff::fail(FF_E_CUDA, "ff_debug_set_trace: %s", cudaGetErrorString(e));
+  return FF_OK;
+}
 
 extern "C" int ff_attn_masked_kv(const FFAttnArgs* a, void* stream) {
   FF_REQUIRE(a != nullptr, "ff_attn_masked_kv: null args");

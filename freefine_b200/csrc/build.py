@@ -46,7 +46,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, [sp] + hdrs):
-            cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", sp, "-o", obj]
+            cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+                  (["-DFF_ENABLE_TRACE"] if os.environ.get("FF_TRACE") == "1" else []) + ["-c", sp, "-o", obj]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:

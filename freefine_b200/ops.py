@@ -14,6 +14,17 @@ from ._lib import FF_DT_BF16, FF_DT_F32
 
 _DT = {torch.float32: FF_DT_F32, torch.bfloat16: FF_DT_BF16}
 
+# Measurement hooks (bench.py): COUNTS = kernel launches issued through the C ABI, by entry point;
+# PROFILE = None or a list that receives one CUDA-event pair per ff_attn_masked_kv launch (events are recorded on
+# the launching stream, so the pair brackets exactly that kernel).
+COUNTS: dict = {}
+PROFILE = None
+PLAN_REGISTRY: dict = {}     # device plan pointer -> host (numpy) plan, filled by the controller; read only when PROFILE is on
+
+
+def _count(name: str):
+    COUNTS[name] = COUNTS.get(name, 0) + 1
+
 
 def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -66,6 +77,7 @@ def ddim_cfg_step(eps4, x, noise, cfg_mask, var_mask, guidance_scale, sqrt_1m_at
                               sqrt_1m_at, sqrt_at, sqrt_ap, c_ddim, c_ddpm, sigma, _ptr(x_prev), _ptr(x0), n_edits,
                               Cc, h, w, _stream())
     _lib.check(rc, "ff_ddim_cfg_step")
+    _count("ff_ddim_cfg_step")
     return (x_prev, x0) if want_pred_x0 else x_prev
 
 
@@ -87,6 +99,7 @@ def ddim_step(eps2, x, noise, var_mask, sqrt_1m_at, sqrt_at, sqrt_ap, c_ddim, c_
     rc = _lib.load().ff_ddim_step(_ptr(eps2), _ptr(x), _ptr(noise), _ptr(var_mask), sqrt_1m_at, sqrt_at, sqrt_ap,
                                   c_ddim, c_ddpm, sigma, _ptr(x_prev), _ptr(x0), n_edits, Cc, h, w, _stream())
     _lib.check(rc, "ff_ddim_step")
+    _count("ff_ddim_step")
     return (x_prev, x0) if want_pred_x0 else x_prev
 
 
@@ -101,6 +114,7 @@ def ddim_inv_step(eps, x, sqrt_1m_at, sqrt_at, sqrt_an, c_next, want_pred_x0=Fal
     rc = _lib.load().ff_ddim_inv_step(_ptr(eps), _ptr(x), sqrt_1m_at, sqrt_at, sqrt_an, c_next, _ptr(x_next), _ptr(x0),
                                       x.numel(), _stream())
     _lib.check(rc, "ff_ddim_inv_step")
+    _count("ff_ddim_inv_step")
     return (x_next, x0) if want_pred_x0 else x_next
 
 
@@ -136,6 +150,7 @@ def warp_affine_blend(src, theta, dsize=None, mask_src=None, bg=None, mode="bili
                                           N, Cc, H, W, dH, dW, 0 if mode == "bilinear" else 1, _DT[src.dtype],
                                           _stream())
     _lib.check(rc, "ff_warp_affine_blend")
+    _count("ff_warp_affine_blend")
     return (out, mask_out) if want_mask else out
 
 
@@ -159,6 +174,7 @@ def mask_downsample_pack(masks, h, w, bits=None, popcount=None):
     rc = _lib.load().ff_mask_downsample_pack(_ptr(masks), n, H, W, h, w, _ptr(bits), bits.shape[1], _ptr(popcount),
                                              _stream())
     _lib.check(rc, "ff_mask_downsample_pack")
+    _count("ff_mask_downsample_pack")
     return bits, popcount
 
 
@@ -196,8 +212,17 @@ def attn_masked_kv(q, k, v, plan, heads, scale, bitmasks=None, popcount=None, ou
     a.s_q, a.s_kv = Sq, Skv
     a.out_dtype = _DT[out_dtype]
     a.scale = float(scale)
+    prof = PROFILE
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     rc = _lib.load().ff_attn_masked_kv(C.byref(a), _stream())
     _lib.check(rc, "ff_attn_masked_kv")
+    COUNTS["ff_attn_masked_kv"] = COUNTS.get("ff_attn_masked_kv", 0) + 1
+    if prof is not None:
+        ev1.record()
+        prof.append(dict(ev0=ev0, ev1=ev1, B=B, Bk=Bk, s_q=Sq, s_kv=Skv, d=Cc // heads, heads=heads, plan=PLAN_REGISTRY.get(plan.data_ptr()),
+                         popcount=popcount))
     return out
 
 
@@ -214,6 +239,7 @@ def cross_region_blend(hs, bitmasks, region_ids):
     rc = _lib.load().ff_cross_region_blend(_ptr(hs), _ptr(bitmasks), bitmasks.shape[1], _ptr(region_ids), B // 4, S, Cc,
                                            _DT[hs.dtype], _stream())
     _lib.check(rc, "ff_cross_region_blend")
+    _count("ff_cross_region_blend")
     return hs
 
 

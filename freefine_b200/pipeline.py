@@ -461,5 +461,93 @@ class FreeFinePipeline:
         return edit_img, ref_img
 
 
+    # ------------------------------------------------------------------------------------------------------------
+    # batched entry point (extension: E edits share one stream batch; the reference loops over edits one by one,
+    # evaluation/FreeFine/freefine_batch_infer_2d.py:177-234)
+    # ------------------------------------------------------------------------------------------------------------
+    def prepare_various_mask_batch(self, shifted, ori, draw, cons, lat_hw, use_auto_draw, reduce_inp_artifacts):
+        """prepare_various_mask (model.py:1432-1512) for E edits at once on device tensors [E,H,W] uint8 (any nonzero =
+        set).  Same uint8 algebra (wrap-around included, quirk Q1) as the per-edit method."""
+        b = lambda t: (t > 0).to(torch.uint8)
+
+        def dil(t, k):
+            a = k // 2
+            x = F.pad(b(t)[:, None].float(), (a, k - 1 - a, a, k - 1 - a), value=0.0)
+            return F.max_pool2d(x, kernel_size=k, stride=1)[:, 0].to(torch.uint8)
+
+        sh, orim = b(shifted), b(ori)
+        if not use_auto_draw:
+            flex = b(draw) * (1 - sh)
+            fg = flex + sh
+            fg[fg > 0] = 1
+            comp = flex
+            if not reduce_inp_artifacts:
+                lvar = flex
+            else:
+                lvar = (1 - b(cons)) * (1 - sh) * dil(ori, 30) + flex
+                lvar[lvar > 0] = 1
+        else:
+            fg = sh
+            c2 = b(cons) - orim
+            if not reduce_inp_artifacts:
+                comp = (1 - c2) * (1 - sh) * dil(shifted, 15)
+            else:
+                comp = dil(ori, 30) + dil(shifted, 15)
+                comp[comp > 0] = 1
+                comp = comp * ((1 - c2) * (1 - sh))
+            lvar = comp
+        ds = lambda t: F.interpolate(t[:, None], lat_hw, mode='nearest')[:, 0].contiguous()
+        return fg, sh, orim, ds(comp), ds(lvar)
+
+    @torch.no_grad()
+    def FreeFine_generation_batch(self, ori_imgs, ori_masks, edit_params, guidance_texts, guidance_scale=7.5, eta=1.0,
+                                  end_step=50, num_step=50, start_step=35, method_type='tca', seed=42, draw_masks=None,
+                                  use_auto_draw=True, reduce_inp_artifacts=True, end_scale=0.0, inp_bgs=None,
+                                  thetas=None, return_latents=False):
+        """E whole 2-D edits (coarse warp+blend -> DDIM inversion -> TCA sampling -> decode) in one stream batch.
+        ori_imgs: uint8 [E,H,W,3] (numpy / pinned host tensor / CUDA tensor), ori_masks: uint8 [E,H,W] 0/1,
+        edit_params: list of (dx,dy,rz,sx,sy) (or precomputed `thetas` f32 [E,2,3] when the masks live on the device).
+        Defaults are the reference's GeoBench-2D settings (freefine_batch_infer_2d.py:212-230).
+        Returns uint8 images [E,H,W,3] on the side the inputs came from (host inputs -> host numpy)."""
+        from . import coarse_edit
+        assert method_type in ['tca', 'mmsa', 'mmsa_es'], method_type
+        seed_everything(seed)
+        host_in = not (torch.is_tensor(ori_imgs) and ori_imgs.is_cuda)
+        to_dev = lambda a: (a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))).to(self.device, non_blocking=True)
+        imgs_u8, masks = to_dev(ori_imgs), to_dev(ori_masks)
+        E, H, W = masks.shape
+        if thetas is None:
+            mh = ori_masks.cpu().numpy() if torch.is_tensor(ori_masks) else np.asarray(ori_masks)
+            thetas = torch.tensor(np.stack([coarse_edit.cv2_theta(coarse_edit.edit_matrix(mh[e], edit_params[e]), W, H)
+                                            for e in range(E)]), dtype=torch.float32)
+        imgs = imgs_u8.permute(0, 3, 1, 2).float().contiguous()
+        bgs = imgs if inp_bgs is None else to_dev(inp_bgs).permute(0, 3, 1, 2).float().contiguous()
+        coarse, tgt = coarse_edit.re_edit_2d_device(imgs, masks.contiguous(), to_dev(thetas), bgs)
+        coarse = coarse.round().clamp(0, 255)                                   # the reference hands a uint8 image on
+        draw = torch.zeros_like(masks) if draw_masks is None else to_dev(draw_masks)
+        lat_hw = (H // 8, W // 8)
+        fg, sh, orim, comp, lvar = self.prepare_various_mask_batch(tgt, masks, draw, tgt, lat_hw, use_auto_draw,
+                                                                   reduce_inp_artifacts)
+        src = torch.stack([coarse, imgs], dim=1).reshape(2 * E, 3, H, W) / 127.5 - 1
+        _, inverted = self.invert(src, [""] * (2 * E), guidance_scale=1.0, num_inference_steps=num_step,
+                                  num_actual_inference_steps=num_step - start_step, return_intermediates=True)
+        c = self.controller
+        c.reset()
+        c.fg_retain_mask, c.fg_retain_mask_st2, c.fg_ref_mask, c.local_edit_region = fg, sh, orim, fg
+        prompts = [p for t in guidance_texts for p in (t, "")]
+        image, inter = self.forward_sampling(prompt=prompts, refer_latents=inverted[::-1], end_step=end_step,
+                                             latents=inverted[-1].clone(), guidance_scale=guidance_scale,
+                                             num_inference_steps=num_step, num_actual_inference_steps=num_step - start_step,
+                                             eta=eta, completion_mask_cfg=comp, local_var_reg=lvar, method_type=method_type,
+                                             end_scale=end_scale, return_intermediates=True, verbose=True)
+        c.reset()
+        out = (image.view(E, 2, 3, H, W)[:, 0].permute(0, 2, 3, 1) * 255).to(torch.uint8)
+        if host_in:
+            out = out.cpu().numpy()
+        if return_latents:
+            return out, inter[-1]
+        return out
+
+
 __all__ = ["FreeFinePipeline", "Attention_Modulator", "register_attention_control",
            "register_attention_control_4bggen", "register_attention_control_compose", "randn_tensor"]

@@ -133,6 +133,36 @@ def style_align_plan(n_edits: int, heads: int, src_id=None) -> np.ndarray:
     return p
 
 
+def algorithmic_flops(plan: np.ndarray, s_q: int, s_kv: int, d: int, popcount=None) -> float:
+    """ALGORITHMIC FLOPs of one ff_attn_masked_kv launch: 4*d per (query, allowed key) pair of every
+    pass -- QK^T + PV of exactly the pairs the softmax needs.  Padding (d -> 48/80/160), masked-out columns inside
+    a partially masked tile and the hi/lo split of P are overhead, not work.  popcount[i] = set bits of bitmask row i."""
+    total = 0.0
+    for e in plan.reshape(-1):
+        for ps in e["passes"][: int(e["n_pass"])]:
+            flags = int(ps["flags"])
+            n_r = int(popcount[int(ps["row_mask"])]) if ps["row_mask"] >= 0 else 0
+            if ps["key_mask"] >= 0:
+                n_k = int(popcount[int(ps["key_mask"])])
+                c0 = s_kv - n_k if flags & FF_PASS_KEY_INVERT else n_k          # keys allowed for rows with rowbit 0
+            else:
+                c0 = s_kv
+            if flags & FF_PASS_ROW_WEIGHT:
+                pairs = n_r * c0
+            elif flags & FF_PASS_ROW_XOR and ps["key_mask"] >= 0:
+                pairs = (s_q - n_r) * c0 + n_r * (s_kv - c0)
+            else:
+                pairs = s_q * c0
+            if ps["kv_stream2"] >= 0:
+                if ps["key_mask2"] >= 0:
+                    n2 = int(popcount[int(ps["key_mask2"])])
+                    pairs += s_q * (s_kv - n2 if flags & FF_PASS_KEY2_INVERT else n2)
+                else:
+                    pairs += s_q * s_kv
+            total += 4.0 * d * pairs
+    return total
+
+
 def describe(plan: np.ndarray) -> str:
     """Human-readable dump (debugging / DESIGN.md examples)."""
     out = []

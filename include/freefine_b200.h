@@ -159,6 +159,10 @@ int ff_ddim_inv_step(const float* eps, const float* x, float sqrt_1m_at, float s
 int ff_cross_region_blend(void* hs, const uint32_t* bitmasks, int32_t mask_words, const int32_t* region_mask,
                           int32_t n_edits, int32_t S, int32_t C, int32_t dtype, void* stream);
 
+/* Debugging aid, not used by the product path: progress trace of ff_attn_masked_kv into a device-visible buffer of
+ * 8 uint32 per CTA (see csrc/attn_tcgen05.cu); NULL switches it off.                                              */
+int ff_debug_set_trace(void* device_visible_ptr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,143 @@
+"""Whole edits on the GPU through the reference-compatible call surface (Attention_Modulator +
+register_attention_control + FreeFinePipeline) against final latents produced by the UNMODIFIED reference on CPU
+(tests/golden/pipeline.npz, tiny stand-in UNet with SD1.5 head dims, identical weights / inputs / noise).
+Tolerance (BASELINE.json north_star): final latents within 1e-2 relative L2."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from freefine_b200 import _lib
+    _lib.load()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return torch.device("cuda:0")
+
+
+def _make(dev):
+    from freefine_b200.pipeline import Attention_Modulator, FreeFinePipeline, register_attention_control
+    from freefine_b200.standin import build_standin
+    parts = build_standin("tiny", device=dev)
+    controller = Attention_Modulator(start_layer=10)
+    pipe = FreeFinePipeline.from_parts(parts, controller, device=dev)
+    register_attention_control(pipe, controller)
+    pipe.modify_unet_forward()
+    assert controller.num_att_layers == 32
+    return pipe, controller
+
+
+def _rel_l2(a, b):
+    return float((a - b).norm() / b.norm())
+
+
+@pytest.mark.parametrize("name", list(cases.PIPE_CASES))
+def test_full_edit_matches_reference(dev, golden, name, monkeypatch):
+    import freefine_b200.pipeline as P
+    g = golden["pipeline"]
+    c = cases.PIPE_CASES[name]
+    pipe, controller = _make(dev)
+    counter = {"k": 0}
+
+    def fake_randn(shape, generator=None, device=None, dtype=None):
+        t = cases.step_noise(c["seed"], counter["k"], shape).to(device)
+        counter["k"] += 1
+        return t
+
+    monkeypatch.setattr(P, "randn_tensor", fake_randn)
+    img, coarse, tgt_mask = g[name + "/img"], g[name + "/coarse"], g[name + "/tgt_mask"]
+    ori_mask = pipe.mask_reduce_dim(g[name + "/ori_mask"])
+    _, inv = pipe.DDIM_inversion_func(img=coarse, mask=tgt_mask, prompt="", num_step=c["num_step"],
+                                      start_step=c["start_step"], ref_img=img, verbose=True)
+    inv_ref = torch.from_numpy(g[name + "/inverted"])
+    assert len(inv) == inv_ref.shape[0]
+    assert _rel_l2(inv[-1].cpu(), inv_ref[-1]) < 1e-2
+    edit_img, ref_img, inter = pipe.Details_Preserving_regeneration(
+        coarse, inv, c["prompt"], tgt_mask, ori_mask, g[name + "/draw"], num_steps=c["num_step"],
+        start_step=c["start_step"], end_step=c["end_step"], guidance_scale=c["gs"], eta=c["eta"], share_attn=True,
+        method_type=c["method"], verbose=True, local_text_edit=True, local_perturbation=True,
+        return_intermediates=True, cons_area=g[name + "/cons"], use_auto_draw=c["use_auto_draw"],
+        end_scale=c["end_scale"], reduce_inp_artifacts=c["reduce_inp_artifacts"])
+    lat_ref = torch.from_numpy(g[name + "/latents"])
+    assert len(inter) == lat_ref.shape[0]
+    assert counter["k"] == int(g[name + "/n_noise"])
+    errs = [_rel_l2(a.cpu(), b) for a, b in zip(inter, lat_ref)]
+    assert errs[-1] < 1e-2, errs
+    assert edit_img.shape == g[name + "/edit_img"].shape and edit_img.dtype == np.uint8
+    assert np.abs(edit_img.astype(np.int32) - g[name + "/edit_img"].astype(np.int32)).max() <= 8
+
+
+def test_mask_prep_bit_exact_on_device(dev, golden):
+    g = golden["masks"]
+    pipe, _ = _make(dev)
+    init = torch.zeros(1, 4, 16, 16)
+    for auto in (False, True):
+        for red in (False, True):
+            r = pipe.prepare_various_mask(g["shifted"].copy(), g["ori"].copy(), g["draw"].copy(), 128, 128, init, verbose=True,
+                                          use_auto_draw=auto, cons_area=g["cons"].copy(), reduce_inp_artifacts=red)
+            for nm, t in zip(("fg", "sh", "ori_t", "comp", "lvar"), r):
+                ref = g[f"auto{int(auto)}_red{int(red)}/{nm}"]
+                assert t.dtype == torch.uint8 and np.array_equal(t.cpu().numpy(), ref), (auto, red, nm)
+    for k in (15, 30):
+        assert np.array_equal(pipe.dilate_mask(g["ori"][:, :, 0], k), g[f"dilate{k}"])
+
+
+def test_batched_edits_match_single(dev, golden):
+    """E=2 edits in one stream batch == the same edits run one at a time (the reference cannot batch)."""
+    import freefine_b200.pipeline as P
+    g = golden["pipeline"]
+    pipe, controller = _make(dev)
+    names = ["quirk_free", "mmsa"]
+    C = cases.PIPE_CASES
+    n_step, start, end = 6, 1, 4
+    torch.manual_seed(0)
+    lat, masks = {}, {}
+    for nm in names:
+        img, coarse = g[nm + "/img"], g[nm + "/coarse"]
+        src = torch.cat([pipe.preprocess_image(coarse, dev), pipe.preprocess_image(img, dev)])
+        _, lst = pipe.invert(src, "", guidance_scale=1.0, num_inference_steps=n_step, num_actual_inference_steps=n_step - start,
+                             return_intermediates=True, verbose=True)
+        controller.reset()
+        lat[nm] = lst
+        masks[nm] = pipe.prepare_various_mask(g[nm + "/tgt_mask"], pipe.mask_reduce_dim(g[nm + "/ori_mask"]), g[nm + "/draw"],
+                                              128, 128, lst[-1], verbose=True)
+    noise = torch.randn(n_step, 4, 4, 16, 16, generator=torch.Generator().manual_seed(9)).to(dev)
+
+    def run(sel):
+        controller.reset()
+        controller.fg_retain_mask = torch.stack([masks[n][0] for n in sel])
+        controller.fg_retain_mask_st2 = torch.stack([masks[n][1] for n in sel])
+        controller.fg_ref_mask = torch.stack([masks[n][2] for n in sel])
+        controller.local_edit_region = controller.fg_retain_mask
+        k = {"i": 0}
+        idx = [names.index(n) for n in sel]
+
+        def fake(shape, generator=None, device=None, dtype=None):
+            t = noise[k["i"]].reshape(2, 2, 4, 16, 16)[idx].reshape(shape)
+            k["i"] += 1
+            return t.contiguous()
+
+        P.randn_tensor, old = fake, P.randn_tensor
+        try:
+            refer = [torch.cat([lat[n][j] for n in sel]) for j in range(len(lat[sel[0]]))][::-1]
+            _, inter = pipe.forward_sampling(prompt=["a photo", ""] * len(sel), refer_latents=refer, end_step=end,
+                                             latents=refer[0].clone(), guidance_scale=7.5, num_inference_steps=n_step,
+                                             num_actual_inference_steps=n_step - start, eta=1.0,
+                                             completion_mask_cfg=torch.stack([masks[n][3] for n in sel]),
+                                             local_var_reg=torch.stack([masks[n][4] for n in sel]), method_type='tca',
+                                             verbose=True, return_intermediates=True)
+        finally:
+            P.randn_tensor = old
+        return inter[-1]
+
+    both = run(names)
+    for i, nm in enumerate(names):
+        one = run([nm])
+        assert _rel_l2(both[2 * i:2 * i + 2].cpu(), one.cpu()) < 1e-4, nm

@@ -116,12 +116,12 @@ def test_tca_vs_oracle_sd15_shapes(dev, S, d, res, method, kind):
 
 def test_peaked_softmax_and_large_logits(dev):
     """|logits| ~ 30: exercises the lazy-rescale path (running max grows by > 2^8 across tiles)."""
-    heads, d, S = 8, 40, 512
+    heads, d, S = 8, 40, 1024
     q, k, v = cases.qkv(4, S, heads * d, 901, logit_scale=12.0)
     # make later keys systematically larger so the row max keeps growing tile after tile
     k = (k * torch.linspace(0.2, 2.0, S)[None, :, None]).bfloat16().float()
-    src = O.process_mask_before_attention(torch.from_numpy(cases.blob_mask(128, 902)), S).numpy()
-    tgt = O.process_mask_before_attention(torch.from_numpy(cases.blob_mask(128, 903)), S).numpy()
+    src = O.process_mask_before_attention(torch.from_numpy(cases.blob_mask(256, 902)), S).numpy()
+    tgt = O.process_mask_before_attention(torch.from_numpy(cases.blob_mask(256, 903)), S).numpy()
     plan = plans.tca_plan(1, heads, "tca", 0.5, lambda e: 0, lambda e: 1)
     out = _run(dev, q, k, v, plan, heads, d ** -0.5, [src, tgt])
     ref = O.tca(q, k, v, heads, d ** -0.5, src, tgt, "tca", 0.5)
@@ -144,10 +144,11 @@ def test_full_size_properties(dev):
     # constant over tokens AND equal across the 4 streams of an edit so every pass returns the same constant
     vc = const[::4].repeat_interleave(4, 0).expand(4 * E, S, heads * d).contiguous()
     out_c = _run(dev, q, k, vc, plan, heads, d ** -0.5, flat)
-    assert float((out_c - vc).abs().max()) < 1e-5 * float(vc.abs().max()) + 1e-5
+    # (the tensor core accumulates 4096 products per row in fp32 with truncation: a few 1e-5 relative)
+    assert float((out_c - vc).abs().max()) < 2e-4 * float(vc.abs().max())
     out1 = _run(dev, q, k, v, plan, heads, d ** -0.5, flat)
     out2 = _run(dev, q, k, (2 * v), plan, heads, d ** -0.5, flat)
-    assert float((out2 - 2 * out1).abs().max()) < 1e-5
+    assert float((out2 - 2 * out1).abs().max()) < 1e-4
     assert bool(torch.isfinite(out1).all())
     e = 3
     p1 = plans.tca_plan(1, heads, "tca", 0.4, lambda _: 0, lambda _: 1)

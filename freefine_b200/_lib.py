@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libfreefine_b200.so")
 FF_MAX_PASS = 4
 FF_DT_F32, FF_DT_BF16 = 0, 1
 FF_PASS_KEY_INVERT, FF_PASS_ROW_XOR, FF_PASS_ROW_WEIGHT, FF_PASS_KEY2_INVERT = 1, 2, 4, 8
+FF_PASS_KEY_PREFIX, FF_PASS_KEY2_PREFIX = 16, 32
 
 
 class FFAttnPass(C.Structure):

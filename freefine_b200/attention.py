@@ -111,6 +111,7 @@ class Attention_Modulator(AttentionControl):
         self.upcast_attention = False
         self.upcast_softmax = False
         self.log_mask = False
+        self.sort_keys = True             # B200 path: sort masked K/V streams "mask bits first" -> prefix masks
         self._tables = {}                 # (kind, S) -> (signature, bits, popcount)
         self._plans = {}                  # key -> device plan bytes
 
@@ -188,7 +189,20 @@ class Attention_Modulator(AttentionControl):
             ops.PLAN_REGISTRY[p.data_ptr()] = host      # host copy for FLOP accounting (bench.py)
         return p
 
-    def _attend(self, query, key, value, plan, bits=None, pop=None):
+    def _kv_index(self, kind: str, seq: int, bits, stream_masks):
+        """Cached row-gather index that sorts the keys of the masked K/V streams "mask bits first" (plans.kv_sort_index)
+        for the table (kind, seq): with sorted keys the kernel's key masks are prefix lengths (FF_PASS_KEY_PREFIX)."""
+        ck = (kind, "kvidx", seq)
+        hit = self._tables.get(ck)
+        if hit is not None and hit[0] is bits:
+            return hit[1]
+        shifts = torch.arange(32, device=bits.device, dtype=torch.int32)
+        key_bits = ((bits[:, :, None] >> shifts) & 1).reshape(bits.shape[0], -1)[:, :seq]
+        idx = plans.kv_sort_index(key_bits, stream_masks)
+        self._tables[ck] = (bits, idx)
+        return idx
+
+    def _attend(self, query, key, value, plan, bits=None, pop=None, kv_index=None):
         self._device = query.device
         dt = query.dtype
         if dt not in (torch.float32, torch.bfloat16):
@@ -196,6 +210,11 @@ class Attention_Modulator(AttentionControl):
         q = query.to(torch.bfloat16).contiguous()
         k = key.to(torch.bfloat16).contiguous()
         v = value.to(torch.bfloat16).contiguous()
+        if kv_index is not None:
+            # sort the keys of the masked streams (softmax is permutation invariant over keys): row gather of K and V
+            Bk, Sk, Ck = k.shape
+            k = k.view(Bk * Sk, Ck).index_select(0, kv_index).view(Bk, Sk, Ck)
+            v = v.view(Bk * Sk, Ck).index_select(0, kv_index).view(Bk, Sk, Ck)
         return ops.attn_masked_kv(q, k, v, plan, self.heads, self.scale, bits, pop, out_dtype=dt)
 
     def plain_attention(self, query, key, value):
@@ -230,9 +249,13 @@ class Attention_Modulator(AttentionControl):
         if bits.shape[0] not in (2 * E if kind == "edit" else E,):
             raise ValueError(f"{E} edits in the stream batch but masks for {bits.shape[0]} rows")
         cg = None if self.method == 'mmsa' else float(self.context_guidance)
-        plan = self._plan((kind, E, self.heads, self.method, cg),
-                          lambda: plans.tca_plan(E, self.heads, self.method, cg, src_id, tgt_id, kind=kind))
-        out = self._attend(query, key, value, plan, bits, pop)
+        pf = self.sort_keys
+        plan = self._plan((kind, E, self.heads, self.method, cg, pf),
+                          lambda: plans.tca_plan(E, self.heads, self.method, cg, src_id, tgt_id, kind=kind, prefix=pf))
+        kv_index = None
+        if pf:   # the ref streams (u_r, c_r) supply every masked pass: sort their keys by the edit's key mask
+            kv_index = self._kv_index(kind, S, bits, [src_id(s // 4) if s % 2 else -1 for s in range(B)])
+        out = self._attend(query, key, value, plan, bits, pop, kv_index)
         self._advance()
         return out
 
@@ -258,10 +281,12 @@ class Attention_Modulator(AttentionControl):
         # one "edit" whose table rows are [src_0..src_{N-1}, tgt_0..tgt_{N-1}]
         bits, pop = self._table("compose", S, [m for m in src] + [m for m in tgt])
         cg = None if self.method == 'mmsa' else float(self.context_guidance)
-        plan = self._plan(("compose", N, self.heads, self.method, cg),
+        pf = self.sort_keys
+        plan = self._plan(("compose", N, self.heads, self.method, cg, pf),
                           lambda: plans.compose_plan(N, self.heads, self.method, cg, list(range(N)),
-                                                     list(range(N, 2 * N))))
-        out = self._attend(query, key, value, plan, bits, pop)
+                                                     list(range(N, 2 * N)), prefix=pf))
+        kv_index = self._kv_index("compose", S, bits, [-1] + list(range(N)) + [-1]) if pf else None
+        out = self._attend(query, key, value, plan, bits, pop, kv_index)
         self._advance()
         return out
 
@@ -276,9 +301,11 @@ class Attention_Modulator(AttentionControl):
         if self.method == 'sdsa':
             bits, pop = self._table("sdsa", S, [mask])
             src_id = lambda e: e
-        plan = self._plan(("style", E, self.heads, self.method),
-                          lambda: plans.style_align_plan(E, self.heads, src_id))
-        out = self._attend(query, key, value, plan, bits, pop)
+        pf = self.sort_keys and src_id is not None
+        plan = self._plan(("style", E, self.heads, self.method, pf),
+                          lambda: plans.style_align_plan(E, self.heads, src_id, prefix=pf))
+        kv_index = self._kv_index("sdsa", S, bits, [s // 4 if s % 2 else -1 for s in range(B)]) if pf else None
+        out = self._attend(query, key, value, plan, bits, pop, kv_index)
         self._advance()
         return out
 

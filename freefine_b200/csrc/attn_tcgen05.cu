@@ -181,30 +181,126 @@ struct KParams {
   float scale_log2;   // scale * log2(e)
 };
 
-// Pass-level decisions every role must take identically.
-struct PassInfo {
-  int kv[2];       // stream of each KV segment (-1: no such segment)
-  bool active;
+// ---------------------------------------------------------------------------------------------------------------
+// Per-pass / per-tile decisions.  EVERY role (TMA producer, MMA issuer, softmax warps) evaluates these identically,
+// so that skipped K/V tiles are skipped by all of them without any communication.
+//
+//   keybit(k)   = bit k of the pass's key mask (bit-vector mode)  or  k < T (PREFIX mode: the caller sorted the keys
+//                 of that stream so that the T = popcount set keys come first -- softmax is permutation invariant)
+//   rowflip(q)  = ROW_XOR & rowbit(q)
+//   allowed(q,k)= keybit(k) ^ KEY_INVERT ^ rowflip(q)
+// A 128-key tile is IN (all keybits 1), OUT (all 0) or MIX; a ragged last tile is always MIX.  For IN/OUT tiles the
+// mask degenerates to ONE predicate per query row (no per-element work at all); the tile is skipped entirely when
+// that predicate is false for every row of the query tile.  Only MIX tiles evaluate bits per element.
+// ---------------------------------------------------------------------------------------------------------------
+enum { TILE_ALL = 0, TILE_IN = 1, TILE_OUT = 2, TILE_MIX = 3 };
+
+struct SegCtx {
+  int kv;           // K/V stream of this segment (-1: none)
+  int kmask;        // key mask id (-1: every key)
+  int T;            // popcount of the key mask
+  bool kinv, prefix;
 };
-__device__ __forceinline__ PassInfo pass_info(const FFAttnPass& ps, const KParams& p, int q0) {
-  PassInfo pi;
-  pi.kv[0] = ps.kv_stream;
-  pi.kv[1] = ps.kv_stream2;
-  pi.active = true;
-  if ((ps.flags & FF_PASS_ROW_WEIGHT) && ps.row_mask >= 0) {
-    // the pass contributes roww(q)=rowbit(q): skip it when no row of this tile is inside the region
-    uint32_t any = 0;
-    for (int c = 0; c < BM / 32; ++c) {
-      const int base = q0 + 32 * c;
+struct PassCtx {
+  SegCtx s0, s1;
+  bool rowxor, active, two_seg;
+  bool has_rf0, has_rf1;   // the query tile has (valid) rows with rowflip 0 / 1
+};
+
+__device__ __forceinline__ PassCtx make_ctx(const FFAttnPass& ps, const KParams& p, int q0) {
+  PassCtx c;
+  c.s0.kv = ps.kv_stream;
+  c.s1.kv = ps.kv_stream2;
+  c.two_seg = ps.kv_stream2 >= 0;
+  c.s0.kmask = ps.key_mask;
+  c.s1.kmask = ps.key_mask2;
+  c.s0.kinv = (ps.flags & FF_PASS_KEY_INVERT) != 0;
+  c.s1.kinv = (ps.flags & FF_PASS_KEY2_INVERT) != 0;
+  c.s0.prefix = (ps.flags & FF_PASS_KEY_PREFIX) != 0;
+  c.s1.prefix = (ps.flags & FF_PASS_KEY2_PREFIX) != 0;
+  c.s0.T = ps.key_mask >= 0 ? __ldg(p.popc + ps.key_mask) : 0;
+  c.s1.T = ps.key_mask2 >= 0 ? __ldg(p.popc + ps.key_mask2) : 0;
+  c.rowxor = (ps.flags & FF_PASS_ROW_XOR) != 0 && ps.row_mask >= 0;
+  c.active = true;
+  c.has_rf0 = true;
+  c.has_rf1 = false;
+  if (ps.row_mask >= 0 && (c.rowxor || (ps.flags & FF_PASS_ROW_WEIGHT))) {
+    uint32_t any1 = 0, any0 = 0;
+    for (int w = 0; w < BM / 32; ++w) {
+      const int base = q0 + 32 * w;
       if (base >= p.s_q) break;
-      uint32_t w = __ldg(p.bitmasks + (size_t)ps.row_mask * p.mask_words + (base >> 5));
+      const uint32_t bits = __ldg(p.bitmasks + (size_t)ps.row_mask * p.mask_words + (base >> 5));
       const int rem = p.s_q - base;
-      if (rem < 32) w &= (1u << rem) - 1u;
-      any |= w;
+      const uint32_t valid = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+      any1 |= bits & valid;
+      any0 |= ~bits & valid;
     }
-    pi.active = any != 0;
+    if (ps.flags & FF_PASS_ROW_WEIGHT) c.active = any1 != 0;   // roww(q) = rowbit(q): nothing to add for this tile
+    if (c.rowxor) {
+      c.has_rf0 = any0 != 0;
+      c.has_rf1 = any1 != 0;
+    }
   }
-  return pi;
+  return c;
+}
+
+// quirk Q4: is the allowed set of rows with flip value f EMPTY (=> those rows attend uniformly to every key)?
+__device__ __forceinline__ bool uniform_for(const PassCtx& c, const SegCtx& g, bool f, int s_kv) {
+  if (c.two_seg || g.kmask < 0) return false;
+  return (f ? s_kv - g.T : g.T) == 0;
+}
+
+__device__ __forceinline__ int tile_class(const SegCtx& g, int j, const KParams& p) {
+  const int lo = j * BN;
+  if (lo + BN > p.s_kv) return TILE_MIX;                    // ragged tile: invalid columns need per-element masking
+  if (g.kmask < 0) return TILE_ALL;
+  if (g.prefix) return lo + BN <= g.T ? TILE_IN : (lo >= g.T ? TILE_OUT : TILE_MIX);
+  uint32_t a = 0xffffffffu, o = 0;
+  for (int w = 0; w < BN / 32; ++w) {
+    const uint32_t bits = __ldg(p.bitmasks + (size_t)g.kmask * p.mask_words + (lo >> 5) + w);
+    a &= bits;
+    o |= bits;
+  }
+  return a == 0xffffffffu ? TILE_IN : (o == 0 ? TILE_OUT : TILE_MIX);
+}
+
+// one predicate per row for IN/OUT/ALL tiles
+__device__ __forceinline__ bool row_allowed(int cls, bool flip, bool uniform) {
+  return uniform || cls == TILE_ALL || ((cls == TILE_IN) != flip);
+}
+
+__device__ __forceinline__ bool tile_skip(const PassCtx& c, const SegCtx& g, int cls, int s_kv) {
+  if (cls == TILE_MIX || cls == TILE_ALL) return false;
+  bool need = false;
+  if (c.has_rf0) need = need || row_allowed(cls, g.kinv, uniform_for(c, g, g.kinv, s_kv));
+  if (c.has_rf1) need = need || row_allowed(cls, !g.kinv, uniform_for(c, g, !g.kinv, s_kv));
+  return !need;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&b);
+}
+
+// 16 scores -> exp2(s*sc + nb), row-sum, P as hi/lo bf16 pairs.  MASKED: bit i of `bits` gates key i.
+template <bool MASKED>
+__device__ __forceinline__ void softmax_chunk(const float (&s)[16], uint32_t (&hl)[16], float sc, float nb,
+                                              uint32_t bits, float2& la, float2& lb) {
+  const float2 sc2 = make_float2(sc, sc), nb2 = make_float2(nb, nb);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float2 x = __ffma2_rn(make_float2(s[2 * i], s[2 * i + 1]), sc2, nb2);
+    if (MASKED) {
+      x.x = (bits >> (2 * i)) & 1u ? x.x : -INFINITY;
+      x.y = (bits >> (2 * i + 1)) & 1u ? x.y : -INFINITY;
+    }
+    const float2 e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+    if (i & 1) lb = __fadd2_rn(lb, e); else la = __fadd2_rn(la, e);
+    const uint32_t b0 = __float_as_uint(e.x), b1 = __float_as_uint(e.y);
+    hl[i] = __byte_perm(b0, b1, 0x7632);                         // hi: truncated upper halves, key 2i in the low half
+    const float2 r = __fadd2_rn(e, make_float2(-__uint_as_float(b0 & 0xffff0000u), -__uint_as_float(b1 & 0xffff0000u)));
+    hl[8 + i] = pack_bf16x2(r.x, r.y);                           // lo = bf16(p - hi)
+  }
 }
 
 template <int DPAD>
@@ -268,13 +364,18 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       for (int kt = 0; kt < C::NKT; ++kt)
         tma_load_4d(sQ + kt * TILE_BYTES, &tm_q, kt * BOX_COLS, head, q0, stream, bar_q);
       int it = 0;
+#pragma unroll 1
       for (int ip = 0; ip < n_pass; ++ip) {
         const FFAttnPass ps = plan->pass[ip];
-        const PassInfo pi = pass_info(ps, p, q0);
-        if (!pi.active) continue;
+        const PassCtx cx = make_ctx(ps, p, q0);
+        if (!cx.active) continue;
+#pragma unroll 1
         for (int seg = 0; seg < 2; ++seg) {
-          if (pi.kv[seg] < 0) continue;
-          for (int j = 0; j < n_kv_tiles; ++j, ++it) {
+          const SegCtx sg = seg ? cx.s1 : cx.s0;
+          if (sg.kv < 0) continue;
+#pragma unroll 1
+          for (int j = 0; j < n_kv_tiles; ++j) {
+            if (tile_skip(cx, sg, tile_class(sg, j, p), p.s_kv)) continue;
             const int stage = it % C::NSTAGE, use = it / C::NSTAGE;
             FF_TRACE(it, 10);
             if (use > 0) mbar_wait(bar_kv_empty + 8 * stage, (use - 1) & 1);
@@ -283,9 +384,10 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             const uint32_t sK = sKV + stage * C::SMEM_STAGE, sV = sK + C::NKT * TILE_BYTES;
             mbar_expect_tx(full, 2 * C::NKT * TILE_BYTES);
             for (int kt = 0; kt < C::NKT; ++kt) {
-              tma_load_4d(sK + kt * TILE_BYTES, &tm_k, kt * BOX_COLS, head, j * BN, pi.kv[seg], full);
-              tma_load_4d(sV + kt * TILE_BYTES, &tm_v, kt * BOX_COLS, head, j * BN, pi.kv[seg], full);
+              tma_load_4d(sK + kt * TILE_BYTES, &tm_k, kt * BOX_COLS, head, j * BN, sg.kv, full);
+              tma_load_4d(sV + kt * TILE_BYTES, &tm_v, kt * BOX_COLS, head, j * BN, sg.kv, full);
             }
+            ++it;
           }
         }
       }
@@ -298,14 +400,19 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       FF_TRACE(0, 20);
       mbar_wait(bar_q, 0);
       int it = 0;
+#pragma unroll 1
       for (int ip = 0; ip < n_pass; ++ip) {
         const FFAttnPass ps = plan->pass[ip];
-        const PassInfo pi = pass_info(ps, p, q0);
-        if (!pi.active) continue;
+        const PassCtx cx = make_ctx(ps, p, q0);
+        if (!cx.active) continue;
         bool first = true;
+#pragma unroll 1
         for (int seg = 0; seg < 2; ++seg) {
-          if (pi.kv[seg] < 0) continue;
-          for (int j = 0; j < n_kv_tiles; ++j, ++it) {
+          const SegCtx sg = seg ? cx.s1 : cx.s0;
+          if (sg.kv < 0) continue;
+#pragma unroll 1
+          for (int j = 0; j < n_kv_tiles; ++j) {
+            if (tile_skip(cx, sg, tile_class(sg, j, p), p.s_kv)) continue;
             const int stage = it % C::NSTAGE, use = it / C::NSTAGE;
             const uint32_t sK = sKV + stage * C::SMEM_STAGE, sV = sK + C::NKT * TILE_BYTES;
             FF_TRACE(it, 21);
@@ -338,6 +445,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             tc_commit(bar_kv_empty + 8 * stage);
             tc_commit(bar_o);
             first = false;
+            ++it;
           }
         }
       }
@@ -355,77 +463,88 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     }
     bool acc_started = false;   // ACC_TMEM: has any pass been added yet (uniform across the CTA)
     int it = 0;
+#pragma unroll 1
     for (int ip = 0; ip < n_pass; ++ip) {
       const FFAttnPass ps = plan->pass[ip];
-      const PassInfo pi = pass_info(ps, p, q0);
-      if (!pi.active) continue;
+      const PassCtx cx = make_ctx(ps, p, q0);
+      if (!cx.active) continue;
       // ---- per-row constants of this pass
       uint32_t rb = 0;
       if (ps.row_mask >= 0 && row < p.s_q)
         rb = (__ldg(p.bitmasks + (size_t)ps.row_mask * p.mask_words + (row >> 5)) >> (row & 31)) & 1u;
-      const bool row_flip = (ps.flags & FF_PASS_ROW_XOR) && rb;
-      float m_used = -INFINITY, l = 0.f;
+      const bool rowflip = cx.rowxor && rb;
+      float m_used = 0.f;
+      float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
       bool first = true;
+#pragma unroll 1
       for (int seg = 0; seg < 2; ++seg) {
-        if (pi.kv[seg] < 0) continue;
-        const int kmask = seg == 0 ? ps.key_mask : ps.key_mask2;
-        const bool kinv = (ps.flags & (seg == 0 ? FF_PASS_KEY_INVERT : FF_PASS_KEY2_INVERT)) != 0;
-        const bool flip = kinv != row_flip;
-        // quirk Q4: a row whose allowed set is empty attends uniformly to every key
-        bool uniform = false;
-        if (kmask >= 0 && pi.kv[1] < 0) {
-          const int cnt = __ldg(p.popc + kmask);
-          uniform = (flip ? p.s_kv - cnt : cnt) == 0;
-        }
+        const SegCtx sg = seg ? cx.s1 : cx.s0;
+        if (sg.kv < 0) continue;
+        const bool flip = sg.kinv != rowflip;
+        const bool uniform = uniform_for(cx, sg, flip, p.s_kv);   // quirk Q4 (per row: depends on its flip value)
         const float sc = uniform ? 0.f : p.scale_log2;
-        for (int j = 0; j < n_kv_tiles; ++j, ++it) {
-          // ---- allowed-key words of this tile for this row
-          uint32_t aw[4];
-          bool all_on = true;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int kbase = j * BN + 32 * c;
-            const int rem = p.s_kv - kbase;
-            const uint32_t valid = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
-            uint32_t w = 0xffffffffu;
-            if (kmask >= 0 && !uniform && rem > 0) {
-              w = __ldg(p.bitmasks + (size_t)kmask * p.mask_words + (kbase >> 5));
-              if (flip) w = ~w;
-            }
-            aw[c] = w & valid;
-            all_on = all_on && (aw[c] == 0xffffffffu);
-          }
-          const bool fast = __all_sync(0xffffffffu, all_on);
-
+#pragma unroll 1
+        for (int j = 0; j < n_kv_tiles; ++j) {
+          const int cls = tile_class(sg, j, p);
+          if (tile_skip(cx, sg, cls, p.s_kv)) continue;
           FF_TRACE(it, 30);
           mbar_wait(bar_s, it & 1);
           FF_TRACE(it, 31);
           tc_fence_after();
-          // ---- sweep 1: row max over the allowed keys (raw scores)
-          float mt = -INFINITY;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float s[32];
-            tmem_ld32(tlane + C::TMEM_S + 32 * c, s);
+          // ---- sweep 1: row max over ALL 128 columns (an upper bound of the max over the allowed keys is all the
+          // softmax needs: bf16/fp32 keep their relative precision whatever the reference point; padded columns are 0)
+          float mt;
+          {
+            float sa[32], sb[32];
+            float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+            tmem_ld32(tlane + C::TMEM_S, sa);
             tmem_wait_ld();
-            if (fast) {
+            tmem_ld32(tlane + C::TMEM_S + 32, sb);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) mt = fmaxf(mt, s[i]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) mt = fmaxf(mt, (aw[c] >> i) & 1u ? s[i] : -INFINITY);
+            for (int i = 0; i < 32; i += 8) {
+              m0 = fmaxf(m0, fmaxf(sa[i], sa[i + 1]));
+              m1 = fmaxf(m1, fmaxf(sa[i + 2], sa[i + 3]));
+              m2 = fmaxf(m2, fmaxf(sa[i + 4], sa[i + 5]));
+              m3 = fmaxf(m3, fmaxf(sa[i + 6], sa[i + 7]));
             }
+            tmem_wait_ld();
+            tmem_ld32(tlane + C::TMEM_S + 64, sa);
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              m0 = fmaxf(m0, fmaxf(sb[i], sb[i + 1]));
+              m1 = fmaxf(m1, fmaxf(sb[i + 2], sb[i + 3]));
+              m2 = fmaxf(m2, fmaxf(sb[i + 4], sb[i + 5]));
+              m3 = fmaxf(m3, fmaxf(sb[i + 6], sb[i + 7]));
+            }
+            tmem_wait_ld();
+            tmem_ld32(tlane + C::TMEM_S + 96, sb);
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              m0 = fmaxf(m0, fmaxf(sa[i], sa[i + 1]));
+              m1 = fmaxf(m1, fmaxf(sa[i + 2], sa[i + 3]));
+              m2 = fmaxf(m2, fmaxf(sa[i + 4], sa[i + 5]));
+              m3 = fmaxf(m3, fmaxf(sa[i + 6], sa[i + 7]));
+            }
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              m0 = fmaxf(m0, fmaxf(sb[i], sb[i + 1]));
+              m1 = fmaxf(m1, fmaxf(sb[i + 2], sb[i + 3]));
+              m2 = fmaxf(m2, fmaxf(sb[i + 4], sb[i + 5]));
+              m3 = fmaxf(m3, fmaxf(sb[i + 6], sb[i + 7]));
+            }
+            mt = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
           }
-          const float mts = uniform ? ((aw[0] | aw[1] | aw[2] | aw[3]) ? 0.f : -INFINITY) : mt * p.scale_log2;
-          // ---- running max, lazy rescale of O (TMEM read-modify-write only when the max grew by > 2^8)
+          const float mts = uniform ? 0.f : mt * p.scale_log2;
+          // ---- running reference point, lazy rescale of O (TMEM read-modify-write only when it grew by > 2^8)
           float alpha = 1.f;
           bool grow = false;
-          if (first || m_used == -INFINITY) {
-            m_used = mts;        // nothing accumulated for this row yet: its O row is exactly 0 (or about to be overwritten)
+          if (first) {
+            m_used = mts;
           } else if (mts > m_used + RESCALE_THRESHOLD) {
             alpha = fast_exp2(m_used - mts);
             m_used = mts;
-            l *= alpha;
+            la.x *= alpha; la.y *= alpha; lb.x *= alpha; lb.y *= alpha;
             grow = true;
           }
           if (__any_sync(0xffffffffu, grow)) {
@@ -444,49 +563,70 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
               tmem_st16(tlane + C::TMEM_O + 16 * c, ob);
             }
           }
-          const float mref = m_used == -INFINITY ? 0.f : m_used;
           // ---- sweep 2: p = 2^(s*scale*log2e - m), row sum.  P goes to the tensor core as TWO bf16 operands,
           // p = hi + lo (hi = truncated upper 16 bits, lo = bf16(p - hi)): 16 mantissa bits instead of 8, so the
-          // result stays within the fp32-reference tolerance; the second PV MMA rides on tensor-pipe slack (the
-          // tile is exp-bound).  The 16 keys of K-step ks (S columns [16ks,16ks+16)) are overwritten in place by
-          // hi -> [16ks,16ks+8) and lo -> [16ks+8,16ks+16): only columns this thread has already consumed.
-#pragma unroll
-          for (int ks = 0; ks < BN / 16; ++ks) {
-            float s[16];
+          // result stays within the fp32-reference tolerance; the second PV MMA rides on tensor-pipe slack.  The 16
+          // keys of K-step ks (S columns [16ks,16ks+16)) are overwritten in place by hi -> [16ks,16ks+8) and
+          // lo -> [16ks+8,16ks+16): only columns this thread has already consumed.
+          if (cls != TILE_MIX) {
+            // one predicate per row: bias -m (allowed) or -inf (row reads nothing from this tile -> p = 0)
+            const float nb = row_allowed(cls, flip, uniform) ? -m_used : -INFINITY;
+            float ca[16], cb[16];
             uint32_t hl[16];
-            tmem_ld16(tlane + C::TMEM_S + 16 * ks, s);
+            tmem_ld16(tlane + C::TMEM_S, ca);
             tmem_wait_ld();
-            const uint32_t awk = aw[ks >> 1] >> (16 * (ks & 1));
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float e = fast_exp2(fmaf(s[i], sc, -mref));
-              if (!fast) e = (awk >> i) & 1u ? e : 0.f;
-              s[i] = e;
-              l += e;
+            for (int ks = 0; ks < BN / 16; ks += 2) {
+              tmem_ld16(tlane + C::TMEM_S + 16 * (ks + 1), cb);          // in flight while chunk ks is processed
+              softmax_chunk<false>(ca, hl, sc, nb, 0u, la, lb);
+              tmem_st16(tlane + C::TMEM_S + 16 * ks, hl);
+              tmem_wait_ld();
+              if (ks + 2 < BN / 16) tmem_ld16(tlane + C::TMEM_S + 16 * (ks + 2), ca);
+              softmax_chunk<false>(cb, hl, sc, nb, 0u, la, lb);
+              tmem_st16(tlane + C::TMEM_S + 16 * (ks + 1), hl);
+              if (ks + 2 < BN / 16) tmem_wait_ld();
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const uint32_t b0 = __float_as_uint(s[2 * i]), b1 = __float_as_uint(s[2 * i + 1]);
-              hl[i] = __byte_perm(b0, b1, 0x7632);                        // low half = key 2i, high half = key 2i+1
-              const float r0 = s[2 * i] - __uint_as_float(b0 & 0xffff0000u);
-              const float r1 = s[2 * i + 1] - __uint_as_float(b1 & 0xffff0000u);
-              const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
-              hl[8 + i] = *reinterpret_cast<const uint32_t*>(&l2);
+          } else {
+            // boundary / ragged tile: evaluate allowed(q,k) per element on 16-bit slices of the mask words
+            const float nb = -m_used;
+#pragma unroll 1
+            for (int ks = 0; ks < BN / 16; ++ks) {
+              const int kbase = j * BN + 16 * ks;
+              const int rem = p.s_kv - kbase;
+              const uint32_t valid = rem >= 16 ? 0xffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+              uint32_t kb = 0xffffu;
+              if (sg.kmask >= 0 && !uniform && rem > 0) {
+                if (sg.prefix) {
+                  const int t = sg.T - kbase;
+                  kb = t >= 16 ? 0xffffu : (t <= 0 ? 0u : ((1u << t) - 1u));
+                } else {
+                  kb = (__ldg(p.bitmasks + (size_t)sg.kmask * p.mask_words + (kbase >> 5)) >> (kbase & 31)) & 0xffffu;
+                }
+                if (flip) kb = ~kb;
+              }
+              float cs[16];
+              uint32_t hl[16];
+              tmem_ld16(tlane + C::TMEM_S + 16 * ks, cs);
+              tmem_wait_ld();
+              softmax_chunk<true>(cs, hl, sc, nb, kb & valid, la, lb);
+              tmem_st16(tlane + C::TMEM_S + 16 * ks, hl);
             }
-            tmem_st16(tlane + C::TMEM_S + 16 * ks, hl);
           }
           tmem_wait_st();
           tc_fence_before();
           mbar_arrive(bar_p);
           FF_TRACE(it, 34);
           first = false;
+          ++it;
         }
       }
+      if (first) continue;     // (defensive) no tile of this pass was processed: nothing to add
       // ---- end of pass: acc += weight * roww / l * O
       FF_TRACE(it, 35);
       mbar_wait(bar_o, (it - 1) & 1);
       FF_TRACE(it, 36);
       tc_fence_after();
+      const float l = (la.x + la.y) + (lb.x + lb.y);
       float coef = ps.weight;
       if (ps.flags & FF_PASS_ROW_WEIGHT) coef = rb ? coef : 0.f;
       coef = l > 0.f ? coef / l : 0.f;
@@ -542,14 +682,10 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           if (row_ok && 16 * c + 8 * g < p.head_dim) {   // head_dim % 8 == 0
             if (p.out_dtype == FF_DT_BF16) {
               uint4 v;
-              __nv_bfloat162 b0 = __floats2bfloat162_rn(o[8 * g + 0], o[8 * g + 1]);
-              __nv_bfloat162 b1 = __floats2bfloat162_rn(o[8 * g + 2], o[8 * g + 3]);
-              __nv_bfloat162 b2 = __floats2bfloat162_rn(o[8 * g + 4], o[8 * g + 5]);
-              __nv_bfloat162 b3 = __floats2bfloat162_rn(o[8 * g + 6], o[8 * g + 7]);
-              v.x = *reinterpret_cast<uint32_t*>(&b0);
-              v.y = *reinterpret_cast<uint32_t*>(&b1);
-              v.z = *reinterpret_cast<uint32_t*>(&b2);
-              v.w = *reinterpret_cast<uint32_t*>(&b3);
+              v.x = pack_bf16x2(o[8 * g + 0], o[8 * g + 1]);
+              v.y = pack_bf16x2(o[8 * g + 2], o[8 * g + 3]);
+              v.z = pack_bf16x2(o[8 * g + 4], o[8 * g + 5]);
+              v.w = pack_bf16x2(o[8 * g + 6], o[8 * g + 7]);
               *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + o_off + 16 * c + 8 * g) = v;
             } else {
               float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + o_off + 16 * c + 8 * g);

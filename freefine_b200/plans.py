@@ -17,8 +17,8 @@ from __future__ import annotations
 
 import numpy as np
 
-from ._lib import (FF_MAX_PASS, FF_PASS_KEY2_INVERT, FF_PASS_KEY_INVERT, FF_PASS_ROW_WEIGHT, FF_PASS_ROW_XOR,
-                   PLAN_BYTES)
+from ._lib import (FF_MAX_PASS, FF_PASS_KEY2_INVERT, FF_PASS_KEY2_PREFIX, FF_PASS_KEY_INVERT, FF_PASS_KEY_PREFIX,
+                   FF_PASS_ROW_WEIGHT, FF_PASS_ROW_XOR, PLAN_BYTES)
 
 PASS_DTYPE = np.dtype([("kv_stream", "<i4"), ("key_mask", "<i4"), ("row_mask", "<i4"), ("flags", "<u4"),
                        ("weight", "<f4"), ("kv_stream2", "<i4"), ("key_mask2", "<i4"), ("reserved", "<i4")])
@@ -62,13 +62,18 @@ def plain_plan(n_streams: int, heads: int, kv_of=None) -> np.ndarray:
     return p
 
 
-def tca_plan(n_edits: int, heads: int, method: str, cg, src_id, tgt_id, kind: str = "edit") -> np.ndarray:
+def tca_plan(n_edits: int, heads: int, method: str, cg, src_id, tgt_id, kind: str = "edit",
+             prefix: bool = False) -> np.ndarray:
     """Temporal_contextal_attention (attention.py:1043-1091) / _bg (:1284-1324) for n_edits edits of 4 streams.
 
     src_id(e) / tgt_id(e): bit-vector ids of edit e's fg_ref_mask (keys) and fg_retain_mask (rows); for kind='bg'
     src_id is the object mask (allowed keys = NOT object for every row) and tgt_id is unused.
     method 'mmsa': out = O_ref;  'tca': out = cg*O_ref + (1-cg)*O_self.
+    prefix=True: the caller hands the kernel K,V whose ref-stream rows are sorted "source keys first"
+    (kv_sort_index), so key masks become prefix lengths (FF_PASS_KEY_PREFIX): no per-element mask work, all-masked
+    K/V tiles are skipped.
     """
+    pf = FF_PASS_KEY_PREFIX if prefix else 0
     if method not in ("tca", "mmsa"):
         raise ValueError(f"method must be 'tca' or 'mmsa', got {method!r}")
     if kind not in ("edit", "bg"):
@@ -89,9 +94,9 @@ def tca_plan(n_edits: int, heads: int, method: str, cg, src_id, tgt_id, kind: st
                 if masked and kind == "edit":
                     # allowed(q,k) = (tgt[q] == src[k]) = src[k] ^ 1 ^ tgt[q]
                     _add(p, s, h, r, w_ref, key_mask=src_id(e), row_mask=tgt_id(e),
-                         flags=FF_PASS_KEY_INVERT | FF_PASS_ROW_XOR)
+                         flags=FF_PASS_KEY_INVERT | FF_PASS_ROW_XOR | pf)
                 elif masked:
-                    _add(p, s, h, r, w_ref, key_mask=src_id(e), flags=FF_PASS_KEY_INVERT)
+                    _add(p, s, h, r, w_ref, key_mask=src_id(e), flags=FF_PASS_KEY_INVERT | pf)
                 else:
                     _add(p, s, h, r, w_ref)
                 if method == "tca":
@@ -99,7 +104,7 @@ def tca_plan(n_edits: int, heads: int, method: str, cg, src_id, tgt_id, kind: st
     return p
 
 
-def compose_plan(n_src: int, heads: int, method: str, cg, src_ids, tgt_ids) -> np.ndarray:
+def compose_plan(n_src: int, heads: int, method: str, cg, src_ids, tgt_ids, prefix: bool = False) -> np.ndarray:
     """Temporal_contextal_attention_compose (attention.py:1092-1140): streams [u_e, r_1..r_N, c_e]; the two edit
     streams get sum_i tgt_i(q) * softmax_{k in src_i}(q K_{r_i}) V_{r_i}; ref streams plain self-attention.  No Q0."""
     if method not in ("tca", "mmsa"):
@@ -111,7 +116,8 @@ def compose_plan(n_src: int, heads: int, method: str, cg, src_ids, tgt_ids) -> n
             if s in (0, B - 1):
                 w_new = 1.0 if method == "mmsa" else float(cg)
                 for i in range(n_src):
-                    _add(p, s, h, 1 + i, w_new, key_mask=src_ids[i], row_mask=tgt_ids[i], flags=FF_PASS_ROW_WEIGHT)
+                    _add(p, s, h, 1 + i, w_new, key_mask=src_ids[i], row_mask=tgt_ids[i],
+                         flags=FF_PASS_ROW_WEIGHT | (FF_PASS_KEY_PREFIX if prefix else 0))
                 if method == "tca":
                     _add(p, s, h, s, 1.0 - float(cg))
             else:
@@ -119,7 +125,7 @@ def compose_plan(n_src: int, heads: int, method: str, cg, src_ids, tgt_ids) -> n
     return p
 
 
-def style_align_plan(n_edits: int, heads: int, src_id=None) -> np.ndarray:
+def style_align_plan(n_edits: int, heads: int, src_id=None, prefix: bool = False) -> np.ndarray:
     """style_align_share_attention (attention.py:1142-1192): keys/values [self ; ref] under ONE softmax; with
     src_id (SDSA) the ref half is masked by fg_ref_mask on the Q0-masked (stream, head) pairs (:940-951)."""
     p = _empty(4 * n_edits, heads)
@@ -129,8 +135,25 @@ def style_align_plan(n_edits: int, heads: int, src_id=None) -> np.ndarray:
             r = 4 * e + (1 if sl < 2 else 3)
             for h in range(heads):
                 km2 = src_id(e) if (src_id is not None and q0_masked(heads, sl, h)) else -1
-                _add(p, s, h, s, 1.0, kv2=r, key_mask2=km2)
+                _add(p, s, h, s, 1.0, kv2=r, key_mask2=km2, flags=FF_PASS_KEY2_PREFIX if (prefix and km2 >= 0) else 0)
     return p
+
+
+def kv_sort_index(key_bits, stream_masks) -> "torch.Tensor":
+    """Row-gather index that sorts the keys of the masked K/V streams "set bits first" (stable), identity elsewhere.
+
+    key_bits: bool/uint8 tensor [n_masks, S] (token-resolution masks, e.g. unpacked from ff_mask_downsample_pack);
+    stream_masks: list of length n_kv_streams, entry = mask row that orders that stream's keys, or -1 (keep order).
+    Returns int64 [n_kv_streams * S] flat row indices into the [n_kv_streams*S, C] view of K / V.  Softmax is
+    permutation invariant over keys, so attention over (K[idx], V[idx]) with prefix masks equals attention over (K, V)
+    with the bit-vector masks."""
+    import torch
+    n, S = key_bits.shape
+    order = torch.sort(key_bits.to(torch.uint8), dim=1, descending=True, stable=True).indices      # [n_masks, S]
+    ident = torch.arange(S, device=key_bits.device)
+    rows = [order[m] if m >= 0 else ident for m in stream_masks]
+    base = (torch.arange(len(stream_masks), device=key_bits.device) * S)[:, None]
+    return (torch.stack(rows) + base).reshape(-1)
 
 
 def algorithmic_flops(plan: np.ndarray, s_q: int, s_kv: int, d: int, popcount=None) -> float:
@@ -178,4 +201,5 @@ def describe(plan: np.ndarray) -> str:
 
 
 __all__ = ["PASS_DTYPE", "PLAN_DTYPE", "q0_masked", "plain_plan", "tca_plan", "compose_plan", "style_align_plan",
-           "describe", "FF_PASS_KEY_INVERT", "FF_PASS_ROW_XOR", "FF_PASS_ROW_WEIGHT", "FF_PASS_KEY2_INVERT"]
+           "kv_sort_index", "algorithmic_flops", "describe", "FF_PASS_KEY_INVERT", "FF_PASS_ROW_XOR", "FF_PASS_ROW_WEIGHT",
+           "FF_PASS_KEY2_INVERT", "FF_PASS_KEY_PREFIX", "FF_PASS_KEY2_PREFIX"]

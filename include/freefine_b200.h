@@ -67,7 +67,11 @@ enum {
   FF_PASS_KEY_INVERT = 1u,  /* allowed = NOT keybit                                               */
   FF_PASS_ROW_XOR = 2u,     /* allowed ^= rowbit  (rows inside the region read the complement set) */
   FF_PASS_ROW_WEIGHT = 4u,  /* multiply the pass output by rowbit (compose: sum_i tgt_i(q) * O_i)   */
-  FF_PASS_KEY2_INVERT = 8u  /* KEY_INVERT for the second segment                                  */
+  FF_PASS_KEY2_INVERT = 8u, /* KEY_INVERT for the second segment                                  */
+  FF_PASS_KEY_PREFIX = 16u, /* the caller SORTED the keys of kv_stream so that the popcount[key_mask] set keys   */
+                            /* come first: keybit(k) = k < popcount[key_mask] (no bit-vector read; whole K/V     */
+                            /* tiles become all-in / all-out and are skipped or processed without mask work)     */
+  FF_PASS_KEY2_PREFIX = 32u /* same for the second segment                                        */
 };
 
 typedef struct FFAttnPass {

@@ -5,7 +5,8 @@ Never imported by the product."""
 import numpy as np
 import torch
 
-from freefine_b200.plans import (FF_PASS_KEY2_INVERT, FF_PASS_KEY_INVERT, FF_PASS_ROW_WEIGHT, FF_PASS_ROW_XOR)
+from freefine_b200.plans import (FF_PASS_KEY2_INVERT, FF_PASS_KEY2_PREFIX, FF_PASS_KEY_INVERT, FF_PASS_KEY_PREFIX,
+                                 FF_PASS_ROW_WEIGHT, FF_PASS_ROW_XOR)
 
 
 def unpack_bits(words: np.ndarray, n: int) -> np.ndarray:
@@ -23,8 +24,11 @@ def run_plan(q, k, v, plan, heads, scale, bitmasks=None):
     kh = k.reshape(k.shape[0], Skv, heads, d)
     vh = v.reshape(v.shape[0], Skv, heads, d)
 
-    def kbits(mid, S):
-        return torch.ones(S, dtype=torch.bool) if mid < 0 else torch.from_numpy(unpack_bits(bitmasks[mid], S))
+    def kbits(mid, S, prefix=False):
+        if mid < 0:
+            return torch.ones(S, dtype=torch.bool)
+        b = torch.from_numpy(unpack_bits(bitmasks[mid], S))
+        return (torch.arange(S) < int(b.sum())) if prefix else b      # PREFIX: keys were sorted "set bits first"
 
     for s in range(B):
         for h in range(heads):
@@ -34,14 +38,15 @@ def run_plan(q, k, v, plan, heads, scale, bitmasks=None):
                 flags = int(ps["flags"])
                 rb = (torch.zeros(Sq, dtype=torch.bool) if ps["row_mask"] < 0
                       else torch.from_numpy(unpack_bits(bitmasks[int(ps["row_mask"])], Sq)))
-                segs = [(int(ps["kv_stream"]), int(ps["key_mask"]), bool(flags & FF_PASS_KEY_INVERT))]
+                segs = [(int(ps["kv_stream"]), int(ps["key_mask"]), bool(flags & FF_PASS_KEY_INVERT), bool(flags & FF_PASS_KEY_PREFIX))]
                 if ps["kv_stream2"] >= 0:
-                    segs.append((int(ps["kv_stream2"]), int(ps["key_mask2"]), bool(flags & FF_PASS_KEY2_INVERT)))
+                    segs.append((int(ps["kv_stream2"]), int(ps["key_mask2"]), bool(flags & FF_PASS_KEY2_INVERT),
+                                 bool(flags & FF_PASS_KEY2_PREFIX)))
                 ks, vs, al = [], [], []
-                for kv, km, inv in segs:
+                for kv, km, inv, pfx in segs:
                     ks.append(kh[kv, :, h])
                     vs.append(vh[kv, :, h])
-                    a = kbits(km, Skv)[None, :].expand(Sq, Skv)
+                    a = kbits(km, Skv, pfx)[None, :].expand(Sq, Skv)
                     if inv:
                         a = ~a
                     if flags & FF_PASS_ROW_XOR:

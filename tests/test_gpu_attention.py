@@ -23,9 +23,14 @@ def dev():
     return torch.device("cuda:0")
 
 
-def _run(dev, q, k, v, plan, heads, scale, flat_masks=None, out_dtype=torch.float32):
+def _run(dev, q, k, v, plan, heads, scale, flat_masks=None, out_dtype=torch.float32, sort_streams=None):
+    """sort_streams: per K/V stream the mask row that orders its keys (prefix mode) or -1."""
     from freefine_b200 import ops
     S = max(q.shape[1], k.shape[1])
+    if sort_streams is not None:
+        idx = plans.kv_sort_index(torch.from_numpy(np.stack([np.asarray(m) != 0 for m in flat_masks])), sort_streams)
+        k = k.reshape(-1, k.shape[-1])[idx].reshape(k.shape)
+        v = v.reshape(-1, v.shape[-1])[idx].reshape(v.shape)
     bm = pc = None
     if flat_masks is not None:
         words = ops.mask_words(S)
@@ -54,6 +59,10 @@ def test_tca_golden(dev, golden, name):
     assert err < TOL, err
     ob = _run(dev, i["q"], i["k"], i["v"], plan, i["heads"], i["scale"], [src, tgt], out_dtype=torch.bfloat16)
     assert bool(((ob - ref).abs() <= TOL + 2.0 ** -8 * ref.abs()).all())
+    # sorted-key (prefix) mode: same result from K,V with the ref streams' keys sorted "source first"
+    pp = plans.tca_plan(1, i["heads"], i["method"], i["cg"], lambda e: 0, lambda e: 1, kind=i["kind"], prefix=True)
+    op = _run(dev, i["q"], i["k"], i["v"], pp, i["heads"], i["scale"], [src, tgt], sort_streams=[-1, 0, -1, 0])
+    assert float((op - ref).abs().max()) < TOL
 
 
 def test_plain_cross_compose_style_golden(dev, golden):
@@ -91,6 +100,12 @@ def test_plain_cross_compose_style_golden(dev, golden):
     assert float((out - T("style_ssa/out")).abs().max()) < TOL
     out = _run(dev, T("style/q"), T("style/k"), T("style/v"), plans.style_align_plan(1, 8, lambda e: 0), 8, sc, [src])
     assert float((out - T("style_sdsa/out")).abs().max()) < TOL
+    out = _run(dev, T("style/q"), T("style/k"), T("style/v"), plans.style_align_plan(1, 8, lambda e: 0, prefix=True), 8, sc,
+               [src], sort_streams=[-1, 0, -1, 0])
+    assert float((out - T("style_sdsa/out")).abs().max()) < TOL
+    plan = plans.compose_plan(2, 8, "tca", 0.3, [0, 1], [2, 3], prefix=True)
+    out = _run(dev, T("compose/q"), T("compose/k"), T("compose/v"), plan, 8, sc, srcs + tgts, sort_streams=[-1, 0, 1, -1])
+    assert float((out - T("compose_tca/out")).abs().max()) < TOL
 
 
 @pytest.mark.parametrize("S,d,res,method,kind", [(1024, 80, 256, "tca", "edit"), (1024, 40, 256, "tca", "edit"),
@@ -105,13 +120,15 @@ def test_tca_vs_oracle_sd15_shapes(dev, S, d, res, method, kind):
         flat.append(O.process_mask_before_attention(torch.from_numpy(cases.blob_mask(res, 700 + e)), S).numpy())      # src
         flat.append(O.process_mask_before_attention(torch.from_numpy(cases.blob_mask(res, 800 + e)), S).numpy())      # tgt
     cg = 0.55
-    plan = plans.tca_plan(E, heads, method, cg, lambda e: 2 * e, lambda e: 2 * e + 1, kind=kind)
-    out = _run(dev, q, k, v, plan, heads, d ** -0.5, flat)
-    for e in range(E):
-        sl = slice(4 * e, 4 * e + 4)
-        ref = O.tca(q[sl], k[sl], v[sl], heads, d ** -0.5, flat[2 * e], flat[2 * e + 1], method, cg, kind=kind)
-        err = float((out[sl] - ref).abs().max())
-        assert err < TOL, (e, err)
+    refs = [O.tca(q[4 * e:4 * e + 4], k[4 * e:4 * e + 4], v[4 * e:4 * e + 4], heads, d ** -0.5, flat[2 * e], flat[2 * e + 1],
+                  method, cg, kind=kind) for e in range(E)]
+    for prefix in (False, True):
+        plan = plans.tca_plan(E, heads, method, cg, lambda e: 2 * e, lambda e: 2 * e + 1, kind=kind, prefix=prefix)
+        out = _run(dev, q, k, v, plan, heads, d ** -0.5, flat,
+                   sort_streams=[2 * (s // 4) if s % 2 else -1 for s in range(4 * E)] if prefix else None)
+        for e in range(E):
+            err = float((out[4 * e:4 * e + 4] - refs[e]).abs().max())
+            assert err < TOL, (prefix, e, err)
 
 
 def test_peaked_softmax_and_large_logits(dev):
@@ -138,21 +155,25 @@ def test_full_size_properties(dev):
     for e in range(E):
         flat.append(O.process_mask_before_attention(torch.from_numpy(cases.blob_mask(512, 1100 + e, (0.08, 0.2))), S).numpy())
         flat.append(O.process_mask_before_attention(torch.from_numpy(cases.blob_mask(512, 1200 + e, (0.08, 0.2))), S).numpy())
-    plan = plans.tca_plan(E, heads, "tca", 0.4, lambda e: 2 * e, lambda e: 2 * e + 1)
+    plan = plans.tca_plan(E, heads, "tca", 0.4, lambda e: 2 * e, lambda e: 2 * e + 1, prefix=True)
+    sort = [2 * (s // 4) if s % 2 else -1 for s in range(4 * E)]
     const = torch.randn(4 * E, 1, heads * d, generator=torch.Generator().manual_seed(5)).bfloat16().float()
     # per edit the ref streams (1,3) provide V for the ref passes, the stream itself for the self pass: make V
     # constant over tokens AND equal across the 4 streams of an edit so every pass returns the same constant
     vc = const[::4].repeat_interleave(4, 0).expand(4 * E, S, heads * d).contiguous()
-    out_c = _run(dev, q, k, vc, plan, heads, d ** -0.5, flat)
+    out_c = _run(dev, q, k, vc, plan, heads, d ** -0.5, flat, sort_streams=sort)
     # (the tensor core accumulates 4096 products per row in fp32 with truncation: a few 1e-5 relative)
     assert float((out_c - vc).abs().max()) < 2e-4 * float(vc.abs().max())
-    out1 = _run(dev, q, k, v, plan, heads, d ** -0.5, flat)
-    out2 = _run(dev, q, k, (2 * v), plan, heads, d ** -0.5, flat)
+    out1 = _run(dev, q, k, v, plan, heads, d ** -0.5, flat, sort_streams=sort)
+    out2 = _run(dev, q, k, (2 * v), plan, heads, d ** -0.5, flat, sort_streams=sort)
+    out_bits = _run(dev, q, k, v, plans.tca_plan(E, heads, "tca", 0.4, lambda e: 2 * e, lambda e: 2 * e + 1), heads, d ** -0.5, flat)
+    assert float((out_bits - out1).abs().max()) < 1e-4       # bit-vector mode == sorted-key mode
     assert float((out2 - 2 * out1).abs().max()) < 1e-4
     assert bool(torch.isfinite(out1).all())
     e = 3
-    p1 = plans.tca_plan(1, heads, "tca", 0.4, lambda _: 0, lambda _: 1)
-    alone = _run(dev, q[4 * e:4 * e + 4], k[4 * e:4 * e + 4], v[4 * e:4 * e + 4], p1, heads, d ** -0.5, flat[2 * e:2 * e + 2])
+    p1 = plans.tca_plan(1, heads, "tca", 0.4, lambda _: 0, lambda _: 1, prefix=True)
+    alone = _run(dev, q[4 * e:4 * e + 4], k[4 * e:4 * e + 4], v[4 * e:4 * e + 4], p1, heads, d ** -0.5, flat[2 * e:2 * e + 2],
+                 sort_streams=[-1, 0, -1, 0])
     assert torch.equal(alone, out1[4 * e:4 * e + 4])
     # one head-slice of one stream against the oracle (seconds on CPU): masked head 0 of the cond-edit stream
     s, h = 4 * e + 2, 0

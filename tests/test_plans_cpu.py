@@ -85,3 +85,36 @@ def test_batched_edits_equal_sequential():
     for e in range(2):
         ref = O.tca(q[4 * e:4 * e + 4], k[4 * e:4 * e + 4], v[4 * e:4 * e + 4], 8, 8 ** -0.5, flat[2 * e], flat[2 * e + 1], "tca", 0.6)
         assert float((out[4 * e:4 * e + 4] - ref).abs().max()) < 2e-5
+
+
+def test_prefix_mode_sorted_keys_equals_bitmask_mode(golden):
+    """FF_PASS_KEY_PREFIX + keys sorted "mask bits first" (plans.kv_sort_index) == the bit-vector plan (softmax is
+    permutation invariant over keys)."""
+    g = golden["attention"]
+    for name in ("tca_h8_s256", "bg_tca_h8_s256", "tca_h8_s64_onekey", "tca_h8_s64_empty", "tca_h8_s64_full"):
+        i = cases.attn_case_inputs(name)
+        src, tgt = g[name + "/src_ds"], g[name + "/tgt_ds"]
+        bm = _bits(src, tgt)
+        plan = plans.tca_plan(1, i["heads"], i["method"], i["cg"], lambda e: 0, lambda e: 1, kind=i["kind"], prefix=True)
+        idx = plans.kv_sort_index(torch.from_numpy(np.stack([src, tgt]) != 0), [-1, 0, -1, 0])
+        S, C = i["k"].shape[1:]
+        ks = i["k"].reshape(-1, C)[idx].reshape(4, S, C)
+        vs = i["v"].reshape(-1, C)[idx].reshape(4, S, C)
+        out = run_plan(i["q"], ks, vs, plan, i["heads"], i["scale"], bm)
+        assert float((out - torch.from_numpy(g[name + "/out"])).abs().max()) < 5e-5, name
+    # SDSA / compose variants
+    T = lambda k: torch.from_numpy(g[k])
+    src = O.process_mask_before_attention(T("style/src"), 64).numpy()
+    idx = plans.kv_sort_index(torch.from_numpy(src[None] != 0), [-1, 0, -1, 0])
+    k, v = T("style/k"), T("style/v")
+    ks, vs = k.reshape(-1, 64)[idx].reshape(k.shape), v.reshape(-1, 64)[idx].reshape(v.shape)
+    out = run_plan(T("style/q"), ks, vs, plans.style_align_plan(1, 8, lambda e: 0, prefix=True), 8, 8 ** -0.5, _bits(src))
+    assert float((out - T("style_sdsa/out")).abs().max()) < 2e-5
+    srcs = [O.process_mask_before_attention(m, 64).numpy() for m in T("compose/srcs")]
+    tgts = [O.process_mask_before_attention(m, 64).numpy() for m in T("compose/tgts")]
+    idx = plans.kv_sort_index(torch.from_numpy(np.stack(srcs) != 0), [-1, 0, 1, -1])
+    k, v = T("compose/k"), T("compose/v")
+    ks, vs = k.reshape(-1, 64)[idx].reshape(k.shape), v.reshape(-1, 64)[idx].reshape(v.shape)
+    out = run_plan(T("compose/q"), ks, vs, plans.compose_plan(2, 8, "tca", 0.3, [0, 1], [2, 3], prefix=True), 8, 8 ** -0.5,
+                   _bits(*srcs, *tgts))
+    assert float((out - T("compose_tca/out")).abs().max()) < 2e-5

@@ -462,6 +462,122 @@ class FreeFinePipeline:
 
 
     # ------------------------------------------------------------------------------------------------------------
+    # background generation / object removal (reference model.py:656-812, :1088-1118, :1611-1620, :1751-1804);
+    # the attention side is register_attention_control_4bggen + Temporal_contextal_attention_bg
+    # ------------------------------------------------------------------------------------------------------------
+    def prepare_mask_bggen(self, mask, sup_res_w, sup_res_h, init_code):
+        """reference model.py:1611-1620"""
+        mask_tensor = self.prepare_tensor_mask(mask, sup_res_w, sup_res_h)
+        lvar = F.interpolate(mask_tensor[None, None], (init_code.shape[2], init_code.shape[3]), mode='nearest')
+        return mask_tensor, lvar.squeeze(0).squeeze(0)
+
+    @torch.no_grad()
+    def forward_sampling_background_gen(self, prompt, batch_size=1, end_step=None, height=512, width=512,
+                                        num_inference_steps=50, num_actual_inference_steps=None, guidance_scale=7.5,
+                                        latents=None, refer_latents=None, unconditioning=None, neg_prompt=None,
+                                        return_intermediates=False, eta=0.0, local_var_reg=None, local_cfg_reg=None,
+                                        local_text_edit=True, share_attn=True, method_type='tca', verbose=False,
+                                        local_perturbation=True, end_scale=0.5, latent_blended=True,
+                                        blend_range=(0, 40), **kwds):
+        """reference model.py:656-812.  The inversion ran on the source image alone (1 stream per edit); each step the
+        ref stream is refer_latents[i-start_step] (no +1 offset here: quirk Q5) and only the edit stream is kept."""
+        assert guidance_scale > 1.0, 'USING THIS MODULE CFG Must > 1.0'
+        self.method_type = method_type
+        c = self.controller
+        if share_attn:
+            if method_type == 'tca':
+                c.use_tca, c.layer_idx, c.method = True, list(range(10, 16)), 'tca'
+            elif method_type in ('mmsa', 'mmsa_es'):
+                c.use_tca, c.layer_idx, c.method = True, list(range(10, 16)), 'mmsa'
+            elif method_type == 'ssa':
+                c.use_style_align, c.method = True, 'ssa'
+            elif method_type == 'sdsa':
+                c.use_style_align, c.method = True, 'sdsa'
+        c.use_cfg = True
+        c.local_edit = local_text_edit
+        if isinstance(prompt, str) and batch_size > 1:
+            prompt = [prompt] * batch_size
+        cond = self.get_text_embeddings(prompt)
+        n2 = cond.shape[0]
+        E = n2 // 2
+        uncond = self.get_text_embeddings([neg_prompt if neg_prompt else ""] * n2)
+        text_embeddings = torch.cat([uncond.reshape(E, 2, *uncond.shape[1:]), cond.reshape(E, 2, *cond.shape[1:])],
+                                    dim=1).reshape(4 * E, *cond.shape[1:])
+        self.scheduler.set_timesteps(num_inference_steps)
+        if num_actual_inference_steps is None:
+            num_actual_inference_steps = num_inference_steps
+        start_step = num_inference_steps - num_actual_inference_steps
+        C, h, w = latents.shape[1:]
+        edit = latents.float().reshape(-1, C, h, w)[:E] if latents.shape[0] == E else latents.float().reshape(E, -1, C, h, w)[:, 0]
+        latents_list = [latents]
+        var_mask = local_var_reg if local_perturbation else torch.ones_like(local_var_reg)
+        for i, t in enumerate(self.scheduler.timesteps):
+            if i < start_step:
+                continue
+            ref = refer_latents[i - start_step].float().reshape(E, C, h, w)
+            lat = torch.stack([edit, ref], dim=1)                                   # [E,2,C,h,w]
+            if method_type == 'tca':
+                c.context_guidance = self.linear_param(i, start_step, end_step, num_inference_steps, end_scale=end_scale)
+            elif method_type == 'mmsa_es' and i >= end_step:
+                c.use_tca = False
+            model_inputs = torch.cat([lat, lat], dim=1).reshape(4 * E, C, h, w)
+            c.log_mask = False
+            noise_pred = self._unet(model_inputs, t, text_embeddings)
+            out = self.cfg_ctrl_step(noise_pred, t, lat.reshape(2 * E, C, h, w), local_cfg_reg if local_text_edit else None,
+                                     var_mask, guidance_scale, eta=eta)
+            edit = out.reshape(E, 2, C, h, w)[:, 0]
+            latents_list.append(edit if E > 1 else edit[0])
+            last = out
+        image = self.latent2image(last, return_type="pt")
+        if return_intermediates:
+            return image, latents_list
+        return image, None
+
+    def Details_Preserving_regeneration_background(self, ori_img, inverted_latents, edit_prompt, ori_mask, num_steps=100,
+                                                   start_step=30, end_step=10, guidance_scale=3.5, eta=1, verbose=False,
+                                                   local_text_edit=True, local_perturbation=True, end_scale=0.5,
+                                                   return_intermediates=False, share_attn=True, method_type='tca',
+                                                   latent_blended=True, blend_range=(0, 40)):
+        """reference model.py:1751-1804"""
+        init_code_orig = deepcopy(inverted_latents[-1])
+        full_h, full_w = ori_img.shape[:2]
+        mask_tensor, local_var_reg = self.prepare_mask_bggen(ori_mask, full_h, full_w, init_code_orig)
+        c = self.controller
+        c.fg_retain_mask = mask_tensor.to(self.device)
+        c.local_edit_region = mask_tensor.to(self.device)
+        c.reset()
+        gen_images, intermediates = self.forward_sampling_background_gen(
+            prompt=[edit_prompt, ""], end_step=end_step, batch_size=2, refer_latents=inverted_latents[::-1],
+            latents=init_code_orig, guidance_scale=guidance_scale, num_inference_steps=num_steps,
+            num_actual_inference_steps=num_steps - start_step, eta=eta, local_cfg_reg=local_var_reg,
+            local_var_reg=local_var_reg, share_attn=share_attn, method_type=method_type, verbose=verbose,
+            local_text_edit=local_text_edit, local_perturbation=local_perturbation,
+            return_intermediates=return_intermediates, end_scale=end_scale, latent_blended=latent_blended,
+            blend_range=blend_range)
+        c.reset()
+        edit = (gen_images[0].permute(1, 2, 0).detach().cpu().numpy() * 255).astype(np.uint8)
+        return edit, intermediates
+
+    def FreeFine_background_generation(self, ori_img, ori_mask, guidance_text, guidance_scale, eta, end_step=10,
+                                       num_step=50, start_step=25, share_attn=True, method_type='tca',
+                                       local_text_edit=True, local_perturbation=True, verbose=True, seed=42,
+                                       return_intermediates=False, end_scale=0.5, latent_blended=False,
+                                       blend_range=(0, 40)):
+        """reference model.py:1088-1118 (needs register_attention_control_4bggen).  Extra kwargs the published drivers
+        pass (`use_auto_draw`, `reduce_inp_artifacts`) are rejected by the reference signature too."""
+        seed_everything(seed)
+        ori_mask = self.mask_reduce_dim(ori_mask)
+        _, inverted = self.DDIM_inversion_func(img=ori_img, mask=ori_mask, prompt="", num_step=num_step,
+                                               start_step=start_step, ref_img=None, verbose=verbose)
+        edit, intermediates = self.Details_Preserving_regeneration_background(
+            ori_img, inverted, guidance_text, ori_mask, num_steps=num_step, start_step=start_step, end_step=end_step,
+            guidance_scale=guidance_scale, eta=eta, share_attn=share_attn, method_type=method_type, verbose=verbose,
+            end_scale=end_scale, local_text_edit=local_text_edit, local_perturbation=local_perturbation,
+            return_intermediates=return_intermediates, latent_blended=latent_blended, blend_range=blend_range)
+        self.last_intermediates = intermediates
+        return edit
+
+    # ------------------------------------------------------------------------------------------------------------
     # batched entry point (extension: E edits share one stream batch; the reference loops over edits one by one,
     # evaluation/FreeFine/freefine_batch_infer_2d.py:177-234)
     # ------------------------------------------------------------------------------------------------------------

@@ -137,3 +137,11 @@ PIPE_CASES = {
     "mmsa":         dict(seed=3, res=128, num_step=8, start_step=2, end_step=8, eta=0.0, gs=5.0, method="mmsa",
                          use_auto_draw=False, reduce_inp_artifacts=False, end_scale=0.5, prompt="a photo of a thing"),
 }
+
+
+BG_CASES = {
+    "bg_tca":  dict(seed=4, res=128, num_step=8, start_step=1, end_step=5, eta=1.0, gs=7.5, method="tca", end_scale=0.5,
+                    prompt="empty scene"),
+    "bg_mmsa": dict(seed=5, res=128, num_step=6, start_step=1, end_step=6, eta=0.0, gs=7.5, method="mmsa", end_scale=0.5,
+                    prompt="empty scene"),
+}

@@ -188,6 +188,31 @@ def gen_pipeline(ref):
         out[name + "/latents"] = torch.stack(inter).numpy()
         out[name + "/edit_img"], out[name + "/ref_img"] = edit_img, ref_img
         out[name + "/n_noise"] = np.array(counter["k"])
+    # background generation / object removal (register_attention_control_4bggen, model.py:1088-1118 without the GIF)
+    for name, c in cases.BG_CASES.items():
+        parts = build_standin("tiny")
+        pipe, controller = ref_import.make_reference_pipeline(ref, parts, flavour="bggen")
+        img, ori_mask3, _, _, _ = cases.edit_case_inputs(c["seed"], c["res"])
+        counter = {"k": 0}
+
+        def fake_randn(shape, generator=None, device=None, dtype=None, _c=c, _n=counter):
+            t = cases.step_noise(_c["seed"], _n["k"], shape)
+            _n["k"] += 1
+            return t
+
+        ref.model.randn_tensor = fake_randn
+        torch.manual_seed(c["seed"])
+        ori_mask = pipe.mask_reduce_dim(ori_mask3)
+        _, inv = pipe.DDIM_inversion_func(img=img, mask=ori_mask, prompt="", num_step=c["num_step"], start_step=c["start_step"],
+                                          ref_img=None, verbose=True)
+        edit_img, inter = pipe.Details_Preserving_regeneration_background(
+            img, inv, c["prompt"], ori_mask, num_steps=c["num_step"], start_step=c["start_step"], end_step=c["end_step"],
+            guidance_scale=c["gs"], eta=c["eta"], verbose=True, end_scale=c["end_scale"], return_intermediates=True,
+            method_type=c["method"])
+        out[name + "/img"], out[name + "/ori_mask"] = img, ori_mask3
+        out[name + "/inverted"] = torch.stack(inv).numpy()
+        out[name + "/latents"] = torch.stack([x.reshape(4, *x.shape[-2:]) for x in inter]).numpy()
+        out[name + "/edit_img"] = edit_img
     np.savez_compressed(os.path.join(OUT, "pipeline.npz"), **out)
 
 

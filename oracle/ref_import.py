@@ -100,7 +100,7 @@ def load():
     return types.SimpleNamespace(attention=attention, model=model, vis_utils=vis_utils, geo_utils=geo_utils)
 
 
-def make_reference_pipeline(ref, parts, device="cpu"):
+def make_reference_pipeline(ref, parts, device="cpu", flavour="edit"):
     """FreeFinePipeline.__new__ + stand-in parts, wired like freefine_batch_infer_2d.py:149-155."""
     P = ref.model.FreeFinePipeline
     if not isinstance(getattr(P, "device", None), property):
@@ -111,6 +111,7 @@ def make_reference_pipeline(ref, parts, device="cpu"):
     pipe.tokenizer, pipe.text_encoder, pipe.scheduler = parts.tokenizer, parts.text_encoder, parts.scheduler
     controller = ref.attention.Attention_Modulator(start_layer=10)
     pipe.controller = controller
-    ref.attention.register_attention_control(pipe, controller)
+    {"edit": ref.attention.register_attention_control, "bggen": ref.attention.register_attention_control_4bggen,
+     "compose": ref.attention.register_attention_control_compose}[flavour](pipe, controller)
     pipe.modify_unet_forward()
     return pipe, controller

@@ -142,3 +142,52 @@ def test_batched_edits_match_single(dev, golden):
         one = run([nm])
         # our kernels are batch-invariant; the library convolutions / GEMMs of the UNet pick batch-dependent algorithms
         assert _rel_l2(both[2 * i:2 * i + 2].cpu(), one.cpu()) < 1e-3, nm
+
+
+@pytest.mark.parametrize("name", list(cases.BG_CASES))
+def test_background_generation_matches_reference(dev, golden, name, monkeypatch):
+    """Object removal path: register_attention_control_4bggen + FreeFine_background_generation's inner calls."""
+    import freefine_b200.pipeline as P
+    from freefine_b200.pipeline import Attention_Modulator, FreeFinePipeline, register_attention_control_4bggen
+    from freefine_b200.standin import build_standin
+    g = golden["pipeline"]
+    c = cases.BG_CASES[name]
+    parts = build_standin("tiny", device=dev)
+    controller = Attention_Modulator(start_layer=10)
+    pipe = FreeFinePipeline.from_parts(parts, controller, device=dev)
+    register_attention_control_4bggen(pipe, controller)
+    pipe.modify_unet_forward()
+    counter = {"k": 0}
+
+    def fake_randn(shape, generator=None, device=None, dtype=None):
+        t = cases.step_noise(c["seed"], counter["k"], shape).to(device)
+        counter["k"] += 1
+        return t
+
+    monkeypatch.setattr(P, "randn_tensor", fake_randn)
+    img = g[name + "/img"]
+    ori_mask = pipe.mask_reduce_dim(g[name + "/ori_mask"])
+    _, inv = pipe.DDIM_inversion_func(img=img, mask=ori_mask, prompt="", num_step=c["num_step"], start_step=c["start_step"],
+                                      ref_img=None, verbose=True)
+    assert _rel_l2(inv[-1].cpu(), torch.from_numpy(g[name + "/inverted"])[-1]) < 1e-2
+    edit_img, inter = pipe.Details_Preserving_regeneration_background(
+        img, inv, c["prompt"], ori_mask, num_steps=c["num_step"], start_step=c["start_step"], end_step=c["end_step"],
+        guidance_scale=c["gs"], eta=c["eta"], verbose=True, end_scale=c["end_scale"], return_intermediates=True,
+        method_type=c["method"])
+    ref = torch.from_numpy(g[name + "/latents"])
+    assert len(inter) == ref.shape[0]
+    assert _rel_l2(inter[-1].reshape(ref[-1].shape).cpu(), ref[-1]) < 1e-2
+    assert np.abs(edit_img.astype(np.int32) - g[name + "/edit_img"].astype(np.int32)).max() <= 8
+
+
+def test_re_edit_2d_matches_cv2_reference(dev, golden):
+    """Coarse edit on the warp kernel vs the reference's cv2 re_edit_2d outputs stored in the pipeline fixtures
+    (pure translations here: mask bit-exact, image exact up to the uint8 rounding of cv2's fixed-point bilinear)."""
+    from freefine_b200.coarse_edit import re_edit_2d
+    g = golden["pipeline"]
+    for name in cases.PIPE_CASES:
+        c = cases.PIPE_CASES[name]
+        img, ori_mask3, edit_param, _, _ = cases.edit_case_inputs(c["seed"], c["res"])
+        final, tmask, hole = re_edit_2d(img, ori_mask3, edit_param, img)
+        assert np.array_equal(tmask, g[name + "/tgt_mask"]), name
+        assert np.abs(final.astype(np.int32) - g[name + "/coarse"].astype(np.int32)).max() <= 1, name

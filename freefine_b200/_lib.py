@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libfreefine_b200.so")
+LIB_PATH = os.environ.get("FREEFINE_B200_LIB", os.path.join(_HERE, "lib", "libfreefine_b200.so"))
 
 FF_MAX_PASS = 4
 FF_DT_F32, FF_DT_BF16 = 0, 1

@@ -26,22 +26,35 @@
 namespace {
 
 constexpr int BM = 128;                 // query rows per CTA
-constexpr int BN = 128;                 // keys per tile
+constexpr int BN = 64;                  // keys per tile (S is double-buffered in TMEM: 2 x 64 columns)
 constexpr int BOX_COLS = 64;            // channels per TMA box (128 bytes of bf16 = one swizzle-128B row)
-constexpr int TILE_BYTES = BN * 128;    // 16 KiB: 128 rows x 128 B
+constexpr int TILE_BYTES = BM * 128;    // Q box: 128 rows x 128 B = 16 KiB
+constexpr int KV_BYTES = BN * 128;      // K / V box: 64 rows x 128 B = 8 KiB
 constexpr int NUM_THREADS = 192;
-constexpr float RESCALE_THRESHOLD = 8.f;   // log2 units
+#ifdef FF_DBG_NORESCALE
+constexpr float RESCALE_THRESHOLD = 1e30f;
+#else
+constexpr float RESCALE_THRESHOLD = 24.f;  // log2 units: p <= 2^24 keeps fp32 / bf16 relative precision, rescales are rare
+#endif
 
 template <int DPAD> struct Cfg {
   static constexpr int NKT = (DPAD + BOX_COLS - 1) / BOX_COLS;          // 64-channel boxes per operand tile
-  static constexpr int NSTAGE = DPAD <= 80 ? 2 : 1;                     // K/V ring depth
+#ifdef FF_DBG_NSTAGE
+  static constexpr int NSTAGE = FF_DBG_NSTAGE;
+#else
+  static constexpr int NSTAGE = DPAD <= 48 ? 4 : (DPAD <= 80 ? 3 : 2);  // K/V ring depth
+#endif
   static constexpr bool ACC_TMEM = DPAD > 80;                           // cross-pass accumulator location
-  static constexpr int TMEM_S = 0, TMEM_O = BN, TMEM_ACC = BN + DPAD;
-  static constexpr int TMEM_USED = BN + DPAD + (ACC_TMEM ? DPAD : 0);
+  static constexpr int TMEM_S = 0, TMEM_O = 2 * BN, TMEM_ACC = 2 * BN + DPAD;   // S buffers at columns 0 and BN
+  static constexpr int TMEM_USED = 2 * BN + DPAD + (ACC_TMEM ? DPAD : 0);
   static constexpr int TMEM_COLS = TMEM_USED <= 256 ? 256 : 512;
   static constexpr int SMEM_Q = NKT * TILE_BYTES;
-  static constexpr int SMEM_STAGE = 2 * NKT * TILE_BYTES;               // K tiles then V tiles
+  static constexpr int SMEM_STAGE = 2 * NKT * KV_BYTES;                 // K tiles then V tiles
+#ifdef FF_DBG_ONE_CTA
+  static constexpr int SMEM_BYTES = SMEM_Q + NSTAGE * SMEM_STAGE + 1024 + 256 + 60 * 1024;   // force 1 CTA / SM
+#else
   static constexpr int SMEM_BYTES = SMEM_Q + NSTAGE * SMEM_STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+#endif
   static constexpr int MIN_CTAS = (SMEM_BYTES <= 113 * 1024 && TMEM_COLS == 256) ? 2 : 1;
 };
 
@@ -77,6 +90,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
   }
+}
+// non-blocking probe of a phase (used to hide the ~90-cycle fast-path latency of try_wait behind useful work)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
                                             uint32_t bar) {
@@ -140,6 +165,36 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// tcgen05.ld writes its destination registers ASYNCHRONOUSLY; they are valid only after tcgen05.wait::ld.  To the
+// compiler an inline-asm output is defined at the asm statement, so arithmetic on the loaded values could legally be
+// scheduled ABOVE a separate wait statement.  These wait variants take the loaded registers as in/out operands, which
+// pins every use behind the wait.
+__device__ __forceinline__ void tmem_wait_ld16(float (&v)[16]) {
+#ifdef FF_PLAIN_WAIT
+  tmem_wait_ld();
+  return;
+#endif
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld32(float (&v)[32]) {
+#ifdef FF_PLAIN_WAIT
+  tmem_wait_ld();
+  return;
+#endif
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -313,9 +368,12 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   const uint32_t sQ = smem_base;
   const uint32_t sKV = smem_base + C::SMEM_Q;
   const uint32_t bar_base = sKV + C::NSTAGE * C::SMEM_STAGE;
-  const uint32_t bar_q = bar_base, bar_s = bar_base + 8, bar_p = bar_base + 16, bar_o = bar_base + 24;
-  const uint32_t bar_kv_full = bar_base + 32, bar_kv_empty = bar_base + 32 + 8 * C::NSTAGE;
-  const uint32_t tmem_slot = bar_base + 32 + 16 * C::NSTAGE;            // u32 written by tcgen05.alloc
+  const uint32_t bar_q = bar_base;
+  // [2] each, indexed by tile parity: s_full / p_full per S buffer; o_done alternates too, so that a warp that skipped
+  // o_done waits for several tiles can never be fooled by phase-parity aliasing (a phase is 2 tiles long)
+  const uint32_t bar_s = bar_base + 16, bar_p = bar_base + 32, bar_o = bar_base + 48;
+  const uint32_t bar_kv_full = bar_base + 64, bar_kv_empty = bar_base + 64 + 8 * C::NSTAGE;
+  const uint32_t tmem_slot = bar_base + 64 + 16 * C::NSTAGE;            // u32 written by tcgen05.alloc
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
@@ -330,8 +388,11 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   if (threadIdx.x == 0) {
     mbar_init(bar_q, 1);
     mbar_init(bar_s, 1);
+    mbar_init(bar_s + 8, 1);
     mbar_init(bar_p, BM);
+    mbar_init(bar_p + 8, BM);
     mbar_init(bar_o, 1);
+    mbar_init(bar_o + 8, 1);
     for (int i = 0; i < C::NSTAGE; ++i) {
       mbar_init(bar_kv_full + 8 * i, 1);
       mbar_init(bar_kv_empty + 8 * i, 1);
@@ -381,11 +442,11 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             if (use > 0) mbar_wait(bar_kv_empty + 8 * stage, (use - 1) & 1);
             FF_TRACE(it, 11);
             const uint32_t full = bar_kv_full + 8 * stage;
-            const uint32_t sK = sKV + stage * C::SMEM_STAGE, sV = sK + C::NKT * TILE_BYTES;
-            mbar_expect_tx(full, 2 * C::NKT * TILE_BYTES);
+            const uint32_t sK = sKV + stage * C::SMEM_STAGE, sV = sK + C::NKT * KV_BYTES;
+            mbar_expect_tx(full, 2 * C::NKT * KV_BYTES);
             for (int kt = 0; kt < C::NKT; ++kt) {
-              tma_load_4d(sK + kt * TILE_BYTES, &tm_k, kt * BOX_COLS, head, j * BN, sg.kv, full);
-              tma_load_4d(sV + kt * TILE_BYTES, &tm_v, kt * BOX_COLS, head, j * BN, sg.kv, full);
+              tma_load_4d(sK + kt * KV_BYTES, &tm_k, kt * BOX_COLS, head, j * BN, sg.kv, full);
+              tma_load_4d(sV + kt * KV_BYTES, &tm_v, kt * BOX_COLS, head, j * BN, sg.kv, full);
             }
             ++it;
           }
@@ -400,6 +461,30 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       FF_TRACE(0, 20);
       mbar_wait(bar_q, 0);
       int it = 0;
+      // PV(t) is issued one tile late: QK(t+1) -> S[(t+1)&1] goes first so that it runs while the softmax warps are
+      // still busy with tile t (S is double-buffered); the tensor pipe executes this thread's MMAs in issue order, so
+      // QK(t+2), which overwrites the S/P buffer of tile t, is always behind PV(t).
+      bool pend = false, pend_first = false;
+      int pend_stage = 0;
+      auto issue_pv = [&](int t, int stage, bool first_of_pass) {
+        const uint32_t sV = sKV + stage * C::SMEM_STAGE + C::NKT * KV_BYTES;
+        FF_TRACE(t, 23);
+        mbar_wait(bar_p + 8 * (t & 1), (t >> 1) & 1);
+        FF_TRACE(t, 24);
+        tc_fence_after();
+        // O (+)= P_hi V + P_lo V : A = P halves (bf16 in TMEM, 8 columns per 16 keys: K-step ks keeps hi in columns
+        // [16ks,16ks+8) and lo in [16ks+8,16ks+16) of its S buffer), B = V tile, MN-major; 16 keys = 2048 B per
+        // K-step, 64-channel groups KV_BYTES apart (LBO)
+#pragma unroll
+        for (int ks = 0; ks < BN / 16; ++ks) {
+          const uint32_t a_hi = tmem + C::TMEM_S + BN * (t & 1) + 16 * ks;
+          const uint64_t vdesc = smem_desc_sw128(sV + ks * 2048, KV_BYTES);
+          mma_ts(tmem + C::TMEM_O, a_hi, vdesc, idesc_pv, (!first_of_pass || ks > 0) ? 1u : 0u);
+          mma_ts(tmem + C::TMEM_O, a_hi + 8, vdesc, idesc_pv, 1u);
+        }
+        tc_commit(bar_kv_empty + 8 * stage);
+        tc_commit(bar_o + 8 * (t & 1));
+      };
 #pragma unroll 1
       for (int ip = 0; ip < n_pass; ++ip) {
         const FFAttnPass ps = plan->pass[ip];
@@ -414,41 +499,30 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           for (int j = 0; j < n_kv_tiles; ++j) {
             if (tile_skip(cx, sg, tile_class(sg, j, p), p.s_kv)) continue;
             const int stage = it % C::NSTAGE, use = it / C::NSTAGE;
-            const uint32_t sK = sKV + stage * C::SMEM_STAGE, sV = sK + C::NKT * TILE_BYTES;
+            const uint32_t sK = sKV + stage * C::SMEM_STAGE;
             FF_TRACE(it, 21);
             mbar_wait(bar_kv_full + 8 * stage, use & 1);
             FF_TRACE(it, 22);
             tc_fence_after();
-            // S = Q K^T.  The S/P columns are free: softmax(it-1) arrived on p_full before PV(it-1) was issued and
-            // the tensor pipe executes this thread's MMAs in issue order.
+            // S[it&1] = Q K^T
 #pragma unroll
             for (int ks = 0; ks < DPAD / 16; ++ks) {
-              const uint32_t off = (ks >> 2) * TILE_BYTES + (ks & 3) * 32;   // 16 channels = 32 B inside the row
-              mma_ss(tmem + C::TMEM_S, smem_desc_sw128(sQ + off, 16), smem_desc_sw128(sK + off, 16), idesc_qk,
-                     ks > 0);
+              const uint32_t qoff = (ks >> 2) * TILE_BYTES + (ks & 3) * 32;   // 16 channels = 32 B inside the row
+              const uint32_t koff = (ks >> 2) * KV_BYTES + (ks & 3) * 32;
+              mma_ss(tmem + C::TMEM_S + BN * (it & 1), smem_desc_sw128(sQ + qoff, 16), smem_desc_sw128(sK + koff, 16),
+                     idesc_qk, ks > 0);
             }
-            tc_commit(bar_s);
-            FF_TRACE(it, 23);
-            mbar_wait(bar_p, it & 1);
-            FF_TRACE(it, 24);
-            tc_fence_after();
-            // O (+)= P_hi V + P_lo V : A = P halves (bf16 in TMEM, 8 columns per 16 keys: K-step ks keeps hi in
-            // columns [16ks,16ks+8) and lo in [16ks+8,16ks+16)), B = V tile, MN-major; 16 keys = 2048 B per K-step,
-            // 64-channel groups TILE_BYTES apart (LBO)
-#pragma unroll
-            for (int ks = 0; ks < BN / 16; ++ks) {
-              const uint32_t a_hi = tmem + C::TMEM_S + 16 * ks;
-              const uint64_t vdesc = smem_desc_sw128(sV + ks * 2048, TILE_BYTES);
-              mma_ts(tmem + C::TMEM_O, a_hi, vdesc, idesc_pv, (!first || ks > 0) ? 1u : 0u);
-              mma_ts(tmem + C::TMEM_O, a_hi + 8, vdesc, idesc_pv, 1u);
-            }
-            tc_commit(bar_kv_empty + 8 * stage);
-            tc_commit(bar_o);
+            tc_commit(bar_s + 8 * (it & 1));
+            if (pend) issue_pv(it - 1, pend_stage, pend_first);
+            pend = true;
+            pend_stage = stage;
+            pend_first = first;
             first = false;
             ++it;
           }
         }
       }
+      if (pend) issue_pv(it - 1, pend_stage, pend_first);
     }
   } else {
     // ===================================== softmax + epilogue ===============================
@@ -476,6 +550,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       float m_used = 0.f;
       float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
       bool first = true;
+      bool s_ready = false;      // outcome of the early probe of this tile's s_full phase
 #pragma unroll 1
       for (int seg = 0; seg < 2; ++seg) {
         const SegCtx sg = seg ? cx.s1 : cx.s0;
@@ -488,18 +563,27 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           const int cls = tile_class(sg, j, p);
           if (tile_skip(cx, sg, cls, p.s_kv)) continue;
           FF_TRACE(it, 30);
-          mbar_wait(bar_s, it & 1);
+          if (!s_ready) mbar_wait(bar_s + 8 * (it & 1), (it >> 1) & 1);
           FF_TRACE(it, 31);
           tc_fence_after();
-          // ---- sweep 1: row max over ALL 128 columns (an upper bound of the max over the allowed keys is all the
+          // o_done protocol.  o_done alternates between two mbarriers (tile parity), and every thread OBSERVES every
+          // phase of each of them in order: phase it-2 is probed here without blocking (it completed long ago; the
+          // probe's latency hides behind the tile) and, if the probe failed, waited for at the end of the tile.  Only
+          // then is a blocking wait for phase it-1 (rescale below, or end of pass) exact: having observed it-3 on the
+          // same barrier, that barrier can only be in phase it-1 or later.  (Waiting ONLY when a rescale was needed let
+          // a late mbarrier arrival alias the phase parity: the wait fell through while PV(it-1) was still
+          // accumulating -- observed on hardware with 2 CTAs/SM and a deep K/V ring.)
+          const bool o2_done = it >= 2 ? mbar_test(bar_o + 8 * (it & 1), ((it - 2) >> 1) & 1) : true;
+          const uint32_t tS = tlane + C::TMEM_S + BN * (it & 1);     // this tile's S / P buffer
+          // ---- sweep 1: row max over ALL 64 columns (an upper bound of the max over the allowed keys is all the
           // softmax needs: bf16/fp32 keep their relative precision whatever the reference point; padded columns are 0)
           float mt;
           {
             float sa[32], sb[32];
             float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-            tmem_ld32(tlane + C::TMEM_S, sa);
-            tmem_wait_ld();
-            tmem_ld32(tlane + C::TMEM_S + 32, sb);
+            tmem_ld32(tS, sa);
+            tmem_wait_ld32(sa);
+            tmem_ld32(tS + 32, sb);
 #pragma unroll
             for (int i = 0; i < 32; i += 8) {
               m0 = fmaxf(m0, fmaxf(sa[i], sa[i + 1]));
@@ -507,25 +591,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
               m2 = fmaxf(m2, fmaxf(sa[i + 4], sa[i + 5]));
               m3 = fmaxf(m3, fmaxf(sa[i + 6], sa[i + 7]));
             }
-            tmem_wait_ld();
-            tmem_ld32(tlane + C::TMEM_S + 64, sa);
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              m0 = fmaxf(m0, fmaxf(sb[i], sb[i + 1]));
-              m1 = fmaxf(m1, fmaxf(sb[i + 2], sb[i + 3]));
-              m2 = fmaxf(m2, fmaxf(sb[i + 4], sb[i + 5]));
-              m3 = fmaxf(m3, fmaxf(sb[i + 6], sb[i + 7]));
-            }
-            tmem_wait_ld();
-            tmem_ld32(tlane + C::TMEM_S + 96, sb);
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              m0 = fmaxf(m0, fmaxf(sa[i], sa[i + 1]));
-              m1 = fmaxf(m1, fmaxf(sa[i + 2], sa[i + 3]));
-              m2 = fmaxf(m2, fmaxf(sa[i + 4], sa[i + 5]));
-              m3 = fmaxf(m3, fmaxf(sa[i + 6], sa[i + 7]));
-            }
-            tmem_wait_ld();
+            tmem_wait_ld32(sb);
 #pragma unroll
             for (int i = 0; i < 32; i += 8) {
               m0 = fmaxf(m0, fmaxf(sb[i], sb[i + 1]));
@@ -549,7 +615,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           }
           if (__any_sync(0xffffffffu, grow)) {
             FF_TRACE(it, 32);
-            mbar_wait(bar_o, (it - 1) & 1);      // PV(it-1) has finished writing O
+            mbar_wait(bar_o + 8 * ((it - 1) & 1), ((it - 1) >> 1) & 1);   // PV(it-1) finished writing O
             FF_TRACE(it, 33);
             tc_fence_after();
 #pragma unroll
@@ -557,7 +623,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
               float o[16];
               uint32_t ob[16];
               tmem_ld16(tlane + C::TMEM_O + 16 * c, o);
-              tmem_wait_ld();
+              tmem_wait_ld16(o);
 #pragma unroll
               for (int i = 0; i < 16; ++i) ob[i] = __float_as_uint(o[i] * alpha);
               tmem_st16(tlane + C::TMEM_O + 16 * c, ob);
@@ -573,18 +639,18 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             const float nb = row_allowed(cls, flip, uniform) ? -m_used : -INFINITY;
             float ca[16], cb[16];
             uint32_t hl[16];
-            tmem_ld16(tlane + C::TMEM_S, ca);
-            tmem_wait_ld();
+            tmem_ld16(tS, ca);
+            tmem_wait_ld16(ca);
 #pragma unroll
             for (int ks = 0; ks < BN / 16; ks += 2) {
-              tmem_ld16(tlane + C::TMEM_S + 16 * (ks + 1), cb);          // in flight while chunk ks is processed
+              tmem_ld16(tS + 16 * (ks + 1), cb);                          // in flight while chunk ks is processed
               softmax_chunk<false>(ca, hl, sc, nb, 0u, la, lb);
-              tmem_st16(tlane + C::TMEM_S + 16 * ks, hl);
-              tmem_wait_ld();
-              if (ks + 2 < BN / 16) tmem_ld16(tlane + C::TMEM_S + 16 * (ks + 2), ca);
+              tmem_st16(tS + 16 * ks, hl);
+              tmem_wait_ld16(cb);
+              if (ks + 2 < BN / 16) tmem_ld16(tS + 16 * (ks + 2), ca);
               softmax_chunk<false>(cb, hl, sc, nb, 0u, la, lb);
-              tmem_st16(tlane + C::TMEM_S + 16 * (ks + 1), hl);
-              if (ks + 2 < BN / 16) tmem_wait_ld();
+              tmem_st16(tS + 16 * (ks + 1), hl);
+              if (ks + 2 < BN / 16) tmem_wait_ld16(ca);
             }
           } else {
             // boundary / ragged tile: evaluate allowed(q,k) per element on 16-bit slices of the mask words
@@ -606,16 +672,18 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
               }
               float cs[16];
               uint32_t hl[16];
-              tmem_ld16(tlane + C::TMEM_S + 16 * ks, cs);
-              tmem_wait_ld();
+              tmem_ld16(tS + 16 * ks, cs);
+              tmem_wait_ld16(cs);
               softmax_chunk<true>(cs, hl, sc, nb, kb & valid, la, lb);
-              tmem_st16(tlane + C::TMEM_S + 16 * ks, hl);
+              tmem_st16(tS + 16 * ks, hl);
             }
           }
           tmem_wait_st();
           tc_fence_before();
-          mbar_arrive(bar_p);
+          mbar_arrive(bar_p + 8 * (it & 1));
           FF_TRACE(it, 34);
+          if (!o2_done) mbar_wait(bar_o + 8 * (it & 1), ((it - 2) >> 1) & 1);             // observe phase it-2 (see above)
+          s_ready = mbar_test(bar_s + 8 * ((it + 1) & 1), ((it + 1) >> 1) & 1);            // early probe of the next tile
           first = false;
           ++it;
         }
@@ -623,7 +691,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       if (first) continue;     // (defensive) no tile of this pass was processed: nothing to add
       // ---- end of pass: acc += weight * roww / l * O
       FF_TRACE(it, 35);
-      mbar_wait(bar_o, (it - 1) & 1);
+      mbar_wait(bar_o + 8 * ((it - 1) & 1), ((it - 1) >> 1) & 1);
       FF_TRACE(it, 36);
       tc_fence_after();
       const float l = (la.x + la.y) + (lb.x + lb.y);
@@ -634,13 +702,13 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       for (int c = 0; c < DPAD / 16; ++c) {
         float o[16];
         tmem_ld16(tlane + C::TMEM_O + 16 * c, o);
-        tmem_wait_ld();
+        tmem_wait_ld16(o);
         if constexpr (C::ACC_TMEM) {
           float a[16];
           uint32_t ab[16];
           if (acc_started) {
             tmem_ld16(tlane + C::TMEM_ACC + 16 * c, a);
-            tmem_wait_ld();
+            tmem_wait_ld16(a);
           } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) a[i] = 0.f;
@@ -668,7 +736,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         if constexpr (C::ACC_TMEM) {
           if (acc_started) {
             tmem_ld16(tlane + C::TMEM_ACC + 16 * c, o);
-            tmem_wait_ld();
+            tmem_wait_ld16(o);
           } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) o[i] = 0.f;
@@ -729,13 +797,13 @@ EncodeTiledFn get_encode_fn() {
 
 // [streams, S, heads, d] bf16 view of a dense [streams, S, heads*d] tensor; box = 64 channels x 1 head x 128 rows.
 // Channels >= d of a box are out of bounds in dimension 0 and therefore zero-filled.
-int make_map(CUtensorMap* map, const void* base, int streams, int S, int heads, int d) {
+int make_map(CUtensorMap* map, const void* base, int streams, int S, int heads, int d, int box_rows) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return ff::fail(FF_E_CUDA, "cuTensorMapEncodeTiled entry point not found");
   const cuuint64_t C = (cuuint64_t)heads * d;
   cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)heads, (cuuint64_t)S, (cuuint64_t)streams};
   cuuint64_t strides[3] = {(cuuint64_t)d * 2, C * 2, (cuuint64_t)S * C * 2};
-  cuuint32_t box[4] = {BOX_COLS, 1, BN, 1};
+  cuuint32_t box[4] = {BOX_COLS, 1, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -801,9 +869,9 @@ extern "C" int ff_attn_masked_kv(const FFAttnArgs* a, void* stream) {
 
   alignas(64) CUtensorMap mq, mk, mv;
   int rc;
-  if ((rc = make_map(&mq, a->q, a->n_streams, a->s_q, a->heads, a->head_dim)) != FF_OK) return rc;
-  if ((rc = make_map(&mk, a->k, a->n_kv_streams, a->s_kv, a->heads, a->head_dim)) != FF_OK) return rc;
-  if ((rc = make_map(&mv, a->v, a->n_kv_streams, a->s_kv, a->heads, a->head_dim)) != FF_OK) return rc;
+  if ((rc = make_map(&mq, a->q, a->n_streams, a->s_q, a->heads, a->head_dim, BM)) != FF_OK) return rc;
+  if ((rc = make_map(&mk, a->k, a->n_kv_streams, a->s_kv, a->heads, a->head_dim, BN)) != FF_OK) return rc;
+  if ((rc = make_map(&mv, a->v, a->n_kv_streams, a->s_kv, a->heads, a->head_dim, BN)) != FF_OK) return rc;
 
   KParams kp;
   kp.plan = a->plan;

@@ -6,12 +6,13 @@
 // the warped image, the warped mask and the blended result never make a round trip through HBM.
 //
 // Mapping: one CTA produces a 64x16 output tile for a chunk of channels.  The affine image of that tile is a
-// parallelogram; its bounding box in the source is staged in shared memory with 128-bit loads (each source texel is
-// read from HBM/L2 once per tile instead of up to 4 times, and the 4 bilinear taps become conflict-light LDS), the
+// parallelogram; its bounding box in the source is staged in shared memory with 16-byte cp.async copies, double
+// buffered over channel pairs (the copies of channels c+2,c+3 are in flight while c,c+1 are resampled), so each
+// source texel is read from HBM/L2 once per tile instead of up to 4 times and the 4 bilinear taps are LDS.  The
 // background tile is read and the result written as 128-bit vectors.  If the bounding box does not fit (strong
-// minification) the taps go straight to global memory -- same arithmetic, same result.
-// Coordinates follow ATen's operation order in fp32 with explicit round-to-nearest ops (no FMA contraction):
-//   x_n = (2j+1)/dW - 1;  g = x_n*t00 + y_n*t01 + t02;  ix = ((g+1)*W - 1)/2;  nearest = rint (ties to even).
+// minification) or the layout is not 16-byte friendly, the taps go straight to global memory -- same arithmetic,
+// same result.  Coordinates follow ATen's operation order in fp32 with explicit round-to-nearest ops (no FMA
+// contraction):  x_n = (2j+1)/dW - 1;  g = x_n*t00 + y_n*t01 + t02;  ix = ((g+1)*W - 1)/2;  nearest = rint.
 #include <cuda_bf16.h>
 
 #include "ff_common.cuh"
@@ -20,8 +21,9 @@ namespace {
 
 constexpr int TILE_X = 64, TILE_Y = 16, PX = 4;           // 4 consecutive output pixels per thread
 constexpr int THREADS = (TILE_X / PX) * TILE_Y;           // 256
-constexpr int STAGE_FLOATS = 5632;                        // 22 KB staging buffer per channel (x2 channels)
-constexpr int CH_PER_ITER = 2;
+constexpr int STAGE_BYTES = 22 * 1024;                    // staging buffer per channel
+constexpr int CH_PER_ITER = 2;                            // channels per pipeline stage
+constexpr int SMEM_BYTES = 2 * CH_PER_ITER * STAGE_BYTES; // double buffered: 88 KB -> 2 CTAs / SM
 
 template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
@@ -47,18 +49,18 @@ __device__ __forceinline__ Coord src_coord(int x, int y, int dW, int dH, int W, 
   return c;
 }
 
-// Fetch functor: texel (xi, yi) of the current channel, zero outside the image.
+// Fetch functors: texel (xi, yi) of the current channel, zero outside the image.
 template <typename T> struct GlobalFetch {
   const T* p; int W, H;
   __device__ __forceinline__ float operator()(int xi, int yi) const {
     return (xi >= 0 && xi < W && yi >= 0 && yi < H) ? to_f<T>(__ldg(p + (size_t)yi * W + xi)) : 0.f;
   }
 };
-struct SmemFetch {
-  const float* s; int bx0, by0, bw, bh;   // staged box (already clipped to the image; outside = zero padding)
+template <typename T> struct SmemFetch {
+  const T* s; int bx0, by0, bw, bh;   // staged box (clipped to the image; outside = zero padding)
   __device__ __forceinline__ float operator()(int xi, int yi) const {
     const int u = xi - bx0, v = yi - by0;
-    return (u >= 0 && u < bw && v >= 0 && v < bh) ? s[v * bw + u] : 0.f;
+    return (u >= 0 && u < bw && v >= 0 && v < bh) ? to_f<T>(s[v * bw + u]) : 0.f;
   }
 };
 
@@ -76,14 +78,25 @@ template <typename F> __device__ __forceinline__ float sample(const F& f, Coord 
   return o;
 }
 
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 template <typename T>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 2)
 warp_affine_blend_kernel(const T* __restrict__ src, const float* __restrict__ theta,
                          const uint8_t* __restrict__ mask_src, const T* __restrict__ bg, T* __restrict__ out,
                          uint8_t* __restrict__ mask_out, int C, int H, int W, int dH, int dW, int mode,
                          int ch_per_cta, int tiles_x, int vec_ok) {
-  __shared__ __align__(16) float stage[CH_PER_ITER][STAGE_FLOATS];
+  extern __shared__ __align__(16) uint8_t stage_raw[];
   __shared__ float th[6];
+  constexpr int VEC = 16 / (int)sizeof(T);                 // elements per 16-byte copy
+  constexpr int STAGE_ELEMS = STAGE_BYTES / (int)sizeof(T);
   const int n = blockIdx.z;
   const int tile = blockIdx.x;
   const int tx0 = (tile % tiles_x) * TILE_X, ty0 = (tile / tiles_x) * TILE_Y;
@@ -94,7 +107,7 @@ warp_affine_blend_kernel(const T* __restrict__ src, const float* __restrict__ th
 
   const int lx = (threadIdx.x % (TILE_X / PX)) * PX, ly = threadIdx.x / (TILE_X / PX);
   const int ox = tx0 + lx, oy = ty0 + ly;
-  const bool row_ok = oy < dH;
+  const bool active = oy < dH && ox < dW;
 
   // per-thread source coordinates of its 4 pixels (shared by every channel) and the warped mask
   Coord cd[PX];
@@ -105,13 +118,12 @@ warp_affine_blend_kernel(const T* __restrict__ src, const float* __restrict__ th
     keep[j] = true;
   }
   if (mask_src != nullptr) {
-    GlobalFetch<uint8_t> mf{mask_src + (size_t)n * H * W, W, H};
+    const uint8_t* mp = mask_src + (size_t)n * H * W;
 #pragma unroll
     for (int j = 0; j < PX; ++j) {
-      const bool in = row_ok && (ox + j) < dW;
-      // nearest sample of the mask: index = rint(coordinate)
-      const int xi = __float2int_rn(cd[j].ix), yi = __float2int_rn(cd[j].iy);
-      const uint8_t mv = (in && xi >= 0 && xi < W && yi >= 0 && yi < H) ? __ldg(mf.p + (size_t)yi * W + xi) : 0;
+      const bool in = oy < dH && (ox + j) < dW;
+      const int xi = __float2int_rn(cd[j].ix), yi = __float2int_rn(cd[j].iy);     // nearest: rint(coordinate)
+      const uint8_t mv = (in && xi >= 0 && xi < W && yi >= 0 && yi < H) ? __ldg(mp + (size_t)yi * W + xi) : 0;
       keep[j] = mv != 0;
       if (in && mask_out != nullptr && blockIdx.y == 0) mask_out[((size_t)n * dH + oy) * dW + ox + j] = keep[j];
     }
@@ -125,67 +137,98 @@ warp_affine_blend_kernel(const T* __restrict__ src, const float* __restrict__ th
   int bx1 = (int)floorf(fmaxf(fmaxf(k0.ix, k1.ix), fmaxf(k2.ix, k3.ix))) + 2;
   int by0 = (int)floorf(fminf(fminf(k0.iy, k1.iy), fminf(k2.iy, k3.iy))) - 1;
   int by1 = (int)floorf(fmaxf(fmaxf(k0.iy, k1.iy), fmaxf(k2.iy, k3.iy))) + 2;
-  bx0 = max(bx0, 0) & ~3;                       // 16-byte aligned start for the vector loads
+  bx0 = (max(bx0, 0) / VEC) * VEC;              // 16-byte aligned start for the vector copies
   by0 = max(by0, 0);
   bx1 = min(bx1, W - 1);
   by1 = min(by1, H - 1);
   int bw = bx1 - bx0 + 1, bh = by1 - by0 + 1;
-  bw = (bw + 3) & ~3;
-  if (bx0 + bw > W) bw = W - bx0;               // W % 4 != 0: ragged right edge, scalar staging
+  bw = ((bw + VEC - 1) / VEC) * VEC;
+  if (bx0 + bw > W) bw = W - bx0;               // ragged right edge (W % VEC != 0): scalar staging
   const bool empty_box = (bx1 < bx0) || (by1 < by0);
-  const bool staged = !empty_box && (long long)bw * bh <= STAGE_FLOATS;
-  const bool vec_stage = vec_ok && (bw % 4 == 0) && (W % 4 == 0);
+  const bool staged = !empty_box && (long long)bw * bh <= STAGE_ELEMS;
+  const bool vec_stage = vec_ok && (bw % VEC == 0) && (W % VEC == 0);
 
-  for (int c0 = c_begin; c0 < c_end; c0 += CH_PER_ITER) {
+  auto stage_ptr = [&](int set, int cc) { return reinterpret_cast<T*>(stage_raw) + (size_t)(set * CH_PER_ITER + cc) * STAGE_ELEMS; };
+  // asynchronous staging of channels [c0, c0+nc) into buffer set `set` (one cp.async group)
+  auto issue = [&](int c0, int set) {
     const int nc = min(CH_PER_ITER, c_end - c0);
+    for (int cc = 0; cc < nc; ++cc) {
+      const T* p = src + ((size_t)n * C + c0 + cc) * H * W;
+      T* s = stage_ptr(set, cc);
+      if (vec_stage) {
+        const int bwv = bw / VEC;
+        for (int i = threadIdx.x; i < bwv * bh; i += THREADS) {
+          const int v = i / bwv, u = (i - v * bwv) * VEC;
+          cp_async16(s + v * bw + u, p + (size_t)(by0 + v) * W + bx0 + u);
+        }
+      } else {
+        for (int i = threadIdx.x; i < bw * bh; i += THREADS) {
+          const int v = i / bw, u = i - v * bw;
+          s[i] = __ldg(p + (size_t)(by0 + v) * W + bx0 + u);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+
+  if (staged) issue(c_begin, 0);
+  int it = 0;
+  for (int c0 = c_begin; c0 < c_end; c0 += CH_PER_ITER, ++it) {
+    const int nc = min(CH_PER_ITER, c_end - c0);
+    using V = typename Vec4<T>::type;
+    const bool vec_io = vec_ok && ox + PX <= dW;
+    // background vectors first: these loads are in flight while we wait for the staged copies
+    T b[CH_PER_ITER][PX];
+    if (active && mask_src != nullptr) {
+#pragma unroll
+      for (int cc = 0; cc < CH_PER_ITER; ++cc) {
+        if (cc < nc) {
+          const size_t obase = (((size_t)n * C + c0 + cc) * dH + oy) * dW + ox;
+          if (vec_io) *reinterpret_cast<V*>(b[cc]) = __ldg(reinterpret_cast<const V*>(bg + obase));
+          else
+            for (int j = 0; j < PX && ox + j < dW; ++j) b[cc][j] = bg[obase + j];
+        }
+      }
+    }
     if (staged) {
-      __syncthreads();                            // previous iteration finished reading the buffers
-      for (int cc = 0; cc < nc; ++cc) {
-        const T* p = src + ((size_t)n * C + c0 + cc) * H * W;
-        if (vec_stage && sizeof(T) == 4) {
-          const int bw4 = bw >> 2;
-          for (int i = threadIdx.x; i < bw4 * bh; i += THREADS) {
-            const int v = i / bw4, u4 = i - v * bw4;
-            const float4 t4 = __ldg(reinterpret_cast<const float4*>(p + (size_t)(by0 + v) * W + bx0) + u4);
-            *reinterpret_cast<float4*>(&stage[cc][v * bw + u4 * 4]) = t4;
+      if (c0 + CH_PER_ITER < c_end) {
+        issue(c0 + CH_PER_ITER, (it + 1) & 1);      // prefetch the next channel pair into the other buffer set
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();                              // copies of set it&1 are visible to every thread
+    }
+    if (active) {
+#pragma unroll
+      for (int cc = 0; cc < CH_PER_ITER; ++cc) {
+        if (cc < nc) {
+          const size_t obase = (((size_t)n * C + c0 + cc) * dH + oy) * dW + ox;
+          float r[PX];
+          if (empty_box) {
+#pragma unroll
+            for (int j = 0; j < PX; ++j) r[j] = 0.f;
+          } else if (staged) {
+            SmemFetch<T> f{stage_ptr(it & 1, cc), bx0, by0, bw, bh};
+#pragma unroll
+            for (int j = 0; j < PX; ++j) r[j] = sample(f, cd[j], mode);
+          } else {
+            GlobalFetch<T> f{src + ((size_t)n * C + c0 + cc) * H * W, W, H};
+#pragma unroll
+            for (int j = 0; j < PX; ++j) r[j] = sample(f, cd[j], mode);
           }
-        } else {
-          for (int i = threadIdx.x; i < bw * bh; i += THREADS) {
-            const int v = i / bw, u = i - v * bw;
-            stage[cc][i] = to_f<T>(__ldg(p + (size_t)(by0 + v) * W + bx0 + u));
+          if (vec_io) {
+            T o[PX];
+#pragma unroll
+            for (int j = 0; j < PX; ++j) o[j] = keep[j] ? from_f<T>(r[j]) : b[cc][j];
+            *reinterpret_cast<V*>(out + obase) = *reinterpret_cast<V*>(o);
+          } else {
+            for (int j = 0; j < PX && ox + j < dW; ++j) out[obase + j] = keep[j] ? from_f<T>(r[j]) : b[cc][j];
           }
         }
       }
-      __syncthreads();
     }
-    if (!row_ok || ox >= dW) continue;            // (no barrier below this point inside the iteration)
-    for (int cc = 0; cc < nc; ++cc) {
-      const size_t obase = (((size_t)n * C + c0 + cc) * dH + oy) * dW + ox;
-      float r[PX];
-      if (empty_box) {
-#pragma unroll
-        for (int j = 0; j < PX; ++j) r[j] = 0.f;
-      } else if (staged) {
-        SmemFetch f{stage[cc], bx0, by0, bw, bh};
-#pragma unroll
-        for (int j = 0; j < PX; ++j) r[j] = sample(f, cd[j], mode);
-      } else {
-        GlobalFetch<T> f{src + ((size_t)n * C + c0 + cc) * H * W, W, H};
-#pragma unroll
-        for (int j = 0; j < PX; ++j) r[j] = sample(f, cd[j], mode);
-      }
-      if (vec_ok && ox + PX <= dW) {
-        using V = typename Vec4<T>::type;
-        T b[PX], o[PX];
-        if (mask_src != nullptr) *reinterpret_cast<V*>(b) = __ldg(reinterpret_cast<const V*>(bg + obase));
-#pragma unroll
-        for (int j = 0; j < PX; ++j) o[j] = keep[j] ? from_f<T>(r[j]) : b[j];
-        *reinterpret_cast<V*>(out + obase) = *reinterpret_cast<V*>(o);
-      } else {
-        for (int j = 0; j < PX && ox + j < dW; ++j)
-          out[obase + j] = keep[j] ? from_f<T>(r[j]) : bg[obase + j];
-      }
-    }
+    if (staged) __syncthreads();                    // set it&1 may be refilled by the next iteration's prefetch
   }
 }
 
@@ -201,10 +244,10 @@ extern "C" int ff_warp_affine_blend(const void* src, const float* theta, const u
   FF_REQUIRE(mode == 0 || mode == 1, "ff_warp_affine_blend: mode must be 0 (bilinear) or 1 (nearest)");
   FF_REQUIRE(dtype == FF_DT_F32 || dtype == FF_DT_BF16, "ff_warp_affine_blend: dtype must be f32 or bf16");
   const int tiles_x = (dW + TILE_X - 1) / TILE_X, tiles_y = (dH + TILE_Y - 1) / TILE_Y;
-  // channel chunks: enough CTAs to cover the 148 SMs a few times, but as few as possible so that the per-tile
-  // coordinate / mask work is amortised over many channels
+  // channel chunks: enough CTAs to cover the 148 SMs (2 resident CTAs each) a few times, but as few as possible so
+  // that the per-tile coordinate / mask work is amortised over many channels and the copy pipeline gets long
   const long long tiles = (long long)tiles_x * tiles_y * N;
-  int chunks = (int)((148LL * 8 + tiles - 1) / tiles);
+  int chunks = (int)((148LL * 2 * 4 + tiles - 1) / tiles);
   if (chunks < 1) chunks = 1;
   if (chunks > (C + CH_PER_ITER - 1) / CH_PER_ITER) chunks = (C + CH_PER_ITER - 1) / CH_PER_ITER;
   int ch_per_cta = (C + chunks - 1) / chunks;
@@ -216,12 +259,23 @@ extern "C" int ff_warp_affine_blend(const void* src, const float* theta, const u
                      ((size_t)H * W * es % 16 == 0) && ((size_t)dH * dW * es % 16 == 0);
   dim3 grid(tiles_x * tiles_y, chunks, N);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e1 = cudaFuncSetAttribute(warp_affine_blend_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          SMEM_BYTES);
+    cudaError_t e2 = cudaFuncSetAttribute(warp_affine_blend_kernel<__nv_bfloat16>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e1 != cudaSuccess || e2 != cudaSuccess)
+      return ff::fail(FF_E_CUDA, "ff_warp_affine_blend: cudaFuncSetAttribute: %s",
+                      cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    configured = true;
+  }
   if (dtype == FF_DT_F32)
-    warp_affine_blend_kernel<float><<<grid, THREADS, 0, st>>>(
+    warp_affine_blend_kernel<float><<<grid, THREADS, SMEM_BYTES, st>>>(
         static_cast<const float*>(src), theta, mask_src, static_cast<const float*>(bg), static_cast<float*>(out),
         mask_out, C, H, W, dH, dW, mode, ch_per_cta, tiles_x, vec_ok);
   else
-    warp_affine_blend_kernel<__nv_bfloat16><<<grid, THREADS, 0, st>>>(
+    warp_affine_blend_kernel<__nv_bfloat16><<<grid, THREADS, SMEM_BYTES, st>>>(
         static_cast<const __nv_bfloat16*>(src), theta, mask_src, static_cast<const __nv_bfloat16*>(bg),
         static_cast<__nv_bfloat16*>(out), mask_out, C, H, W, dH, dW, mode, ch_per_cta, tiles_x, vec_ok);
   return ff::check_launch("ff_warp_affine_blend");

@@ -121,7 +121,7 @@ def ddim_inv_step(eps, x, sqrt_1m_at, sqrt_at, sqrt_an, c_next, want_pred_x0=Fal
 # ---------------------------------------------------------------------------------------------------------------
 # (b) warp + blend
 # ---------------------------------------------------------------------------------------------------------------
-def warp_affine_blend(src, theta, dsize=None, mask_src=None, bg=None, mode="bilinear", want_mask=False):
+def warp_affine_blend(src, theta, dsize=None, mask_src=None, bg=None, mode="bilinear", want_mask=False, out=None):
     """src [N,C,H,W] f32/bf16, theta [N,2,3] (or [2,3]) f32 normalised (param2theta), dsize (width, height).
     With mask_src [N,H,W] u8 + bg [N,C,dH,dW]: out = warped_mask ? warped_src : bg (re_edit_2d blend)."""
     if src.dtype not in _DT:
@@ -144,7 +144,12 @@ def warp_affine_blend(src, theta, dsize=None, mask_src=None, bg=None, mode="bili
         _chk(bg, src.dtype, "bg", 4)
         if bg.shape != (N, Cc, dH, dW):
             raise ValueError("bg must be [N,C,dH,dW]")
-    out = torch.empty((N, Cc, dH, dW), dtype=src.dtype, device=src.device)
+    if out is None:
+        out = torch.empty((N, Cc, dH, dW), dtype=src.dtype, device=src.device)
+    else:
+        _chk(out, src.dtype, "out", 4)
+        if out.shape != (N, Cc, dH, dW):
+            raise ValueError("out must be [N,C,dH,dW]")
     mask_out = torch.empty((N, dH, dW), dtype=torch.uint8, device=src.device) if (want_mask and mask_src is not None) else None
     rc = _lib.load().ff_warp_affine_blend(_ptr(src), _ptr(theta), _ptr(mask_src), _ptr(bg), _ptr(out), _ptr(mask_out),
                                           N, Cc, H, W, dH, dW, 0 if mode == "bilinear" else 1, _DT[src.dtype],

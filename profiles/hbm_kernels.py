@@ -1,0 +1,58 @@
+"""Achieved HBM bandwidth of the HBM-bound kernels (b) warp+blend and (c) CFG+DDIM step on L2-exceeding synthetic batches
+(at real sizes -- 128 KiB of latents per edit -- these launches are latency-bound, so the roofline is
+demonstrated at n_edits = 2048 / N*C = 32768).  CUDA-event timing, 3 warm-ups, inputs >> 126 MB L2.
+ALGORITHMIC bytes: (c) eps_u, eps_c, x, noise read + x_prev written (5 tensors of 2*4*h*w*4 B per edit) + 2*h*w mask bytes;
+(c-inv) eps, x read + x_next written; (b) src read once + bg read + out written + mask bytes."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from freefine_b200 import ops
+
+dev = torch.device("cuda:0")
+peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
+    os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
+
+
+def timeit(fn, reps=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    ev[0].record()
+    for i in range(reps):
+        fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(reps))
+    return ms[0], ms[len(ms) // 2]
+
+
+res = {}
+E, h, w = 2048, 64, 64
+eps4 = torch.randn(E, 4, 4, h, w, device=dev)
+x = torch.randn(E, 2, 4, h, w, device=dev)
+noise = torch.randn(E, 2, 4, h, w, device=dev)
+cm = torch.randint(0, 3, (E, h, w), device=dev, dtype=torch.uint8)
+vm = torch.randint(0, 3, (E, h, w), device=dev, dtype=torch.uint8)
+out = torch.empty_like(x)
+k = dict(sqrt_1m_at=0.6, sqrt_at=0.8, sqrt_ap=0.85, c_ddim=0.52, c_ddpm=0.5, sigma=0.14)
+best, med = timeit(lambda: ops.ddim_cfg_step(eps4, x, noise, cm, vm, 7.5, out=out, **k))
+byt = 5 * x.numel() * 4 + 2 * E * h * w
+res["ddim_cfg_step"] = dict(n_edits=E, bytes=byt, ms_best=best, ms_median=med, gbs=byt / best / 1e6, frac=byt / best / 1e6 / peak)
+eps = torch.randn(E, 2, 4, h, w, device=dev)
+best, med = timeit(lambda: ops.ddim_inv_step(eps, x, 0.6, 0.8, 0.85, 0.52))
+byt = 3 * x.numel() * 4
+res["ddim_inv_step"] = dict(n=x.numel(), bytes=byt, ms_best=best, ms_median=med, gbs=byt / best / 1e6, frac=byt / best / 1e6 / peak)
+del eps4, noise, eps
+for NC, label in ((32768, "warp_blend_large"), (2048, "warp_blend_l2_resident")):
+    src = torch.randn(1, NC, 64, 64, device=dev)
+    bg = torch.randn(1, NC, 64, 64, device=dev)
+    mask = (torch.rand(1, 64, 64, device=dev) > 0.5).to(torch.uint8)
+    th = torch.tensor([[[0.95, 0.2, 0.05], [-0.2, 0.95, -0.03]]], device=dev)
+    outb = torch.empty_like(bg)
+    best, med = timeit(lambda: ops.warp_affine_blend(src, th, mask_src=mask, bg=bg, out=outb))
+    byt = 3 * src.numel() * 4 + 2 * 64 * 64
+    res[label] = dict(NC=NC, bytes=byt, ms_best=best, ms_median=med, gbs=byt / best / 1e6, frac=byt / best / 1e6 / peak)
+    del src, bg, outb
+res["peak_hbm_gbs"] = peak
+print(json.dumps(res, indent=1))

@@ -369,11 +369,15 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   const uint32_t sKV = smem_base + C::SMEM_Q;
   const uint32_t bar_base = sKV + C::NSTAGE * C::SMEM_STAGE;
   const uint32_t bar_q = bar_base;
-  // [2] each, indexed by tile parity: s_full / p_full per S buffer; o_done alternates too, so that a warp that skipped
-  // o_done waits for several tiles can never be fooled by phase-parity aliasing (a phase is 2 tiles long)
-  const uint32_t bar_s = bar_base + 16, bar_p = bar_base + 32, bar_o = bar_base + 48;
-  const uint32_t bar_kv_full = bar_base + 64, bar_kv_empty = bar_base + 64 + 8 * C::NSTAGE;
-  const uint32_t tmem_slot = bar_base + 64 + 16 * C::NSTAGE;            // u32 written by tcgen05.alloc
+  // [2] each, indexed by tile parity: s_full / p_full per S buffer.  There is deliberately NO "PV done" barrier that
+  // softmax threads wait on only occasionally: an mbarrier wait is exact only if the waiter has observed every earlier
+  // phase (parity aliasing otherwise -- a skipped-phase wait fell through on hardware while PV was still accumulating).
+  // "PV(t) has completed" is instead derived from s_full, which every softmax thread observes phase by phase:
+  // QK(t+2) is issued after PV(t), and a commit arrives only when ALL earlier MMAs of the issuing thread are done, so
+  // s_full of tile t+2 implies PV(t) (and s_full of tile t+1 implies PV(t-1)).
+  const uint32_t bar_s = bar_base + 16, bar_p = bar_base + 32;
+  const uint32_t bar_kv_full = bar_base + 48, bar_kv_empty = bar_base + 48 + 8 * C::NSTAGE;
+  const uint32_t tmem_slot = bar_base + 48 + 16 * C::NSTAGE;            // u32 written by tcgen05.alloc
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
@@ -391,8 +395,6 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     mbar_init(bar_s + 8, 1);
     mbar_init(bar_p, BM);
     mbar_init(bar_p + 8, BM);
-    mbar_init(bar_o, 1);
-    mbar_init(bar_o + 8, 1);
     for (int i = 0; i < C::NSTAGE; ++i) {
       mbar_init(bar_kv_full + 8 * i, 1);
       mbar_init(bar_kv_empty + 8 * i, 1);
@@ -483,7 +485,6 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           mma_ts(tmem + C::TMEM_O, a_hi + 8, vdesc, idesc_pv, 1u);
         }
         tc_commit(bar_kv_empty + 8 * stage);
-        tc_commit(bar_o + 8 * (t & 1));
       };
 #pragma unroll 1
       for (int ip = 0; ip < n_pass; ++ip) {
@@ -522,7 +523,11 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           }
         }
       }
+      // two virtual s_full commits stand in for the QK(n), QK(n+1) that do not exist, so that "s_full(t+1) => PV(t-1)"
+      // and "s_full(t+2) => PV(t)" also hold for the last tiles of the CTA
+      tc_commit(bar_s + 8 * (it & 1));
       if (pend) issue_pv(it - 1, pend_stage, pend_first);
+      tc_commit(bar_s + 8 * ((it + 1) & 1));
     }
   } else {
     // ===================================== softmax + epilogue ===============================
@@ -550,7 +555,6 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       float m_used = 0.f;
       float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
       bool first = true;
-      bool s_ready = false;      // outcome of the early probe of this tile's s_full phase
 #pragma unroll 1
       for (int seg = 0; seg < 2; ++seg) {
         const SegCtx sg = seg ? cx.s1 : cx.s0;
@@ -563,17 +567,9 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           const int cls = tile_class(sg, j, p);
           if (tile_skip(cx, sg, cls, p.s_kv)) continue;
           FF_TRACE(it, 30);
-          if (!s_ready) mbar_wait(bar_s + 8 * (it & 1), (it >> 1) & 1);
+          mbar_wait(bar_s + 8 * (it & 1), (it >> 1) & 1);
           FF_TRACE(it, 31);
           tc_fence_after();
-          // o_done protocol.  o_done alternates between two mbarriers (tile parity), and every thread OBSERVES every
-          // phase of each of them in order: phase it-2 is probed here without blocking (it completed long ago; the
-          // probe's latency hides behind the tile) and, if the probe failed, waited for at the end of the tile.  Only
-          // then is a blocking wait for phase it-1 (rescale below, or end of pass) exact: having observed it-3 on the
-          // same barrier, that barrier can only be in phase it-1 or later.  (Waiting ONLY when a rescale was needed let
-          // a late mbarrier arrival alias the phase parity: the wait fell through while PV(it-1) was still
-          // accumulating -- observed on hardware with 2 CTAs/SM and a deep K/V ring.)
-          const bool o2_done = it >= 2 ? mbar_test(bar_o + 8 * (it & 1), ((it - 2) >> 1) & 1) : true;
           const uint32_t tS = tlane + C::TMEM_S + BN * (it & 1);     // this tile's S / P buffer
           // ---- sweep 1: row max over ALL 64 columns (an upper bound of the max over the allowed keys is all the
           // softmax needs: bf16/fp32 keep their relative precision whatever the reference point; padded columns are 0)
@@ -615,7 +611,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           }
           if (__any_sync(0xffffffffu, grow)) {
             FF_TRACE(it, 32);
-            mbar_wait(bar_o + 8 * ((it - 1) & 1), ((it - 1) >> 1) & 1);   // PV(it-1) finished writing O
+            mbar_wait(bar_s + 8 * ((it + 1) & 1), ((it + 1) >> 1) & 1);   // s_full(it+1) => PV(it-1) finished writing O
             FF_TRACE(it, 33);
             tc_fence_after();
 #pragma unroll
@@ -682,8 +678,6 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           tc_fence_before();
           mbar_arrive(bar_p + 8 * (it & 1));
           FF_TRACE(it, 34);
-          if (!o2_done) mbar_wait(bar_o + 8 * (it & 1), ((it - 2) >> 1) & 1);             // observe phase it-2 (see above)
-          s_ready = mbar_test(bar_s + 8 * ((it + 1) & 1), ((it + 1) >> 1) & 1);            // early probe of the next tile
           first = false;
           ++it;
         }
@@ -691,7 +685,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       if (first) continue;     // (defensive) no tile of this pass was processed: nothing to add
       // ---- end of pass: acc += weight * roww / l * O
       FF_TRACE(it, 35);
-      mbar_wait(bar_o + 8 * ((it - 1) & 1), ((it - 1) >> 1) & 1);
+      mbar_wait(bar_s + 8 * ((it + 1) & 1), ((it + 1) >> 1) & 1);   // s_full(L+2) => PV(L) of this pass's last tile L = it-1
       FF_TRACE(it, 36);
       tc_fence_after();
       const float l = (la.x + la.y) + (lb.x + lb.y);

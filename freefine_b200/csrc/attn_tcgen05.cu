@@ -325,6 +325,16 @@ __device__ __forceinline__ int tile_class(const SegCtx& g, int j, const KParams&
   return a == 0xffffffffu ? TILE_IN : (o == 0 ? TILE_OUT : TILE_MIX);
 }
 
+// Maximal run of K/V tiles [j, hi) that share the class of tile j.  With sorted keys (PREFIX) or no key mask a
+// segment decomposes into at most four runs (IN*, MIX?, OUT*, ragged?), so every per-tile decision -- class, skip,
+// the per-row predicate -- is taken once per run instead of once per tile; in bit-vector mode a run is one tile.
+__device__ __forceinline__ int run_end(const SegCtx& g, int j, int cls, const KParams& p) {
+  if (cls == TILE_MIX || (g.kmask >= 0 && !g.prefix)) return j + 1;
+  const int n_full = p.s_kv / BN;                                      // tiles without ragged columns
+  if (cls == TILE_IN) { const int t = g.T / BN; return t < n_full ? t : n_full; }
+  return n_full;                                                       // ALL or OUT: up to the ragged tile
+}
+
 // one predicate per row for IN/OUT/ALL tiles
 __device__ __forceinline__ bool row_allowed(int cls, bool flip, bool uniform) {
   return uniform || cls == TILE_ALL || ((cls == TILE_IN) != flip);
@@ -443,8 +453,12 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           const SegCtx sg = seg ? cx.s1 : cx.s0;
           if (sg.kv < 0) continue;
 #pragma unroll 1
-          for (int j = 0; j < n_kv_tiles; ++j) {
-            if (tile_skip(cx, sg, tile_class(sg, j, p), p.s_kv)) continue;
+          for (int j0 = 0; j0 < n_kv_tiles;) {
+            const int cls = tile_class(sg, j0, p), j1 = run_end(sg, j0, cls, p), jb = j0;
+            j0 = j1;
+            if (tile_skip(cx, sg, cls, p.s_kv)) continue;
+#pragma unroll 1
+            for (int j = jb; j < j1; ++j) {
             const int stage = it % C::NSTAGE, use = it / C::NSTAGE;
             FF_TRACE(it, 10);
             if (use > 0) mbar_wait(bar_kv_empty + 8 * stage, (use - 1) & 1);
@@ -457,6 +471,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
               tma_load_4d(sV + kt * KV_BYTES, &tm_v, kt * BOX_COLS, head, j * BN, sg.kv, full);
             }
             ++it;
+            }
           }
         }
       }
@@ -503,8 +518,12 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           const SegCtx sg = seg ? cx.s1 : cx.s0;
           if (sg.kv < 0) continue;
 #pragma unroll 1
-          for (int j = 0; j < n_kv_tiles; ++j) {
-            if (tile_skip(cx, sg, tile_class(sg, j, p), p.s_kv)) continue;
+          for (int j0 = 0; j0 < n_kv_tiles;) {
+            const int cls = tile_class(sg, j0, p), j1 = run_end(sg, j0, cls, p), jb = j0;
+            j0 = j1;
+            if (tile_skip(cx, sg, cls, p.s_kv)) continue;
+#pragma unroll 1
+            for (int j = jb; j < j1; ++j) {
             const int stage = it % C::NSTAGE, use = it / C::NSTAGE;
             const uint32_t sK = sKV + stage * C::SMEM_STAGE;
             FF_TRACE(it, 21);
@@ -526,6 +545,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             pend_first = first;
             first = false;
             ++it;
+            }
           }
         }
       }
@@ -569,9 +589,13 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         const bool uniform = uniform_for(cx, sg, flip, p.s_kv);   // quirk Q4 (per row: depends on its flip value)
         const float sc = uniform ? 0.f : p.scale_log2;
 #pragma unroll 1
-        for (int j = 0; j < n_kv_tiles; ++j) {
-          const int cls = tile_class(sg, j, p);
+        for (int j0 = 0; j0 < n_kv_tiles;) {
+          const int cls = tile_class(sg, j0, p), j1 = run_end(sg, j0, cls, p), jb = j0;
+          j0 = j1;
           if (tile_skip(cx, sg, cls, p.s_kv)) continue;
+          const bool row_ok_cls = row_allowed(cls, flip, uniform);   // per-row predicate of this whole run
+#pragma unroll 1
+          for (int j = jb; j < j1; ++j) {
           FF_TRACE(it, 30);
           mbar_wait(bar_s + 8 * (it & 1), (it >> 1) & 1);
           FF_TRACE(it, 31);
@@ -638,7 +662,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           // lo -> [16ks+8,16ks+16): only columns this thread has already consumed.
           if (cls != TILE_MIX) {
             // one predicate per row: bias -m (allowed) or -inf (row reads nothing from this tile -> p = 0)
-            const float nb = row_allowed(cls, flip, uniform) ? -m_used : -INFINITY;
+            const float nb = row_ok_cls ? -m_used : -INFINITY;
             float ca[16], cb[16];
             uint32_t hl[16];
             tmem_ld16(tS, ca);
@@ -686,6 +710,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           FF_TRACE(it, 34);
           first = false;
           ++it;
+          }
         }
       }
       if (first) continue;     // (defensive) no tile of this pass was processed: nothing to add

@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--preset", default="sd15")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--channels-last", action="store_true", help="run the (library) UNet body in channels_last")
     return ap.parse_args()
 
 
@@ -206,6 +207,8 @@ def run_ours(args):
     torch.backends.cudnn.allow_tf32 = True
 
     parts = build_standin(args.preset, device=dev, dtype=torch.bfloat16)
+    if args.channels_last:
+        parts.unet.to(memory_format=torch.channels_last)
     controller = Attention_Modulator(start_layer=10)
     pipe = FreeFinePipeline.from_parts(parts, controller, device=dev)
     register_attention_control(pipe, controller)

@@ -157,7 +157,7 @@ class Attention_Modulator(AttentionControl):
         return self.get_down_h_w(d_ratio, H, W, seq)
 
     # ---- masks -> bit-vector tables ------------------------------------------------------------------------------
-    def _table(self, kind: str, seq: int, masks):
+    def _table(self, kind: str, seq: int, masks, min_tokens: int = 0):
         """Bit-vector table of `masks` (list of [H,W]/[E,H,W] tensors, stacked edit-major) at `seq` tokens.
         Cached until any mask tensor is replaced or modified in place."""
         sig = tuple((m.data_ptr(), m._version, tuple(m.shape)) for m in masks)
@@ -174,7 +174,10 @@ class Attention_Modulator(AttentionControl):
         h, w = self._grid(H, W, seq)
         # row id = e*len(masks) + j
         stacked = torch.stack(stacks, dim=1).reshape(E * len(stacks), H, W)
-        bits, pop = ops.mask_downsample_pack(stacked, h, w)
+        # (the kernel wants the table wide enough for max(S_q, S_kv) tokens: cross attention has 77 keys)
+        words = ops.mask_words(max(seq, min_tokens))
+        bits = torch.zeros((stacked.shape[0], words), dtype=torch.int32, device=stacked.device)
+        bits, pop = ops.mask_downsample_pack(stacked, h, w, bits=bits)
         self._tables[(kind, seq)] = (sig, bits, pop)
         return bits, pop
 
@@ -345,7 +348,7 @@ class Attention_Modulator(AttentionControl):
         if key.shape[0] != nu + L:
             raise ValueError(f"expected {nu + L} prompt streams, got {key.shape[0]}")
         tg = self.tgt_masks if torch.is_tensor(self.tgt_masks) else torch.stack(list(self.tgt_masks))
-        bits, pop = self._table("cross_compose", S, [m for m in tg])
+        bits, pop = self._table("cross_compose", S, [m for m in tg], min_tokens=key.shape[1])
 
         def build():
             p = plans._empty(Bq, self.heads)
@@ -453,7 +456,9 @@ def _register(model, controller, flavour: str):
                 hidden_states = hidden_states.transpose(-1, -2).reshape(batch_size, channel, height, width)
             if self.residual_connection:
                 hidden_states = hidden_states + residual
-            return hidden_states / self.rescale_output_factor
+            if self.rescale_output_factor != 1.0:      # x / 1.0 == x exactly: skip the extra pass over [B,S,C]
+                hidden_states = hidden_states / self.rescale_output_factor
+            return hidden_states
 
         return forward
 

@@ -38,21 +38,26 @@ template <int V>  // V = 4 (float4 path, hw % 4 == 0) or 1
 __global__ void __launch_bounds__(256)
 ddim_cfg_step_kernel(const float* __restrict__ eps4, const float* __restrict__ x, const float* __restrict__ noise,
                      const uint8_t* __restrict__ cfg_mask, const uint8_t* __restrict__ var_mask, StepCoef k,
-                     float* __restrict__ x_prev, float* __restrict__ pred_x0, int n_edits, int C, int hw, int spe) {
-  // spe = streams per edit in eps4: 4 -> [u_e,u_r,c_e,c_r] (CFG fused here), 2 -> eps already combined [edit, ref]
+                     float* __restrict__ x_prev, float* __restrict__ pred_x0, int n_edits, int C, int hw, int spe,
+                     int so, int cs) {
+  // spe = streams per edit in eps4, so = latent streams per edit (2: [edit, ref], 1: edit only), cs = distance from an
+  // unconditional stream to its conditional partner (0: eps is already guidance-combined):
+  //   edit / bg-gen  spe 4, so 2, cs 2   [u_e,u_r,c_e,c_r]          (model.py:594-617)
+  //   ctrl_step only spe 2, so 2, cs 0
+  //   compose        spe N+2, so 1, cs N+1   [e, r_1..r_N, c_e]     (model.py:407-431)
   const int hwv = hw / V;
-  const long long total = (long long)n_edits * 2 * C * hwv;
+  const long long total = (long long)n_edits * so * C * hwv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int p = (int)(i % hwv);
     long long r = i / hwv;
     const int c = (int)(r % C);
     r /= C;
-    const int s = (int)(r & 1);
-    const int e = (int)(r >> 1);
+    const int s = so == 2 ? (int)(r & 1) : 0;
+    const int e = so == 2 ? (int)(r >> 1) : (int)r;
     const long long off_u = (((long long)(e * spe + s) * C + c) * hw) + (long long)p * V;
-    const long long off_c = spe == 4 ? (((long long)(e * 4 + 2 + s) * C + c) * hw) + (long long)p * V : off_u;
-    const long long off_x = (((long long)(e * 2 + s) * C + c) * hw) + (long long)p * V;
+    const long long off_c = (((long long)(e * spe + s + cs) * C + c) * hw) + (long long)p * V;
+    const long long off_x = (((long long)(e * so + s) * C + c) * hw) + (long long)p * V;
     const long long off_m = (long long)e * hw + (long long)p * V;
     float eu[V], ec[V], xv[V], nz[V], xp[V], x0[V];
     uint8_t cm[V], vm[V];
@@ -78,7 +83,7 @@ ddim_cfg_step_kernel(const float* __restrict__ eps4, const float* __restrict__ x
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       const uint8_t m = s == 0 ? vm[j] : (uint8_t)1;
-      step_elem(eu[j], ec[j], xv[j], noise ? nz[j] : 0.f, spe == 4, cfg_mask != nullptr, cfg_mask ? cm[j] : (uint8_t)1,
+      step_elem(eu[j], ec[j], xv[j], noise ? nz[j] : 0.f, cs != 0, cfg_mask != nullptr, cfg_mask ? cm[j] : (uint8_t)1,
                 m, sd, cd, noise != nullptr, k, xp[j], x0[j]);
     }
     if (V == 4) {
@@ -132,7 +137,7 @@ inline int grid_for(long long work_items, int block) {
 
 }  // namespace
 
-static int launch_step(const char* what, const float* eps, int spe, const float* x, const float* noise,
+static int launch_step(const char* what, const float* eps, int spe, int so, int cs, const float* x, const float* noise,
                        const uint8_t* cfg_mask, const uint8_t* var_mask, const StepCoef& k, float* x_prev,
                        float* pred_x0, int32_t n_edits, int32_t C, int32_t h, int32_t w, void* stream) {
   if (!(eps && x && var_mask && x_prev)) return ff::fail(FF_E_INVALID, "%s: null pointer", what);
@@ -145,13 +150,13 @@ static int launch_step(const char* what, const float* eps, int spe, const float*
                    (reinterpret_cast<uintptr_t>(var_mask) % 4 == 0) &&
                    (!cfg_mask || reinterpret_cast<uintptr_t>(cfg_mask) % 4 == 0);
   if (vec) {
-    const long long items = (long long)n_edits * 2 * C * (hw / 4);
+    const long long items = (long long)n_edits * so * C * (hw / 4);
     ddim_cfg_step_kernel<4><<<grid_for(items, 256), 256, 0, st>>>(eps, x, noise, cfg_mask, var_mask, k, x_prev,
-                                                                   pred_x0, n_edits, C, hw, spe);
+                                                                   pred_x0, n_edits, C, hw, spe, so, cs);
   } else {
-    const long long items = (long long)n_edits * 2 * C * hw;
+    const long long items = (long long)n_edits * so * C * hw;
     ddim_cfg_step_kernel<1><<<grid_for(items, 256), 256, 0, st>>>(eps, x, noise, cfg_mask, var_mask, k, x_prev,
-                                                                   pred_x0, n_edits, C, hw, spe);
+                                                                   pred_x0, n_edits, C, hw, spe, so, cs);
   }
   return ff::check_launch(what);
 }
@@ -161,8 +166,8 @@ extern "C" int ff_ddim_cfg_step(const float* eps4, const float* x, const float* 
                                 float sqrt_ap, float c_ddim, float c_ddpm, float sigma, float* x_prev,
                                 float* pred_x0, int32_t n_edits, int32_t C, int32_t h, int32_t w, void* stream) {
   StepCoef k{guidance_scale, sqrt_1m_at, sqrt_at, sqrt_ap, c_ddim, c_ddpm, sigma};
-  return launch_step("ff_ddim_cfg_step", eps4, 4, x, noise, cfg_mask, var_mask, k, x_prev, pred_x0, n_edits, C, h, w,
-                     stream);
+  return launch_step("ff_ddim_cfg_step", eps4, 4, 2, 2, x, noise, cfg_mask, var_mask, k, x_prev, pred_x0, n_edits, C, h,
+                     w, stream);
 }
 
 extern "C" int ff_ddim_step(const float* eps2, const float* x, const float* noise, const uint8_t* var_mask,
@@ -170,8 +175,19 @@ extern "C" int ff_ddim_step(const float* eps2, const float* x, const float* nois
                             float* x_prev, float* pred_x0, int32_t n_edits, int32_t C, int32_t h, int32_t w,
                             void* stream) {
   StepCoef k{0.f, sqrt_1m_at, sqrt_at, sqrt_ap, c_ddim, c_ddpm, sigma};
-  return launch_step("ff_ddim_step", eps2, 2, x, noise, nullptr, var_mask, k, x_prev, pred_x0, n_edits, C, h, w,
+  return launch_step("ff_ddim_step", eps2, 2, 2, 0, x, noise, nullptr, var_mask, k, x_prev, pred_x0, n_edits, C, h, w,
                      stream);
+}
+
+extern "C" int ff_ddim_cfg_step_compose(const float* eps, int32_t streams_per_edit, const float* x, const float* noise,
+                                        const uint8_t* cfg_mask, const uint8_t* var_mask, float guidance_scale,
+                                        float sqrt_1m_at, float sqrt_at, float sqrt_ap, float c_ddim, float c_ddpm,
+                                        float sigma, float* x_prev, float* pred_x0, int32_t n_edits, int32_t C, int32_t h,
+                                        int32_t w, void* stream) {
+  FF_REQUIRE(streams_per_edit >= 2, "ff_ddim_cfg_step_compose: streams_per_edit=%d < 2", streams_per_edit);
+  StepCoef k{guidance_scale, sqrt_1m_at, sqrt_at, sqrt_ap, c_ddim, c_ddpm, sigma};
+  return launch_step("ff_ddim_cfg_step_compose", eps, streams_per_edit, 1, streams_per_edit - 1, x, noise, cfg_mask,
+                     var_mask, k, x_prev, pred_x0, n_edits, C, h, w, stream);
 }
 
 extern "C" int ff_ddim_inv_step(const float* eps, const float* x, float sqrt_1m_at, float sqrt_at, float sqrt_an,

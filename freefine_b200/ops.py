@@ -103,6 +103,30 @@ def ddim_step(eps2, x, noise, var_mask, sqrt_1m_at, sqrt_at, sqrt_ap, c_ddim, c_
     return (x_prev, x0) if want_pred_x0 else x_prev
 
 
+def ddim_cfg_step_compose(eps, streams_per_edit, x, noise, cfg_mask, var_mask, guidance_scale, sqrt_1m_at, sqrt_at,
+                          sqrt_ap, c_ddim, c_ddpm, sigma):
+    """Composition step (model.py:418-431): eps [E*(N+2),C,h,w] = [e, r_1..r_N, c_e] per edit, x [E,C,h,w] (edit stream
+    only); guidance from streams 0 and N+1, single-stream masked DDPM/DDIM update."""
+    _chk(eps, torch.float32, "eps")
+    _chk(x, torch.float32, "x")
+    Cc, h, w = x.shape[-3:]
+    E = x.numel() // (Cc * h * w)
+    if eps.numel() != E * streams_per_edit * Cc * h * w:
+        raise ValueError("eps must hold streams_per_edit streams per edit")
+    _chk(var_mask, torch.uint8, "var_mask")
+    if cfg_mask is not None:
+        _chk(cfg_mask, torch.uint8, "cfg_mask")
+    if noise is not None:
+        _chk(noise, torch.float32, "noise")
+    x_prev = torch.empty_like(x)
+    rc = _lib.load().ff_ddim_cfg_step_compose(_ptr(eps), streams_per_edit, _ptr(x), _ptr(noise), _ptr(cfg_mask), _ptr(var_mask),
+                                              guidance_scale, sqrt_1m_at, sqrt_at, sqrt_ap, c_ddim, c_ddpm, sigma,
+                                              _ptr(x_prev), None, E, Cc, h, w, _stream())
+    _lib.check(rc, "ff_ddim_cfg_step_compose")
+    _count("ff_ddim_cfg_step_compose")
+    return x_prev
+
+
 def ddim_inv_step(eps, x, sqrt_1m_at, sqrt_at, sqrt_an, c_next, want_pred_x0=False):
     """reference inv_step, model.py:109-132."""
     _chk(eps, torch.float32, "eps")

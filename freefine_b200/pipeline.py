@@ -578,6 +578,177 @@ class FreeFinePipeline:
         return edit
 
     # ------------------------------------------------------------------------------------------------------------
+    # cross-image composition / appearance transfer (reference model.py:301-435, :1051-1086, :1367-1388, :1515-1609,
+    # :1701-1750); attention side: register_attention_control_compose + Temporal_contextal_attention_compose
+    # ------------------------------------------------------------------------------------------------------------
+    def prepare_composition_masks(self, ori_mask_lists, tgt_mask_lists, sup_res_w, sup_res_h, init_code,
+                                  dil_completion=False, dil_factor=15, draw_mask=None, appearance_transfer=False):
+        """reference model.py:1515-1609 -> (tgt_masks [n_tgt+1,H,W], ori_masks [N,H,W], local_perturbation [lat],
+        completion_mask_cfg [lat]); uint8 algebra as the reference."""
+        P = lambda m: self.prepare_tensor_mask(m, sup_res_w, sup_res_h)
+        lat = (init_code.shape[2], init_code.shape[3])
+        down = lambda t: F.interpolate(t[None, None], lat, mode='nearest').squeeze(0).squeeze(0)
+        ori = [P(m) for m in ori_mask_lists]
+        tgt = []
+        lp, fg = torch.zeros_like(ori[0]), torch.zeros_like(ori[0])
+        if appearance_transfer:
+            for shifted in tgt_mask_lists:
+                d = P(self.dilate_mask(shifted, dil_factor))
+                tgt.append(d)
+                lp += d
+            lp[lp > 0] = 1
+            tgt.append(1 - lp)
+            lp = down(lp)
+            return torch.stack(tgt), torch.stack(ori), lp, deepcopy(lp)
+        if draw_mask is None:
+            for shifted in tgt_mask_lists:
+                d = P(self.dilate_mask(shifted, dil_factor))
+                sh = P(shifted)
+                tgt.append(d if dil_completion else sh)
+                fg += sh
+                lp += d
+            fg[fg > 0] = 1
+            lp[lp > 0] = 1
+            tgt.append(1 - fg if dil_completion else 1 - lp)
+            lp = down(lp * (1 - fg))
+            return torch.stack(tgt), torch.stack(ori), lp, (deepcopy(lp) if dil_completion else torch.zeros_like(lp))
+        for i, shifted in enumerate(tgt_mask_lists):
+            sh = P(shifted)
+            d = P(draw_mask[i]) + sh
+            d[d > 0] = 1
+            tgt.append(d)
+            fg += sh
+            lp += d
+        fg[fg > 0] = 1
+        lp[lp > 0] = 1
+        tgt.append(1 - lp)
+        lp = down(lp * (1 - fg))
+        return torch.stack(tgt), torch.stack(ori), lp, lp
+
+    @torch.no_grad()
+    def DDIM_inversion_func_compose(self, img, compose_imgs, prompt, num_step, start_step=0, verbose=False):
+        """reference model.py:1367-1388: invert [coarse, ref_1..ref_N] together."""
+        source = torch.cat([self.preprocess_image(im, self.device) for im in [img] + list(compose_imgs)])
+        _, latents_list = self.invert(source, prompt, guidance_scale=1.0, num_inference_steps=num_step,
+                                      num_actual_inference_steps=num_step - start_step, return_intermediates=True,
+                                      verbose=verbose)
+        self.controller.reset()
+        return latents_list
+
+    @torch.no_grad()
+    def forward_sampling_compose(self, prompt, prompt_embeds=None, refer_latents=None, batch_size=1, end_step=None,
+                                 height=512, width=512, num_inference_steps=50, num_actual_inference_steps=None,
+                                 guidance_scale=7.5, latents=None, unconditioning=None, neg_prompt=None,
+                                 return_intermediates=False, eta=0.0, end_scale=0.5, local_var_reg=None,
+                                 local_edit_text=True, cfg_masks_tensor=None, share_attn=True, method_type=None,
+                                 verbose=False, local_perturbation=True, **kwds):
+        """reference model.py:301-435: UNet streams [e, r_1..r_N, c_e]; text batch = (N+1) unconditional + the regional
+        prompts + ""; guidance from streams 0 and N+1; only the edit stream is stepped (ff_ddim_cfg_step_compose)."""
+        self.method_type = method_type
+        assert guidance_scale > 1.0, 'USING THIS MODULE CFG Must > 1.0'
+        c = self.controller
+        if share_attn:
+            if method_type == 'tca':
+                c.use_tca, c.layer_idx, c.method = True, list(range(10, 16)), 'tca'
+            elif method_type in ('mmsa', 'mmsa_es'):
+                c.use_tca, c.layer_idx, c.method = True, list(range(10, 16)), 'mmsa'
+            elif method_type == 'ssa':
+                c.use_style_align, c.method = True, 'ssa'
+            elif method_type == 'sdsa':
+                c.use_style_align, c.method = True, 'sdsa'
+        c.use_cfg = True
+        c.local_edit = local_edit_text
+        prompt = list(prompt) + [""]
+        c.prompt_length = len(prompt)
+        cond = self.get_text_embeddings(prompt)
+        n_lat = latents.shape[0]                                      # N+1 = [edit, ref_1..ref_N]
+        uncond = self.get_text_embeddings([neg_prompt if neg_prompt else ""] * n_lat)
+        text_embeddings = torch.cat([uncond, cond], dim=0)
+        self.scheduler.set_timesteps(num_inference_steps)
+        if num_actual_inference_steps is None:
+            num_actual_inference_steps = num_inference_steps
+        start_step = num_inference_steps - num_actual_inference_steps
+        C, h, w = latents.shape[1:]
+        edit = latents.float()[:1]
+        latents_list = [latents]
+        var_mask = local_var_reg if local_perturbation else torch.ones_like(local_var_reg)
+        for i, t in enumerate(self.scheduler.timesteps):
+            if i < start_step:
+                continue
+            refs = refer_latents[i - start_step + 1][1:].float()      # one step cleaner than t (quirk Q5)
+            if method_type == 'tca':
+                c.context_guidance = self.linear_param(i, start_step, end_step, num_inference_steps, end_scale=end_scale)
+            elif method_type == 'mmsa_es' and i >= end_step:
+                c.use_tca = False
+            model_inputs = torch.cat([edit, refs, edit])              # [e, r_1..r_N, c_e]
+            c.log_mask = False
+            noise_pred = self._unet(model_inputs, t, text_embeddings)
+            noise = None
+            if eta > 0:
+                noise = randn_tensor(edit.shape, device=edit.device, dtype=torch.float32).contiguous()
+            edit = ops.ddim_cfg_step_compose(noise_pred.contiguous(), model_inputs.shape[0], edit.contiguous(), noise,
+                                             self._var_mask(cfg_masks_tensor, 1, h, w) if local_edit_text else None,
+                                             self._var_mask(var_mask, 1, h, w), float(guidance_scale),
+                                             **self._ctrl_coefs(t, eta))
+            latents_list.append(edit[0])
+        image = self.latent2image(edit, return_type="pt")[0]
+        if return_intermediates:
+            return image, latents_list
+        return image, None
+
+    @torch.no_grad()
+    def Details_Preserving_regeneration_compose(self, source_image, inverted_latents, edit_prompt_list, ori_mask_lists,
+                                                tgt_mask_lists, draw_mask, num_steps=100, start_step=30, end_step=10,
+                                                eta=1, guidance_scale=7.5, dil_completion=False,
+                                                appearance_transfer=False, share_attn=True, method_type='tca',
+                                                verbose=False, local_text_edit=True, local_perturbation=True,
+                                                return_intermediates=False, use_share_attention=False, dil_factor=15,
+                                                end_scale=0.5):
+        """reference model.py:1701-1750"""
+        init_code_orig = deepcopy(inverted_latents[-1])
+        full_h, full_w = source_image.shape[:2]
+        tgt_masks, ori_masks, local_pert, comp_cfg = self.prepare_composition_masks(
+            ori_mask_lists, tgt_mask_lists, full_h, full_w, init_code_orig, dil_completion=dil_completion,
+            dil_factor=dil_factor, draw_mask=draw_mask, appearance_transfer=appearance_transfer)
+        c = self.controller
+        c.src_masks, c.tgt_masks = ori_masks.to(self.device), tgt_masks.to(self.device)
+        c.reset()
+        image, intermediates = self.forward_sampling_compose(
+            prompt=edit_prompt_list, refer_latents=inverted_latents[::-1], end_step=end_step,
+            batch_size=init_code_orig.shape[0], latents=init_code_orig, guidance_scale=guidance_scale,
+            num_inference_steps=num_steps, num_actual_inference_steps=num_steps - start_step, eta=eta,
+            local_var_reg=local_pert, local_edit_text=local_text_edit, cfg_masks_tensor=comp_cfg, share_attn=share_attn,
+            method_type=method_type, verbose=verbose, local_perturbation=local_perturbation,
+            return_intermediates=return_intermediates, use_share_attention=use_share_attention, end_scale=end_scale)
+        c.reset()
+        return (image.permute(1, 2, 0).detach().cpu().numpy() * 255).astype(np.uint8), intermediates
+
+    def FreeFine_cross_image_composition(self, img_lists, ori_mask_lists, tgt_mask_lists, coarse_input,
+                                         guidance_text_list, guidance_scale, eta, end_step=10, num_step=50,
+                                         start_step=25, share_attn=True, method_type='tca', local_text_edit=True,
+                                         local_perturbation=True, verbose=True, seed=42, draw_mask=None,
+                                         return_intermediates=False, use_auto_draw=False, end_scale=0.5,
+                                         dil_completion=False, dil_factor=15, appearance_transfer=False):
+        """reference model.py:1051-1086 (needs register_attention_control_compose).  As published the reference raises
+        TypeError here -- it forwards `use_auto_draw` to a function without that parameter; this
+        entry point accepts the argument and drops it, the inner functions are the parity targets."""
+        methods = ['tca', 'ssa', 'sdsa', 'mmsa', 'mmsa_es']
+        assert method_type in methods, f"check method type f{method_type}, which is not in {methods}"
+        seed_everything(seed)
+        ori_mask_lists = [self.mask_reduce_dim(m) for m in ori_mask_lists]
+        tgt_mask_lists = [self.mask_reduce_dim(m) for m in tgt_mask_lists]
+        inverted = self.DDIM_inversion_func_compose(img=coarse_input, compose_imgs=img_lists, prompt="", num_step=num_step,
+                                                    start_step=start_step, verbose=verbose)
+        image, intermediates = self.Details_Preserving_regeneration_compose(
+            coarse_input, inverted, guidance_text_list, ori_mask_lists, tgt_mask_lists, draw_mask, num_steps=num_step,
+            start_step=start_step, end_step=end_step, dil_factor=dil_factor, guidance_scale=guidance_scale, eta=eta,
+            share_attn=share_attn, method_type=method_type, verbose=verbose, dil_completion=dil_completion,
+            local_text_edit=local_text_edit, local_perturbation=local_perturbation,
+            return_intermediates=return_intermediates, end_scale=end_scale, appearance_transfer=appearance_transfer)
+        self.last_intermediates = intermediates
+        return image
+
+    # ------------------------------------------------------------------------------------------------------------
     # batched entry point (extension: E edits share one stream batch; the reference loops over edits one by one,
     # evaluation/FreeFine/freefine_batch_infer_2d.py:177-234)
     # ------------------------------------------------------------------------------------------------------------

@@ -152,6 +152,14 @@ int ff_ddim_step(const float* eps2, const float* x, const float* noise, const ui
                  float sqrt_at, float sqrt_ap, float c_ddim, float c_ddpm, float sigma, float* x_prev,
                  float* pred_x0, int32_t n_edits, int32_t C, int32_t h, int32_t w, void* stream);
 
+/* Composition form (forward_sampling_compose, model.py:407-431): the UNet batch of an edit is [e, r_1..r_N, c_e]
+ * (streams_per_edit = N+2), guidance uses streams 0 and N+1, and ONLY the edit stream is stepped (single-stream
+ * ctrl_step with the local-DDPM mask): x / noise / x_prev [n_edits, C, h, w].                                       */
+int ff_ddim_cfg_step_compose(const float* eps, int32_t streams_per_edit, const float* x, const float* noise,
+                             const uint8_t* cfg_mask, const uint8_t* var_mask, float guidance_scale, float sqrt_1m_at,
+                             float sqrt_at, float sqrt_ap, float c_ddim, float c_ddpm, float sigma, float* x_prev,
+                             float* pred_x0, int32_t n_edits, int32_t C, int32_t h, int32_t w, void* stream);
+
 /* ff_ddim_inv_step replaces inv_step (model.py:109-132): x_next = sqrt_an*((x - sqrt_1m_at*eps)/sqrt_at) +
  * c_next*eps over n elements; pred_x0 may be NULL.                                                               */
 int ff_ddim_inv_step(const float* eps, const float* x, float sqrt_1m_at, float sqrt_at, float sqrt_an, float c_next,

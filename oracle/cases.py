@@ -145,3 +145,21 @@ BG_CASES = {
     "bg_mmsa": dict(seed=5, res=128, num_step=6, start_step=1, end_step=6, eta=0.0, gs=7.5, method="mmsa", end_scale=0.5,
                     prompt="empty scene"),
 }
+
+
+COMPOSE_CASES = {
+    # appearance transfer (model.py:1516-1539): refs = [appearance image, original image],
+    # src masks = [app_mask, 1-ori_mask], tgt masks = [ori_mask] (+ background appended by prepare_composition_masks)
+    "appearance": dict(seed=6, res=128, num_step=8, start_step=2, end_step=6, eta=1.0, gs=7.5, method="tca", end_scale=0.5,
+                       appearance_transfer=True, dil_completion=False, prompt=["a photo of a thing"]),
+    "compose_mmsa": dict(seed=7, res=128, num_step=6, start_step=1, end_step=6, eta=0.0, gs=5.0, method="mmsa", end_scale=0.5,
+                         appearance_transfer=False, dil_completion=True, prompt=["a thing"]),
+}
+
+
+def compose_case_inputs(seed: int, res: int = 128):
+    img, ori_mask3, _, _, _ = edit_case_inputs(seed, res)
+    app_img, app_mask3, _, _, _ = edit_case_inputs(seed + 10, res)
+    ori = ori_mask3[:, :, 0]
+    return dict(coarse=img, imgs=[app_img, img], ori_masks=[app_mask3[:, :, 0].copy(), (1 - ori).astype(np.uint8)],
+                tgt_masks=[ori.copy()])

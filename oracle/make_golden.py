@@ -213,6 +213,32 @@ def gen_pipeline(ref):
         out[name + "/inverted"] = torch.stack(inv).numpy()
         out[name + "/latents"] = torch.stack([x.reshape(4, *x.shape[-2:]) for x in inter]).numpy()
         out[name + "/edit_img"] = edit_img
+    # cross-image composition / appearance transfer (register_attention_control_compose; entered at the inner functions:
+    # the public entry point raises TypeError as published)
+    for name, c in cases.COMPOSE_CASES.items():
+        parts = build_standin("tiny")
+        pipe, controller = ref_import.make_reference_pipeline(ref, parts, flavour="compose")
+        ci = cases.compose_case_inputs(c["seed"], c["res"])
+        counter = {"k": 0}
+
+        def fake_randn(shape, generator=None, device=None, dtype=None, _c=c, _n=counter):
+            t = cases.step_noise(_c["seed"], _n["k"], shape)
+            _n["k"] += 1
+            return t
+
+        ref.model.randn_tensor = fake_randn
+        torch.manual_seed(c["seed"])
+        inv = pipe.DDIM_inversion_func_compose(img=ci["coarse"], compose_imgs=ci["imgs"], prompt="", num_step=c["num_step"],
+                                               start_step=c["start_step"], verbose=True)
+        image, inter = pipe.Details_Preserving_regeneration_compose(
+            ci["coarse"], inv, list(c["prompt"]), [m.copy() for m in ci["ori_masks"]], [m.copy() for m in ci["tgt_masks"]], None,
+            num_steps=c["num_step"], start_step=c["start_step"], end_step=c["end_step"], eta=c["eta"], guidance_scale=c["gs"],
+            dil_completion=c["dil_completion"], appearance_transfer=c["appearance_transfer"], method_type=c["method"],
+            verbose=True, return_intermediates=True, end_scale=c["end_scale"])
+        out[name + "/inverted"] = torch.stack(inv).numpy()
+        out[name + "/latents"] = torch.stack([x.reshape(4, *x.shape[-2:]) for x in inter[1:]]).numpy()
+        out[name + "/edit_img"] = image
+        out[name + "/tgt_masks"] = controller.tgt_masks.numpy() if controller.tgt_masks is not None else np.zeros(1)
     np.savez_compressed(os.path.join(OUT, "pipeline.npz"), **out)
 
 

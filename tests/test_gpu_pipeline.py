@@ -191,3 +191,48 @@ def test_re_edit_2d_matches_cv2_reference(dev, golden):
         final, tmask, hole = re_edit_2d(img, ori_mask3, edit_param, img)
         assert np.array_equal(tmask, g[name + "/tgt_mask"]), name
         assert np.abs(final.astype(np.int32) - g[name + "/coarse"].astype(np.int32)).max() <= 1, name
+
+
+@pytest.mark.parametrize("name", list(cases.COMPOSE_CASES))
+def test_cross_image_composition_matches_reference(dev, golden, name, monkeypatch):
+    """Composition / appearance transfer: register_attention_control_compose + the inner functions of
+    FreeFine_cross_image_composition (the reference's public entry point raises TypeError as published, quirk Q12)."""
+    import freefine_b200.pipeline as P
+    from freefine_b200.pipeline import Attention_Modulator, FreeFinePipeline, register_attention_control_compose
+    from freefine_b200.standin import build_standin
+    g = golden["pipeline"]
+    c = cases.COMPOSE_CASES[name]
+    ci = cases.compose_case_inputs(c["seed"], c["res"])
+    parts = build_standin("tiny", device=dev)
+    controller = Attention_Modulator(start_layer=10)
+    pipe = FreeFinePipeline.from_parts(parts, controller, device=dev)
+    register_attention_control_compose(pipe, controller)
+    pipe.modify_unet_forward()
+    counter = {"k": 0}
+
+    def fake_randn(shape, generator=None, device=None, dtype=None):
+        t = cases.step_noise(c["seed"], counter["k"], shape).to(device)
+        counter["k"] += 1
+        return t
+
+    monkeypatch.setattr(P, "randn_tensor", fake_randn)
+    inv = pipe.DDIM_inversion_func_compose(img=ci["coarse"], compose_imgs=ci["imgs"], prompt="", num_step=c["num_step"],
+                                           start_step=c["start_step"], verbose=True)
+    assert _rel_l2(inv[-1].cpu(), torch.from_numpy(g[name + "/inverted"])[-1]) < 1e-2
+    image, inter = pipe.Details_Preserving_regeneration_compose(
+        ci["coarse"], inv, list(c["prompt"]), [m.copy() for m in ci["ori_masks"]], [m.copy() for m in ci["tgt_masks"]], None,
+        num_steps=c["num_step"], start_step=c["start_step"], end_step=c["end_step"], eta=c["eta"], guidance_scale=c["gs"],
+        dil_completion=c["dil_completion"], appearance_transfer=c["appearance_transfer"], method_type=c["method"],
+        verbose=True, return_intermediates=True, end_scale=c["end_scale"])
+    assert np.array_equal(controller.tgt_masks.cpu().numpy(), g[name + "/tgt_masks"])          # mask prep: bit-exact
+    ref = torch.from_numpy(g[name + "/latents"])
+    assert len(inter) - 1 == ref.shape[0]
+    assert _rel_l2(inter[-1].reshape(ref[-1].shape).cpu(), ref[-1]) < 1e-2
+    assert np.abs(image.astype(np.int32) - g[name + "/edit_img"].astype(np.int32)).max() <= 8
+    # the public entry point accepts (and drops) use_auto_draw
+    out = pipe.FreeFine_cross_image_composition(ci["imgs"], ci["ori_masks"], ci["tgt_masks"], ci["coarse"], list(c["prompt"]),
+                                                c["gs"], c["eta"], end_step=c["end_step"], num_step=c["num_step"],
+                                                start_step=c["start_step"], method_type=c["method"], use_auto_draw=True,
+                                                end_scale=c["end_scale"], dil_completion=c["dil_completion"],
+                                                appearance_transfer=c["appearance_transfer"])
+    assert out.shape == image.shape and out.dtype == np.uint8

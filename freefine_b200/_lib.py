@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FREEFINE_B200_LIB", os.path.join(_HERE, "lib", "libfreefine_b200.so"))
 
 FF_MAX_PASS = 4
-FF_DT_F32, FF_DT_BF16 = 0, 1
+FF_DT_F32, FF_DT_BF16, FF_DT_F16 = 0, 1, 2
 FF_PASS_KEY_INVERT, FF_PASS_ROW_XOR, FF_PASS_ROW_WEIGHT, FF_PASS_KEY2_INVERT = 1, 2, 4, 8
 FF_PASS_KEY_PREFIX, FF_PASS_KEY2_PREFIX = 16, 32
 
@@ -31,7 +31,7 @@ class FFAttnArgs(C.Structure):
                 ("bitmasks", C.c_void_p), ("mask_popcount", C.c_void_p),
                 ("n_streams", C.c_int32), ("n_kv_streams", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32),
                 ("s_q", C.c_int32), ("s_kv", C.c_int32), ("n_masks", C.c_int32), ("mask_words", C.c_int32),
-                ("out_dtype", C.c_int32), ("scale", C.c_float)]
+                ("out_dtype", C.c_int32), ("scale", C.c_float), ("v_dtype", C.c_int32), ("v_head_stride", C.c_int32)]
 
 
 PLAN_BYTES = C.sizeof(FFAttnHeadPlan)      # 144
@@ -42,6 +42,9 @@ SIGNATURES = {
     "ff_version": (C.c_int, []),
     "ff_last_error": (C.c_char_p, []),
     "ff_attn_masked_kv": (C.c_int, [C.POINTER(FFAttnArgs), C.c_void_p]),
+    "ff_attn_v_head_stride": (C.c_int, [C.c_int32]),
+    "ff_kv_gather_cast": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                    C.c_int32, C.c_void_p]),
     "ff_mask_downsample_pack": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                           C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "ff_warp_affine_blend": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -31,22 +31,38 @@ constexpr int BOX_COLS = 64;            // channels per TMA box (128 bytes of bf
 constexpr int TILE_BYTES = BM * 128;    // Q box: 128 rows x 128 B = 16 KiB
 constexpr int KV_BYTES = BN * 128;      // K / V box: 64 rows x 128 B = 8 KiB
 constexpr int NUM_THREADS = 192;
-#ifdef FF_DBG_NORESCALE
-constexpr float RESCALE_THRESHOLD = 1e30f;
-#else
-constexpr float RESCALE_THRESHOLD = 24.f;  // log2 units: p <= 2^24 keeps fp32 / bf16 relative precision, rescales are rare
+// P operand of the PV contraction (template parameter HILO), chosen by the dtype of V -- tcgen05.mma kind::f16 wants
+// A and B in the SAME 16-bit format (an f16 A with a bf16 B raises an illegal-instruction fault on B200):
+//   V fp16  (HILO=false)  ONE fp16 P operand: 11 significant bits, half the PV tensor work and a third of the packing
+//                         ALU work of
+//   V bf16  (HILO=true)   a hi + lo pair of bf16 P operands (16 significant bits, two TS-MMAs per 16 keys).
+// Lazy-rescale threshold in log2 units: p <= 2^24 keeps fp32 / bf16 relative precision; p <= 2^8 stays far inside
+// the fp16 range.  Rescales are rare either way.
+template <bool HILO> constexpr float rescale_threshold() { return HILO ? 24.f : 8.f; }
+// exp2 of pair i (mod 8) of every 16-score chunk goes to the FMA pipe (degree-3 polynomial) instead of the MUFU unit
+// when bit i of this pattern is set: the softmax of the d=40 layers is bound by the 16 ex2/clk/SM of the MUFU unit.
+#ifndef FF_POLY_PATTERN
+#define FF_POLY_PATTERN 0x00
 #endif
 
-template <int DPAD> struct Cfg {
+// DPAD: head_dim padded to the K-step of Q K^T (a multiple of 16).  DPV: columns of the V tile / of O.  With an fp16 V
+// (HILO=false) the staged V carries a column of ONES at channel head_dim (ff_kv_gather_cast), so the tensor core
+// produces the softmax denominator l = sum_k P[q,k] from exactly the rounded P it multiplies with V -- no row-sum
+// arithmetic in the softmax warps, and numerator and denominator see the same rounding.
+template <int DPAD, bool HILO> struct Cfg {
+  static constexpr int DPV = HILO ? DPAD : (DPAD == 16 ? 16 : (DPAD == 48 ? 48 : DPAD + 16));
   static constexpr int NKT = (DPAD + BOX_COLS - 1) / BOX_COLS;          // 64-channel boxes per operand tile
+  static_assert((DPV + BOX_COLS - 1) / BOX_COLS == NKT, "V tile must span as many boxes as the K tile");
 #ifdef FF_DBG_NSTAGE
   static constexpr int NSTAGE = FF_DBG_NSTAGE;
 #else
   static constexpr int NSTAGE = DPAD <= 48 ? 4 : (DPAD <= 80 ? 3 : 2);  // K/V ring depth
 #endif
-  static constexpr bool ACC_TMEM = DPAD > 80;                           // cross-pass accumulator location
-  static constexpr int TMEM_S = 0, TMEM_O = 2 * BN, TMEM_ACC = 2 * BN + DPAD;   // S buffers at columns 0 and BN
-  static constexpr int TMEM_USED = 2 * BN + DPAD + (ACC_TMEM ? DPAD : 0);
+  // cross-pass accumulator location: TMEM where registers are short (DPAD=48 runs two CTAs per SM on 168 registers
+  // and keeps 64 scores live; 128 + 48 + 48 columns still fit the 256-column allocation), registers otherwise
+  static constexpr bool ACC_TMEM = DPAD > 80 || (DPAD > 16 && DPAD <= 48);
+  static constexpr int TMEM_S = 0, TMEM_O = 2 * BN, TMEM_ACC = 2 * BN + DPV;   // S buffers at columns 0 and BN
+  static constexpr int TMEM_USED = 2 * BN + DPV + (ACC_TMEM ? DPAD : 0);
   static constexpr int TMEM_COLS = TMEM_USED <= 256 ? 256 : 512;
   static constexpr int SMEM_Q = NKT * TILE_BYTES;
   static constexpr int SMEM_STAGE = 2 * NKT * KV_BYTES;                 // K tiles then V tiles
@@ -162,12 +178,25 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
       : "r"(taddr)
       : "memory");
 }
+// one column (the softmax denominator produced by the ones column of V); waits for it
+__device__ __forceinline__ float tmem_ld1_wait(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n\ttcgen05.wait::ld.sync.aligned;"
+               : "=r"(r) : "r"(taddr) : "memory");
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
       "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
       : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -215,8 +244,9 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo
          (1ull << 46) | (2ull << 61);
 }
 // Instruction descriptor kind::f16: D f32, A/B bf16, A K-major, B K-major (b_mn=0) or MN-major (b_mn=1), M=128.
-__host__ __device__ constexpr uint32_t make_idesc(int n, int b_mn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) |
+// f16: A and B are fp16 (format 0) instead of bf16 (format 1) -- the two formats cannot be mixed in one MMA.
+__host__ __device__ constexpr uint32_t make_idesc(int n, int b_mn, bool f16 = false) {
+  return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) |
          ((uint32_t)(BM >> 4) << 24);
 }
 
@@ -374,11 +404,59 @@ __device__ __forceinline__ void softmax_chunk(const float (&s)[16], uint32_t (&h
   }
 }
 
-template <int DPAD>
-__global__ void __launch_bounds__(NUM_THREADS, Cfg<DPAD>::MIN_CTAS)
+// 2^x for two values on the FMA pipe: x = n + f, n = round(x), f in [-0.5, 0.5]; 2^f by a degree-3 minimax polynomial
+// (max relative error 7.6e-5, below the half-ulp 2.4e-4 of the fp16 P operand it feeds), 2^n by an integer add into the
+// exponent field.  x is clamped at -125 (result 2^-125: rounds to 0 in fp16, adds nothing measurable to the row sum).
+__device__ __forceinline__ float2 poly_exp2_x2(float2 x) {
+  const float MAGIC = 12582912.f;   // 1.5 * 2^23: the low mantissa bits of x + MAGIC hold round(x)
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 t = __fadd2_rn(x, make_float2(MAGIC, MAGIC));
+  const float2 n = __fadd2_rn(t, make_float2(-MAGIC, -MAGIC));
+  const float2 f = __fadd2_rn(x, make_float2(-n.x, -n.y));
+  float2 r = __ffma2_rn(make_float2(0.055205512791872025f, 0.055205512791872025f), f,
+                        make_float2(0.24261389672756195f, 0.24261389672756195f));
+  r = __ffma2_rn(r, f, make_float2(0.6932547688484192f, 0.6932547688484192f));
+  r = __ffma2_rn(r, f, make_float2(0.9999276995658875f, 0.9999276995658875f));
+  r.x = __int_as_float(__float_as_int(r.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(r.y) + (__float_as_int(t.y) << 23));
+  return r;
+}
+
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// 16 scores -> p = exp2(s*sc + nb), P as 8 packed fp16 pairs (key 2i in the low half; the row sum comes out of the
+// tensor core: ones column of V).  MASKED: bit i of
+// `bits` gates key i (MUFU only: ex2(-inf) is an exact 0).
+template <bool MASKED>
+__device__ __forceinline__ void softmax_chunk_f16(const float* s, uint32_t* pk, float sc, float nb, uint32_t bits) {
+  const float2 sc2 = make_float2(sc, sc), nb2 = make_float2(nb, nb);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float2 x = __ffma2_rn(make_float2(s[2 * i], s[2 * i + 1]), sc2, nb2);
+    float2 e;
+    if (MASKED) {
+      x.x = (bits >> (2 * i)) & 1u ? x.x : -INFINITY;
+      x.y = (bits >> (2 * i + 1)) & 1u ? x.y : -INFINITY;
+      e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+    } else if ((FF_POLY_PATTERN >> i) & 1) {
+      e = poly_exp2_x2(x);
+    } else {
+      e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+    }
+    pk[i] = pack_f16x2(e.x, e.y);
+  }
+}
+
+template <int DPAD, bool P_HILO>
+__global__ void __launch_bounds__(NUM_THREADS, Cfg<DPAD, P_HILO>::MIN_CTAS)
 attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                       const __grid_constant__ CUtensorMap tm_v, const KParams p) {
-  using C = Cfg<DPAD>;
+  using C = Cfg<DPAD, P_HILO>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B atoms are 1024-B aligned
   const uint32_t sQ = smem_base;
@@ -480,7 +558,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     // ===================================== MMA issuer =======================================
     if (lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc(BN, 0);
-      constexpr uint32_t idesc_pv = make_idesc(DPAD, 1);
+      constexpr uint32_t idesc_pv = make_idesc(C::DPV, 1, !P_HILO);
       FF_TRACE(0, 20);
       mbar_wait(bar_q, 0);
       int it = 0;
@@ -500,10 +578,16 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         // K-step, 64-channel groups KV_BYTES apart (LBO)
 #pragma unroll
         for (int ks = 0; ks < BN / 16; ++ks) {
-          const uint32_t a_hi = tmem + C::TMEM_S + BN * (t & 1) + 16 * ks;
           const uint64_t vdesc = smem_desc_sw128(sV + ks * 2048, KV_BYTES);
-          mma_ts(tmem + C::TMEM_O, a_hi, vdesc, idesc_pv, (!first_of_pass || ks > 0) ? 1u : 0u);
-          mma_ts(tmem + C::TMEM_O, a_hi + 8, vdesc, idesc_pv, 1u);
+          if constexpr (P_HILO) {
+            const uint32_t a_hi = tmem + C::TMEM_S + BN * (t & 1) + 16 * ks;
+            mma_ts(tmem + C::TMEM_O, a_hi, vdesc, idesc_pv, (!first_of_pass || ks > 0) ? 1u : 0u);
+            mma_ts(tmem + C::TMEM_O, a_hi + 8, vdesc, idesc_pv, 1u);
+          } else {
+            // single fp16 P: the 16 keys of K-step ks are the 8 packed columns [8ks, 8ks+8) of the S buffer
+            mma_ts(tmem + C::TMEM_O, tmem + C::TMEM_S + BN * (t & 1) + 8 * ks, vdesc, idesc_pv,
+                   (!first_of_pass || ks > 0) ? 1u : 0u);
+          }
         }
         tc_commit(bar_kv_empty + 8 * stage);
       };
@@ -604,8 +688,8 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           // ---- sweep 1: row max over ALL 64 columns (an upper bound of the max over the allowed keys is all the
           // softmax needs: bf16/fp32 keep their relative precision whatever the reference point; padded columns are 0)
           float mt;
+          float sa[32], sb[32];     // single-operand P: the 64 scores stay in registers for the exp sweep
           {
-            float sa[32], sb[32];
             float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
             tmem_ld32(tS, sa);
             tmem_wait_ld32(sa);
@@ -633,7 +717,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           bool grow = false;
           if (first) {
             m_used = mts;
-          } else if (mts > m_used + RESCALE_THRESHOLD) {
+          } else if (mts > m_used + rescale_threshold<P_HILO>()) {
             alpha = fast_exp2(m_used - mts);
             m_used = mts;
             la.x *= alpha; la.y *= alpha; lb.x *= alpha; lb.y *= alpha;
@@ -645,7 +729,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             FF_TRACE(it, 33);
             tc_fence_after();
 #pragma unroll
-            for (int c = 0; c < DPAD / 16; ++c) {
+            for (int c = 0; c < C::DPV / 16; ++c) {      // (fp16 V: includes the denominator column)
               float o[16];
               uint32_t ob[16];
               tmem_ld16(tlane + C::TMEM_O + 16 * c, o);
@@ -660,6 +744,41 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           // result stays within the fp32-reference tolerance; the second PV MMA rides on tensor-pipe slack.  The 16
           // keys of K-step ks (S columns [16ks,16ks+16)) are overwritten in place by hi -> [16ks,16ks+8) and
           // lo -> [16ks+8,16ks+16): only columns this thread has already consumed.
+          if constexpr (!P_HILO) {
+            // ---- exp sweep from registers: P = fp16(2^(s*scale*log2e - m)) over columns [0,32) of this S buffer
+            // (16 keys of K-step ks -> packed columns [8ks, 8ks+8)); every S column is already in registers.
+            uint32_t pk[8];
+            if (cls != TILE_MIX) {
+              // one predicate per row: bias -m (allowed) or -inf (row reads nothing from this tile -> p = 0)
+              const float nb = row_ok_cls ? -m_used : -INFINITY;
+#pragma unroll
+              for (int c = 0; c < BN / 16; ++c) {
+                softmax_chunk_f16<false>(c < 2 ? sa + 16 * c : sb + 16 * (c - 2), pk, sc, nb, 0u);
+                tmem_st8(tS + 8 * c, pk);
+              }
+            } else {
+              // boundary / ragged tile: evaluate allowed(q,k) per element on 16-bit slices of the mask words
+              const float nb = -m_used;
+#pragma unroll
+              for (int c = 0; c < BN / 16; ++c) {
+                const int kbase = j * BN + 16 * c;
+                const int rem = p.s_kv - kbase;
+                const uint32_t valid = rem >= 16 ? 0xffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+                uint32_t kb = 0xffffu;
+                if (sg.kmask >= 0 && !uniform && rem > 0) {
+                  if (sg.prefix) {
+                    const int t = sg.T - kbase;
+                    kb = t >= 16 ? 0xffffu : (t <= 0 ? 0u : ((1u << t) - 1u));
+                  } else {
+                    kb = (__ldg(p.bitmasks + (size_t)sg.kmask * p.mask_words + (kbase >> 5)) >> (kbase & 31)) & 0xffffu;
+                  }
+                  if (flip) kb = ~kb;
+                }
+                softmax_chunk_f16<true>(c < 2 ? sa + 16 * c : sb + 16 * (c - 2), pk, sc, nb, kb & valid);
+                tmem_st8(tS + 8 * c, pk);
+              }
+            }
+          } else
           if (cls != TILE_MIX) {
             // one predicate per row: bias -m (allowed) or -inf (row reads nothing from this tile -> p = 0)
             const float nb = row_ok_cls ? -m_used : -INFINITY;
@@ -719,7 +838,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       mbar_wait(bar_s + 8 * ((it + 1) & 1), ((it + 1) >> 1) & 1);   // s_full(L+2) => PV(L) of this pass's last tile L = it-1
       FF_TRACE(it, 36);
       tc_fence_after();
-      const float l = (la.x + la.y) + (lb.x + lb.y);
+      const float l = P_HILO ? (la.x + la.y) + (lb.x + lb.y) : tmem_ld1_wait(tlane + C::TMEM_O + p.head_dim);
       float coef = ps.weight;
       if (ps.flags & FF_PASS_ROW_WEIGHT) coef = rb ? coef : 0.f;
       coef = l > 0.f ? coef / l : 0.f;
@@ -822,7 +941,9 @@ EncodeTiledFn get_encode_fn() {
 
 // [streams, S, heads, d] bf16 view of a dense [streams, S, heads*d] tensor; box = 64 channels x 1 head x 128 rows.
 // Channels >= d of a box are out of bounds in dimension 0 and therefore zero-filled.
-int make_map(CUtensorMap* map, const void* base, int streams, int S, int heads, int d, int box_rows) {
+// For the staged fp16 V, d = v_head_stride (real channels + ones column + zero padding, all in bounds).
+int make_map(CUtensorMap* map, const void* base, int streams, int S, int heads, int d, int box_rows,
+             bool f16 = false) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return ff::fail(FF_E_CUDA, "cuTensorMapEncodeTiled entry point not found");
   const cuuint64_t C = (cuuint64_t)heads * d;
@@ -830,7 +951,7 @@ int make_map(CUtensorMap* map, const void* base, int streams, int S, int heads, 
   cuuint64_t strides[3] = {(cuuint64_t)d * 2, C * 2, (cuuint64_t)S * C * 2};
   cuuint32_t box[4] = {BOX_COLS, 1, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -839,20 +960,20 @@ int make_map(CUtensorMap* map, const void* base, int streams, int S, int heads, 
   return FF_OK;
 }
 
-template <int DPAD>
+template <int DPAD, bool HILO>
 int launch(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const KParams& kp, int n_streams,
            cudaStream_t st) {
-  using C = Cfg<DPAD>;
+  using C = Cfg<DPAD, HILO>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_masked_kv_kernel<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attn_masked_kv_kernel<DPAD, HILO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) return ff::fail(FF_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", C::SMEM_BYTES,
                                           cudaGetErrorString(e));
     configured = true;
   }
   dim3 grid((kp.s_q + BM - 1) / BM, kp.heads, n_streams);
-  attn_masked_kv_kernel<DPAD><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(mq, mk, mv, kp);
+  attn_masked_kv_kernel<DPAD, HILO><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(mq, mk, mv, kp);
   return ff::check_launch("ff_attn_masked_kv");
 }
 
@@ -869,6 +990,15 @@ extern "C" int ff_debug_set_trace(void* device_visible_ptr) {
   return FF_OK;
 }
 
+// Channels per head of the staged fp16 V: head_dim real channels, a ones column at channel head_dim, zeros above;
+// equals Cfg<DPAD,false>::DPV of the instantiation ff_attn_masked_kv picks for this head_dim.
+extern "C" int ff_attn_v_head_stride(int32_t head_dim) {
+  if (head_dim <= 8) return Cfg<16, false>::DPV;
+  if (head_dim <= 40) return Cfg<48, false>::DPV;
+  if (head_dim <= 80) return Cfg<80, false>::DPV;
+  return Cfg<160, false>::DPV;
+}
+
 extern "C" int ff_attn_masked_kv(const FFAttnArgs* a, void* stream) {
   FF_REQUIRE(a != nullptr, "ff_attn_masked_kv: null args");
   FF_REQUIRE(a->q && a->k && a->v && a->out && a->plan, "ff_attn_masked_kv: null pointer");
@@ -881,6 +1011,7 @@ extern "C" int ff_attn_masked_kv(const FFAttnArgs* a, void* stream) {
   FF_REQUIRE(ff::aligned16(a->q) && ff::aligned16(a->k) && ff::aligned16(a->v) && ff::aligned16(a->out),
              "ff_attn_masked_kv: q/k/v/out must be 16-byte aligned");
   FF_REQUIRE(a->out_dtype == FF_DT_BF16 || a->out_dtype == FF_DT_F32, "ff_attn_masked_kv: bad out_dtype");
+  FF_REQUIRE(a->v_dtype == FF_DT_BF16 || a->v_dtype == FF_DT_F16, "ff_attn_masked_kv: v_dtype must be bf16 or f16");
   FF_REQUIRE(a->scale > 0.f, "ff_attn_masked_kv: scale must be positive");
   if (a->n_masks > 0) {
     FF_REQUIRE(a->bitmasks && a->mask_popcount, "ff_attn_masked_kv: n_masks>0 but no bitmasks / popcounts");
@@ -896,7 +1027,14 @@ extern "C" int ff_attn_masked_kv(const FFAttnArgs* a, void* stream) {
   int rc;
   if ((rc = make_map(&mq, a->q, a->n_streams, a->s_q, a->heads, a->head_dim, BM)) != FF_OK) return rc;
   if ((rc = make_map(&mk, a->k, a->n_kv_streams, a->s_kv, a->heads, a->head_dim, BN)) != FF_OK) return rc;
-  if ((rc = make_map(&mv, a->v, a->n_kv_streams, a->s_kv, a->heads, a->head_dim, BN)) != FF_OK) return rc;
+  const bool v_f16 = a->v_dtype == FF_DT_F16;
+  if (v_f16)
+    FF_REQUIRE(a->v_head_stride == ff_attn_v_head_stride(a->head_dim),
+               "ff_attn_masked_kv: fp16 V must be staged by ff_kv_gather_cast (v_head_stride=%d, expected %d)",
+               a->v_head_stride, ff_attn_v_head_stride(a->head_dim));
+  if ((rc = make_map(&mv, a->v, a->n_kv_streams, a->s_kv, a->heads, v_f16 ? a->v_head_stride : a->head_dim, BN,
+                     v_f16)) != FF_OK)
+    return rc;
 
   KParams kp;
   kp.plan = a->plan;
@@ -913,8 +1051,14 @@ extern "C" int ff_attn_masked_kv(const FFAttnArgs* a, void* stream) {
   kp.scale_log2 = a->scale * 1.4426950408889634f;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int d = a->head_dim;
-  if (d <= 16) return launch<16>(mq, mk, mv, kp, a->n_streams, st);
-  if (d <= 48) return launch<48>(mq, mk, mv, kp, a->n_streams, st);
-  if (d <= 80) return launch<80>(mq, mk, mv, kp, a->n_streams, st);
-  return launch<160>(mq, mk, mv, kp, a->n_streams, st);
+  if (v_f16) {   // thresholds leave room for the ones column at channel d inside DPV (see ff_attn_v_head_stride)
+    if (d <= 8) return launch<16, false>(mq, mk, mv, kp, a->n_streams, st);
+    if (d <= 40) return launch<48, false>(mq, mk, mv, kp, a->n_streams, st);
+    if (d <= 80) return launch<80, false>(mq, mk, mv, kp, a->n_streams, st);
+    return launch<160, false>(mq, mk, mv, kp, a->n_streams, st);
+  }
+  if (d <= 16) return launch<16, true>(mq, mk, mv, kp, a->n_streams, st);
+  if (d <= 48) return launch<48, true>(mq, mk, mv, kp, a->n_streams, st);
+  if (d <= 80) return launch<80, true>(mq, mk, mv, kp, a->n_streams, st);
+  return launch<160, true>(mq, mk, mv, kp, a->n_streams, st);
 }

@@ -210,16 +210,66 @@ def mask_downsample_pack(masks, h, w, bits=None, popcount=None):
 # ---------------------------------------------------------------------------------------------------------------
 # (a) attention
 # ---------------------------------------------------------------------------------------------------------------
+class StagedV:
+    """fp16 staging of V for ff_attn_masked_kv (ff_kv_gather_cast): data [Bk, Skv, heads, v_head_stride] fp16 with a ones
+    column at channel head_dim."""
+    __slots__ = ("data", "heads", "head_dim")
+
+    def __init__(self, data, heads, head_dim):
+        self.data, self.heads, self.head_dim = data, heads, head_dim
+
+    def values(self):
+        """[Bk, Skv, heads*head_dim] fp16 view-copy of the real channels (tests)."""
+        return self.data[..., : self.head_dim].reshape(self.data.shape[0], self.data.shape[1], -1)
+
+
+def kv_gather_cast(k, v, heads, row_index=None, gather_k=True):
+    """K/V staging in one pass: rows gathered by `row_index` (int64 over the flattened [Bk*Skv] rows, None = identity),
+    V converted bf16 -> fp16 (saturating) into the padded per-head layout of the single-operand P.V path.  Returns
+    (k_sorted bf16, StagedV); K is returned untouched when there is no gather."""
+    _chk(k, torch.bfloat16, "k", 3)
+    _chk(v, torch.bfloat16, "v", 3)
+    if v.shape != k.shape or k.shape[2] % heads:
+        raise ValueError("k and v must have the same shape [Bk,Skv,heads*d]")
+    Bk, Sk, Ck = k.shape
+    d = Ck // heads
+    if row_index is not None:
+        _chk(row_index, torch.int64, "row_index", 1)
+        if row_index.numel() != Bk * Sk:
+            raise ValueError("row_index must hold one source row per K/V row")
+    lib = _lib.load()
+    vhs = lib.ff_attn_v_head_stride(d)
+    do_k = gather_k and row_index is not None
+    k_out = torch.empty_like(k) if do_k else None
+    v_out = torch.empty((Bk, Sk, heads, vhs), dtype=torch.float16, device=v.device)
+    rc = lib.ff_kv_gather_cast(_ptr(k) if do_k else None, _ptr(v), _ptr(row_index), _ptr(k_out), _ptr(v_out),
+                               Bk * Sk, heads, d, _stream())
+    _lib.check(rc, "ff_kv_gather_cast")
+    _count("ff_kv_gather_cast")
+    return (k_out if do_k else k), StagedV(v_out, heads, d)
+
+
 def attn_masked_kv(q, k, v, plan, heads, scale, bitmasks=None, popcount=None, out_dtype=None, out=None):
-    """q [B,Sq,C], k/v [Bk,Skv,C] bf16; plan: uint8 CUDA tensor holding FFAttnHeadPlan[B*heads] (plans.to_device);
+    """q [B,Sq,C], k [Bk,Skv,C] bf16, v a StagedV (fast path: one fp16 P operand, see kv_gather_cast) or bf16 [Bk,Skv,C]
+    (hi+lo bf16 P pair); plan: uint8 CUDA tensor holding FFAttnHeadPlan[B*heads] (plans.to_device);
     bitmasks int32 [n_masks, words], popcount int32 [n_masks].  Returns [B,Sq,C] in out_dtype (default bf16)."""
     _chk(q, torch.bfloat16, "q", 3)
     _chk(k, torch.bfloat16, "k", 3)
-    _chk(v, torch.bfloat16, "v", 3)
     B, Sq, Cc = q.shape
     Bk, Skv, Ck = k.shape
-    if v.shape != k.shape or Ck != Cc or Cc % heads:
-        raise ValueError(f"bad shapes q{tuple(q.shape)} k{tuple(k.shape)} v{tuple(v.shape)} heads={heads}")
+    staged = isinstance(v, StagedV)
+    if staged:
+        vt = v.data
+        _chk(vt, torch.float16, "v", 4)
+        if vt.shape[:3] != (Bk, Skv, heads) or v.head_dim * heads != Ck:
+            raise ValueError(f"staged V {tuple(vt.shape)} does not match k{tuple(k.shape)} heads={heads}")
+    else:
+        vt = v
+        _chk(v, torch.bfloat16, "v", 3)
+        if v.shape != k.shape:
+            raise ValueError(f"bad shapes k{tuple(k.shape)} v{tuple(v.shape)}")
+    if Ck != Cc or Cc % heads:
+        raise ValueError(f"bad shapes q{tuple(q.shape)} k{tuple(k.shape)} heads={heads}")
     _chk(plan, torch.uint8, "plan")
     if plan.numel() != B * heads * _lib.PLAN_BYTES:
         raise ValueError(f"plan holds {plan.numel()} bytes, expected {B * heads * _lib.PLAN_BYTES}")
@@ -229,7 +279,7 @@ def attn_masked_kv(q, k, v, plan, heads, scale, bitmasks=None, popcount=None, ou
     else:
         _chk(out, out_dtype, "out", 3)
     a = _lib.FFAttnArgs()
-    a.q, a.k, a.v, a.out, a.plan = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), plan.data_ptr()
+    a.q, a.k, a.v, a.out, a.plan = q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), plan.data_ptr()
     if bitmasks is not None:
         _chk(bitmasks, torch.int32, "bitmasks", 2)
         _chk(popcount, torch.int32, "popcount", 1)
@@ -241,6 +291,8 @@ def attn_masked_kv(q, k, v, plan, heads, scale, bitmasks=None, popcount=None, ou
     a.s_q, a.s_kv = Sq, Skv
     a.out_dtype = _DT[out_dtype]
     a.scale = float(scale)
+    a.v_dtype = _lib.FF_DT_F16 if staged else FF_DT_BF16
+    a.v_head_stride = vt.shape[3] if staged else 0
     prof = PROFILE
     if prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

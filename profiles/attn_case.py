@@ -23,10 +23,14 @@ for S, d in ((4096, 40), (1024, 80)):
     prefix = os.environ.get("FF_PREFIX", "1") == "1"       # the controller's default: keys sorted "source first"
     plan_np = plans.tca_plan(E, heads, "tca", 0.5, lambda e: 2 * e, lambda e: 2 * e + 1, prefix=prefix)
     plan = ops.to_device_bytes(plan_np, dev)
+    idx = None
     if prefix:
         shifts = torch.arange(32, device=dev, dtype=torch.int32)
         key_bits = ((bits[:, :, None] >> shifts) & 1).reshape(bits.shape[0], -1)[:, :S]
         idx = plans.kv_sort_index(key_bits, [2 * (s // 4) if s % 2 else -1 for s in range(4 * E)])
+    if os.environ.get("FF_P", "f16") == "f16":           # V staged as fp16: single-operand P.V
+        k, v = ops.kv_gather_cast(k, v, heads, idx)
+    elif idx is not None:
         k = k.view(-1, heads * d).index_select(0, idx).view(4 * E, S, heads * d)
         v = v.view(-1, heads * d).index_select(0, idx).view(4 * E, S, heads * d)
     flops = plans.algorithmic_flops(plan_np, S, S, d, pop.cpu().numpy())
@@ -39,5 +43,5 @@ for S, d in ((4096, 40), (1024, 80)):
         ev[i + 1].record()
     torch.cuda.synchronize()
     ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(reps)]
-    print(f"S={S} d={d} streams={4*E} prefix={prefix}: {min(ms):.3f} ms best / {sum(ms)/len(ms):.3f} ms avg, algorithmic {flops/1e9:.1f} GFLOP -> "
+    print(f"S={S} d={d} streams={4*E} prefix={prefix} P={os.environ.get('FF_P', 'f16')}: {min(ms):.3f} ms best / {sum(ms)/len(ms):.3f} ms avg, algorithmic {flops/1e9:.1f} GFLOP -> "
           f"{flops / (min(ms) * 1e-3) / 1e12:.1f} TFLOP/s (dense-equivalent {7*4*S*S*d*heads*E/1e9:.1f} GFLOP)")

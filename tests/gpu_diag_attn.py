@@ -8,6 +8,13 @@ from oracle import ff_oracle as O
 
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
+P_OP = os.environ.get("FF_P", "f16")
+print("P operand:", P_OP)
+
+
+def _v(v, heads):
+    v = v.to(dev).bfloat16().contiguous()
+    return ops.kv_gather_cast(v, v, heads, None)[1] if P_OP == "f16" else v
 
 
 def run(name, B, S, Skv, heads, d, q=None, k=None, v=None):
@@ -18,7 +25,7 @@ def run(name, B, S, Skv, heads, d, q=None, k=None, v=None):
     v = (torch.randn(B, Skv, C, generator=g)).bfloat16().float() if v is None else v
     pl = ops.to_device_bytes(plans.plain_plan(B, heads), dev)
     try:
-        out = ops.attn_masked_kv(q.to(dev).bfloat16(), k.to(dev).bfloat16(), v.to(dev).bfloat16(), pl, heads, d ** -0.5,
+        out = ops.attn_masked_kv(q.to(dev).bfloat16(), k.to(dev).bfloat16(), _v(v, heads), pl, heads, d ** -0.5,
                                  out_dtype=torch.float32)
         torch.cuda.synchronize()
     except Exception as e:
@@ -73,7 +80,7 @@ def run_tca(name, heads, d, S, res, method="tca", kind="edit", cg=0.6):
     pc = torch.tensor([int((src != 0).sum()), int((tgt != 0).sum())], dtype=torch.int32, device=dev)
     plan = plans.tca_plan(1, heads, method, cg, lambda e: 0, lambda e: 1, kind=kind)
     try:
-        out = ops.attn_masked_kv(q.to(dev).bfloat16(), k.to(dev).bfloat16(), v.to(dev).bfloat16(),
+        out = ops.attn_masked_kv(q.to(dev).bfloat16(), k.to(dev).bfloat16(), _v(v, heads),
                                  ops.to_device_bytes(plan, dev), heads, d ** -0.5, bm, pc, out_dtype=torch.float32)
         torch.cuda.synchronize()
     except Exception as e:

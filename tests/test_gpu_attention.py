@@ -23,12 +23,29 @@ def dev():
     return torch.device("cuda:0")
 
 
+P_OPERAND = "f16"
+
+
+@pytest.fixture(autouse=True, params=["f16", "bf16x2"])
+def p_operand(request):
+    """Every parity test runs on both P.V operand paths: V staged as fp16 by ff_kv_gather_cast (one fp16 P operand) and
+    V bf16 (hi+lo bf16 P pair)."""
+    global P_OPERAND
+    P_OPERAND = request.param
+    return request.param
+
+
 def _run(dev, q, k, v, plan, heads, scale, flat_masks=None, out_dtype=torch.float32, sort_streams=None):
     """sort_streams: per K/V stream the mask row that orders its keys (prefix mode) or -1."""
     from freefine_b200 import ops
     S = max(q.shape[1], k.shape[1])
+    idx = None
     if sort_streams is not None:
         idx = plans.kv_sort_index(torch.from_numpy(np.stack([np.asarray(m) != 0 for m in flat_masks])), sort_streams)
+    if P_OPERAND == "f16":
+        k, v = ops.kv_gather_cast(k.to(dev).bfloat16().contiguous(), v.to(dev).bfloat16().contiguous(), heads,
+                                  None if idx is None else idx.to(dev))
+    elif idx is not None:
         k = k.reshape(-1, k.shape[-1])[idx].reshape(k.shape)
         v = v.reshape(-1, v.shape[-1])[idx].reshape(v.shape)
     bm = pc = None
@@ -41,7 +58,8 @@ def _run(dev, q, k, v, plan, heads, scale, flat_masks=None, out_dtype=torch.floa
         bm = torch.from_numpy(arr.view(np.int32)).to(dev)
         pc = torch.tensor([int((np.asarray(m) != 0).sum()) for m in flat_masks], dtype=torch.int32, device=dev)
     pl = ops.to_device_bytes(plan, dev)
-    out = ops.attn_masked_kv(q.to(dev).bfloat16(), k.to(dev).bfloat16(), v.to(dev).bfloat16(), pl, heads, scale, bm, pc,
+    vv = v if isinstance(v, ops.StagedV) else v.to(dev).bfloat16()
+    out = ops.attn_masked_kv(q.to(dev).bfloat16(), k.to(dev).bfloat16(), vv, pl, heads, scale, bm, pc,
                              out_dtype=out_dtype)
     torch.cuda.synchronize()
     return out.float().cpu()

@@ -160,3 +160,26 @@ def test_cross_region_blend(dev, golden):
     bits = torch.from_numpy(O.pack_bits(reg.numpy()).view(np.int32))[None].to(dev)
     out = ops.cross_region_blend(hs.clone().to(dev), bits, torch.zeros(1, dtype=torch.int32, device=dev))
     assert float((out.cpu() - T("cross/out")).abs().max()) < 2e-5
+
+
+def test_kv_gather_cast_bit_exact(dev):
+    """ff_kv_gather_cast == index_select + bf16->fp16 (exact inside the fp16 range, saturating outside) into the padded
+    per-head layout with the ones column."""
+    from freefine_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    for heads, d in ((8, 40), (4, 80), (2, 160), (5, 8)):
+        C = heads * d
+        k = torch.randn(3, 200, C, generator=g).bfloat16().to(dev)
+        v = (torch.randn(3, 200, C, generator=g) * 4).bfloat16()
+        v[0, 0, :4] = torch.tensor([1e6, -1e6, 65504.0, 3e-6]).bfloat16()
+        v = v.to(dev)
+        idx = torch.randperm(600, generator=g).to(dev)
+        ks, vs = ops.kv_gather_cast(k, v, heads, idx)
+        assert vs.data.dtype == torch.float16 and ks.dtype == torch.bfloat16
+        assert torch.equal(ks.view(600, C), k.view(600, C)[idx])
+        ref = v.view(600, C)[idx].float().clamp(-65504, 65504).half()
+        assert torch.equal(vs.values().view(600, C), ref)
+        pad = vs.data[..., d:]
+        assert bool((pad[..., 0] == 1).all()) and bool((pad[..., 1:] == 0).all())
+        k2, v2 = ops.kv_gather_cast(k, v, heads, None)
+        assert k2 is k and torch.equal(v2.values(), v.float().clamp(-65504, 65504).half())

@@ -216,14 +216,9 @@ class Attention_Modulator(AttentionControl):
         q = query.to(torch.bfloat16).contiguous()
         k = key.to(torch.bfloat16).contiguous()
         v = value.to(torch.bfloat16).contiguous()
-        if self.p_operand == "f16":
-            # one pass over K/V: sort the keys of the masked streams (softmax is permutation invariant over keys) and
-            # convert V to fp16, the operand format of the single-MMA P.V contraction
-            k, v = ops.kv_gather_cast(k, v, self.heads, kv_index)
-        elif kv_index is not None:
-            Bk, Sk, Ck = k.shape
-            k = k.view(Bk * Sk, Ck).index_select(0, kv_index).view(Bk, Sk, Ck)
-            v = v.view(Bk * Sk, Ck).index_select(0, kv_index).view(Bk, Sk, Ck)
+        # one pass over K/V: sort the keys of the masked streams (softmax is permutation invariant over keys) and write
+        # V in the kernel's staging layout (operand format of the P.V contraction + ones column for the denominator)
+        k, v = ops.kv_gather_cast(k, v, self.heads, kv_index, p_operand=self.p_operand)
         return ops.attn_masked_kv(q, k, v, plan, self.heads, self.scale, bits, pop, out_dtype=dt)
 
     def plain_attention(self, query, key, value):

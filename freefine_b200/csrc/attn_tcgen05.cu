@@ -4,20 +4,24 @@
 // Attention_Modulator.Temporal_contextal_attention (src/utils/attention.py:1043-1091) and its _bg / _compose /
 // style-align / plain variants; see include/freefine_b200.h for the per-(stream,head) plan semantics.
 //
-// One CTA = one 128-row query tile of one (stream, head).  Six warps:
-//   warps 0-3  softmax + epilogue: thread t owns query row t == TMEM lane t (tcgen05.ld/st 32x32b)
-//   warp  4    TMA producer (one elected lane): Q once, then a ring of K/V tiles (128 keys x 64 channels boxes,
+// One CTA = one 128-row query tile of one (stream, head).  Ten warps:
+//   warps 0-7  softmax + epilogue, two warpgroups on the SAME tile: thread (w, lane) owns query row 32*(w%4)+lane ==
+//              its TMEM lane (tcgen05.ld/st 32x32b) and the key columns [32*(w/4), 32*(w/4)+32) of every 64-key tile.
+//              Four softmax warps per SM sub-partition (two CTAs per SM) keep the MUFU unit, the bound of the d=40
+//              layers, busy while the others wait on barriers / TMEM.
+//   warp  8    TMA producer (one elected lane): Q once, then a ring of K/V tiles (64 keys x 64 channels boxes,
 //              SWIZZLE_128B, channels beyond head_dim zero-filled by the TMA bounds check), + TMEM alloc/dealloc
-//   warp  5    MMA issuer (one elected lane):  S = Q K^T  (SS, M128 N128 K16 x DPAD/16, both operands K-major)
-//                                              O += P V   (TS: P = hi+lo bf16 pair in TMEM, V MN-major from the box)
-// Per K/V tile:  QK^T -> [s_full] -> softmax (2 sweeps over S in TMEM: max, then exp2 / row-sum / P written as a
-// hi+lo bf16 pair over the S columns already consumed) -> [p_full] -> PV -> [o_done, kv_empty].  The running max is only
-// refreshed when it grows by more than 2^8 (lazy rescale: O stays in TMEM, read-modify-written only then).
-// Region masks are bit-vectors; `allowed(q,k)` is evaluated in registers on 32-bit words, nothing [S,S]-shaped
-// exists anywhere.  Every pass of a plan has its own softmax; pass results are combined as
-// sum_p weight_p*roww_p(q)*O_p/l_p in registers (DPAD<=80) or in a third TMEM region (DPAD=160).
-// Overlap of the tensor pipe with the exp-bound softmax comes from two co-resident CTAs per SM (<=256 TMEM columns
-// and <=113 KB shared memory each for head_dim<=48, the S=4096 layers that dominate).
+//   warp  9    MMA issuer (one elected lane):  S = Q K^T  (SS, M128 N64 K16 x DPAD/16, both operands K-major)
+//                                              O += P V   (TS: P from TMEM, V MN-major from the box)
+// Per K/V tile:  QK^T -> [s_full] -> softmax: every thread loads BOTH halves of its row of S (the row max needs all 64
+// scores; computing it twice is cheaper than exchanging it), exponentiates its own half and writes P over its own S
+// columns once the other warpgroup has read them (named barriers) -> [p_full] -> PV -> [kv_empty].  The running
+// reference point is only refreshed when the row max grows by more than 2^8 / 2^24 (lazy rescale: O stays in TMEM,
+// read-modify-written only then).  V is ALWAYS the staging of ff_kv_gather_cast, whose ones column makes P.V also
+// produce the softmax denominator: no row-sum arithmetic in the softmax warps, numerator and denominator see the same
+// rounded P.  Region masks are bit-vectors; `allowed(q,k)` is evaluated in registers on 32-bit words, nothing
+// [S,S]-shaped exists anywhere.  Every pass of a plan has its own softmax; pass results are combined as
+// sum_p weight_p*roww_p(q)*O_p/l_p in a third TMEM region.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -30,9 +34,10 @@ constexpr int BN = 64;                  // keys per tile (S is double-buffered i
 constexpr int BOX_COLS = 64;            // channels per TMA box (128 bytes of bf16 = one swizzle-128B row)
 constexpr int TILE_BYTES = BM * 128;    // Q box: 128 rows x 128 B = 16 KiB
 constexpr int KV_BYTES = BN * 128;      // K / V box: 64 rows x 128 B = 8 KiB
-constexpr int NUM_THREADS = 192;
-// P operand of the PV contraction (template parameter HILO), chosen by the dtype of V -- tcgen05.mma kind::f16 wants
-// A and B in the SAME 16-bit format (an f16 A with a bf16 B raises an illegal-instruction fault on B200):
+constexpr int NUM_SOFTMAX_WARPS = 8;
+constexpr int NUM_THREADS = 32 * (NUM_SOFTMAX_WARPS + 2);
+// P operand of the PV contraction (template parameter HILO), fixed by the dtype of the staged V -- tcgen05.mma
+// kind::f16 wants A and B in the SAME 16-bit format (an f16 A with a bf16 B raises an illegal-instruction fault):
 //   V fp16  (HILO=false)  ONE fp16 P operand: 11 significant bits, half the PV tensor work and a third of the packing
 //                         ALU work of
 //   V bf16  (HILO=true)   a hi + lo pair of bf16 P operands (16 significant bits, two TS-MMAs per 16 keys).
@@ -45,12 +50,11 @@ template <bool HILO> constexpr float rescale_threshold() { return HILO ? 24.f : 
 #define FF_POLY_PATTERN 0x00
 #endif
 
-// DPAD: head_dim padded to the K-step of Q K^T (a multiple of 16).  DPV: columns of the V tile / of O.  With an fp16 V
-// (HILO=false) the staged V carries a column of ONES at channel head_dim (ff_kv_gather_cast), so the tensor core
-// produces the softmax denominator l = sum_k P[q,k] from exactly the rounded P it multiplies with V -- no row-sum
-// arithmetic in the softmax warps, and numerator and denominator see the same rounding.
+// DPAD: head_dim padded to the K-step of Q K^T (a multiple of 16).  DPV: channels per head of the staged V = columns
+// of the V tile / of O: head_dim real channels, a column of ONES at channel head_dim (its P.V column is the softmax
+// denominator l = sum_k P[q,k], from exactly the rounded P that multiplies V), zeros above.
 template <int DPAD, bool HILO> struct Cfg {
-  static constexpr int DPV = HILO ? DPAD : (DPAD == 16 ? 16 : (DPAD == 48 ? 48 : DPAD + 16));
+  static constexpr int DPV = DPAD == 16 ? 16 : (DPAD == 48 ? 48 : DPAD + 16);
   static constexpr int NKT = (DPAD + BOX_COLS - 1) / BOX_COLS;          // 64-channel boxes per operand tile
   static_assert((DPV + BOX_COLS - 1) / BOX_COLS == NKT, "V tile must span as many boxes as the K tile");
 #ifdef FF_DBG_NSTAGE
@@ -58,11 +62,8 @@ template <int DPAD, bool HILO> struct Cfg {
 #else
   static constexpr int NSTAGE = DPAD <= 48 ? 4 : (DPAD <= 80 ? 3 : 2);  // K/V ring depth
 #endif
-  // cross-pass accumulator location: TMEM where registers are short (DPAD=48 runs two CTAs per SM on 168 registers
-  // and keeps 64 scores live; 128 + 48 + 48 columns still fit the 256-column allocation), registers otherwise
-  static constexpr bool ACC_TMEM = DPAD > 80 || (DPAD > 16 && DPAD <= 48);
   static constexpr int TMEM_S = 0, TMEM_O = 2 * BN, TMEM_ACC = 2 * BN + DPV;   // S buffers at columns 0 and BN
-  static constexpr int TMEM_USED = 2 * BN + DPV + (ACC_TMEM ? DPAD : 0);
+  static constexpr int TMEM_USED = 2 * BN + DPV + DPAD;   // S x2, O, cross-pass accumulator
   static constexpr int TMEM_COLS = TMEM_USED <= 256 ? 256 : 512;
   static constexpr int SMEM_Q = NKT * TILE_BYTES;
   static constexpr int SMEM_STAGE = 2 * NKT * KV_BYTES;                 // K tiles then V tiles
@@ -131,6 +132,24 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
       : "memory");
+}
+// Named barriers 1..4 (0 is __syncthreads): producer/consumer hand-shake between the two softmax warpgroups.
+// (immediate ids: with a register id ptxas reserves all 16 hardware barriers for the CTA)
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  switch (id) {
+    case 1: asm volatile("bar.arrive 1, %0;" ::"r"(count) : "memory"); break;
+    case 2: asm volatile("bar.arrive 2, %0;" ::"r"(count) : "memory"); break;
+    case 3: asm volatile("bar.arrive 3, %0;" ::"r"(count) : "memory"); break;
+    default: asm volatile("bar.arrive 4, %0;" ::"r"(count) : "memory"); break;
+  }
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  switch (id) {
+    case 1: asm volatile("bar.sync 1, %0;" ::"r"(count) : "memory"); break;
+    case 2: asm volatile("bar.sync 2, %0;" ::"r"(count) : "memory"); break;
+    case 3: asm volatile("bar.sync 3, %0;" ::"r"(count) : "memory"); break;
+    default: asm volatile("bar.sync 4, %0;" ::"r"(count) : "memory"); break;
+  }
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -383,10 +402,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&b);
 }
 
-// 16 scores -> exp2(s*sc + nb), row-sum, P as hi/lo bf16 pairs.  MASKED: bit i of `bits` gates key i.
+// 16 scores -> p = exp2(s*sc + nb) as hi/lo bf16 pairs: hl[0..8) = hi (truncated upper halves, key 2i in the low
+// half), hl[8..16) = lo = bf16(p - hi).  MASKED: bit i of `bits` gates key i.
 template <bool MASKED>
-__device__ __forceinline__ void softmax_chunk(const float (&s)[16], uint32_t (&hl)[16], float sc, float nb,
-                                              uint32_t bits, float2& la, float2& lb) {
+__device__ __forceinline__ void softmax_chunk_hilo(const float* s, uint32_t* hl, float sc, float nb, uint32_t bits) {
   const float2 sc2 = make_float2(sc, sc), nb2 = make_float2(nb, nb);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -396,11 +415,10 @@ __device__ __forceinline__ void softmax_chunk(const float (&s)[16], uint32_t (&h
       x.y = (bits >> (2 * i + 1)) & 1u ? x.y : -INFINITY;
     }
     const float2 e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
-    if (i & 1) lb = __fadd2_rn(lb, e); else la = __fadd2_rn(la, e);
     const uint32_t b0 = __float_as_uint(e.x), b1 = __float_as_uint(e.y);
-    hl[i] = __byte_perm(b0, b1, 0x7632);                         // hi: truncated upper halves, key 2i in the low half
+    hl[i] = __byte_perm(b0, b1, 0x7632);
     const float2 r = __fadd2_rn(e, make_float2(-__uint_as_float(b0 & 0xffff0000u), -__uint_as_float(b1 & 0xffff0000u)));
-    hl[8 + i] = pack_bf16x2(r.x, r.y);                           // lo = bf16(p - hi)
+    hl[8 + i] = pack_bf16x2(r.x, r.y);
   }
 }
 
@@ -487,15 +505,15 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     mbar_init(bar_q, 1);
     mbar_init(bar_s, 1);
     mbar_init(bar_s + 8, 1);
-    mbar_init(bar_p, BM);
-    mbar_init(bar_p + 8, BM);
+    mbar_init(bar_p, NUM_SOFTMAX_WARPS);        // one elected arrival per softmax warp
+    mbar_init(bar_p + 8, NUM_SOFTMAX_WARPS);
     for (int i = 0; i < C::NSTAGE; ++i) {
       mbar_init(bar_kv_full + 8 * i, 1);
       mbar_init(bar_kv_empty + 8 * i, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == NUM_SOFTMAX_WARPS) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
                  "r"((uint32_t)C::TMEM_COLS)
                  : "memory");
@@ -507,14 +525,14 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   const uint32_t tmem = *tmem_slot_ptr;
 #ifdef FF_ENABLE_TRACE   // build with FF_TRACE=1 (csrc/build.py); off in the product build
   uint32_t* const tr = g_trace;
-  const int trole = warp == 4 ? 0 : (warp == 5 ? 1 : (threadIdx.x == 0 ? 2 : (threadIdx.x == 96 ? 3 : -1)));
-#define FF_TRACE(it_, site_) do { if (tr && trole >= 0 && (warp < 4 || lane == 0)) trace(tr, trole, (uint32_t)(it_), (site_)); } while (0)
+  const int trole = warp == NUM_SOFTMAX_WARPS ? 0 : (warp == NUM_SOFTMAX_WARPS + 1 ? 1 : (threadIdx.x == 0 ? 2 : (threadIdx.x == 224 ? 3 : -1)));
+#define FF_TRACE(it_, site_) do { if (tr && trole >= 0 && (warp < NUM_SOFTMAX_WARPS || lane == 0)) trace(tr, trole, (uint32_t)(it_), (site_)); } while (0)
 #else
 #define FF_TRACE(it_, site_) do { } while (0)
 #endif
   FF_TRACE(0, 1);
 
-  if (warp == 4) {
+  if (warp == NUM_SOFTMAX_WARPS) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       mbar_expect_tx(bar_q, C::NKT * TILE_BYTES);
@@ -554,7 +572,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == NUM_SOFTMAX_WARPS + 1) {
     // ===================================== MMA issuer =======================================
     if (lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc(BN, 0);
@@ -584,8 +602,9 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             mma_ts(tmem + C::TMEM_O, a_hi, vdesc, idesc_pv, (!first_of_pass || ks > 0) ? 1u : 0u);
             mma_ts(tmem + C::TMEM_O, a_hi + 8, vdesc, idesc_pv, 1u);
           } else {
-            // single fp16 P: the 16 keys of K-step ks are the 8 packed columns [8ks, 8ks+8) of the S buffer
-            mma_ts(tmem + C::TMEM_O, tmem + C::TMEM_S + BN * (t & 1) + 8 * ks, vdesc, idesc_pv,
+            // single fp16 P: the 16 keys of K-step ks are 8 packed columns inside the S columns of the warpgroup
+            // that owns them: 32*(ks/2) + 8*(ks%2)
+            mma_ts(tmem + C::TMEM_O, tmem + C::TMEM_S + BN * (t & 1) + 32 * (ks >> 1) + 8 * (ks & 1), vdesc, idesc_pv,
                    (!first_of_pass || ks > 0) ? 1u : 0u);
           }
         }
@@ -641,16 +660,11 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     }
   } else {
     // ===================================== softmax + epilogue ===============================
-    const int row = q0 + threadIdx.x;
-    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
-    float acc[C::ACC_TMEM ? 1 : DPAD];
-    if constexpr (!C::ACC_TMEM) {
-#pragma unroll
-      for (int i = 0; i < DPAD; ++i) acc[i] = 0.f;
-    } else {
-      acc[0] = 0.f;
-    }
-    bool acc_started = false;   // ACC_TMEM: has any pass been added yet (uniform across the CTA)
+    const int wq = warp & 3;        // TMEM lane quarter of this warp (hardware rule: warp w reaches lanes 32*(w%4)..+31)
+    const int half = warp >> 2;     // key columns [32*half, 32*half+32) of every tile; O / accumulator chunks of parity half
+    const int row = q0 + 32 * wq + lane;
+    const uint32_t tlane = tmem + ((uint32_t)(wq * 32) << 16);
+    bool acc_started = false;       // has any pass been added to the TMEM accumulator yet (uniform across the CTA)
     int it = 0;
 #pragma unroll 1
     for (int ip = 0; ip < n_pass; ++ip) {
@@ -663,7 +677,6 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         rb = (__ldg(p.bitmasks + (size_t)ps.row_mask * p.mask_words + (row >> 5)) >> (row & 31)) & 1u;
       const bool rowflip = cx.rowxor && rb;
       float m_used = 0.f;
-      float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
       bool first = true;
 #pragma unroll 1
       for (int seg = 0; seg < 2; ++seg) {
@@ -685,42 +698,90 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           FF_TRACE(it, 31);
           tc_fence_after();
           const uint32_t tS = tlane + C::TMEM_S + BN * (it & 1);     // this tile's S / P buffer
-          // ---- sweep 1: row max over ALL 64 columns (an upper bound of the max over the allowed keys is all the
-          // softmax needs: bf16/fp32 keep their relative precision whatever the reference point; padded columns are 0)
-          float mt;
-          float sa[32], sb[32];     // single-operand P: the 64 scores stay in registers for the exp sweep
-          {
-            float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-            tmem_ld32(tS, sa);
-            tmem_wait_ld32(sa);
-            tmem_ld32(tS + 32, sb);
+          // ---- allowed-key bits of this row for MIX tiles (boundary / ragged): bit i <=> key j*BN + i
+          uint32_t kb_lo = 0xffffffffu, kb_hi = 0xffffffffu;         // columns [0,32) / [32,64)
+          if (cls == TILE_MIX) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              m0 = fmaxf(m0, fmaxf(sa[i], sa[i + 1]));
-              m1 = fmaxf(m1, fmaxf(sa[i + 2], sa[i + 3]));
-              m2 = fmaxf(m2, fmaxf(sa[i + 4], sa[i + 5]));
-              m3 = fmaxf(m3, fmaxf(sa[i + 6], sa[i + 7]));
+            for (int w = 0; w < 2; ++w) {
+              const int kbase = j * BN + 32 * w;
+              const int rem = p.s_kv - kbase;
+              const uint32_t valid = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+              uint32_t kb = 0xffffffffu;
+              if (sg.kmask >= 0 && !uniform && rem > 0) {
+                if (sg.prefix) {
+                  const int t = sg.T - kbase;
+                  kb = t >= 32 ? 0xffffffffu : (t <= 0 ? 0u : ((1u << t) - 1u));
+                } else {
+                  kb = __ldg(p.bitmasks + (size_t)sg.kmask * p.mask_words + (kbase >> 5));   // BN % 32 == 0
+                }
+                if (flip) kb = ~kb;
+              }
+              if (w == 0) kb_lo = kb & valid; else kb_hi = kb & valid;
             }
-            tmem_wait_ld32(sb);
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              m0 = fmaxf(m0, fmaxf(sb[i], sb[i + 1]));
-              m1 = fmaxf(m1, fmaxf(sb[i + 2], sb[i + 3]));
-              m2 = fmaxf(m2, fmaxf(sb[i + 4], sb[i + 5]));
-              m3 = fmaxf(m3, fmaxf(sb[i + 6], sb[i + 7]));
-            }
-            mt = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
           }
-          const float mts = uniform ? 0.f : mt * p.scale_log2;
-          // ---- running reference point, lazy rescale of O (TMEM read-modify-write only when it grew by > 2^8)
+          const uint32_t kb_mine = half ? kb_hi : kb_lo, kb_other = half ? kb_lo : kb_hi;
+          // ---- row max over the ALLOWED keys of the tile (the fp16 P operand has a narrow exponent range: the
+          // reference point must not come from keys this row does not read).  The other warpgroup's half is reduced
+          // first and dropped (registers: two CTAs x 320 threads leave 96 per thread), mine stays for the exp sweep.
+          float mt, sm[32];
+          {
+            float so[32];
+            tmem_ld32(tS + 32 * (half ^ 1), so);
+            tmem_wait_ld32(so);
+            float m0, m1;
+            if (cls != TILE_MIX) {
+              m0 = fmaxf(so[0], so[1]);
+              m1 = fmaxf(so[2], so[3]);
+#pragma unroll
+              for (int i = 4; i < 32; i += 4) {
+                m0 = fmaxf(m0, fmaxf(so[i], so[i + 1]));
+                m1 = fmaxf(m1, fmaxf(so[i + 2], so[i + 3]));
+              }
+            } else {
+              m0 = m1 = -INFINITY;
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                m0 = fmaxf(m0, (kb_other >> i) & 1u ? so[i] : -INFINITY);
+                m1 = fmaxf(m1, (kb_other >> (i + 1)) & 1u ? so[i + 1] : -INFINITY);
+              }
+            }
+            mt = fmaxf(m0, m1);
+          }
+          {
+            tmem_ld32(tS + 32 * half, sm);
+            tmem_wait_ld32(sm);
+            // "this warpgroup has read the tile": the other one may now overwrite ITS columns (read above for the max)
+            named_bar_arrive(1 + 2 * (it & 1) + half, 32 * NUM_SOFTMAX_WARPS);
+            float m0, m1;
+            if (cls != TILE_MIX) {
+              m0 = fmaxf(sm[0], sm[1]);
+              m1 = fmaxf(sm[2], sm[3]);
+#pragma unroll
+              for (int i = 4; i < 32; i += 4) {
+                m0 = fmaxf(m0, fmaxf(sm[i], sm[i + 1]));
+                m1 = fmaxf(m1, fmaxf(sm[i + 2], sm[i + 3]));
+              }
+            } else {
+              m0 = m1 = -INFINITY;
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                m0 = fmaxf(m0, (kb_mine >> i) & 1u ? sm[i] : -INFINITY);
+                m1 = fmaxf(m1, (kb_mine >> (i + 1)) & 1u ? sm[i + 1] : -INFINITY);
+              }
+            }
+            mt = fmaxf(mt, fmaxf(m0, m1));
+            if (cls != TILE_MIX && !row_ok_cls) mt = -INFINITY;
+          }
+          const float mts = uniform ? 0.f : mt * p.scale_log2;     // (-inf: the row reads nothing from this tile)
+          // ---- running reference point, lazy rescale of O (TMEM read-modify-write only when the max grew a lot).
+          // Both threads of a row take identical decisions (same data, same arithmetic).
           float alpha = 1.f;
           bool grow = false;
           if (first) {
             m_used = mts;
           } else if (mts > m_used + rescale_threshold<P_HILO>()) {
-            alpha = fast_exp2(m_used - mts);
+            alpha = fast_exp2(m_used - mts);       // (m_used = -inf, nothing read so far: alpha = 0, O is 0 anyway)
             m_used = mts;
-            la.x *= alpha; la.y *= alpha; lb.x *= alpha; lb.y *= alpha;
             grow = true;
           }
           if (__any_sync(0xffffffffu, grow)) {
@@ -729,7 +790,8 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             FF_TRACE(it, 33);
             tc_fence_after();
 #pragma unroll
-            for (int c = 0; c < C::DPV / 16; ++c) {      // (fp16 V: includes the denominator column)
+            for (int c = 0; c < C::DPV / 16; ++c) {      // (includes the denominator column); chunks split by parity
+              if ((c & 1) != half) continue;
               float o[16];
               uint32_t ob[16];
               tmem_ld16(tlane + C::TMEM_O + 16 * c, o);
@@ -739,93 +801,37 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
               tmem_st16(tlane + C::TMEM_O + 16 * c, ob);
             }
           }
-          // ---- sweep 2: p = 2^(s*scale*log2e - m), row sum.  P goes to the tensor core as TWO bf16 operands,
-          // p = hi + lo (hi = truncated upper 16 bits, lo = bf16(p - hi)): 16 mantissa bits instead of 8, so the
-          // result stays within the fp32-reference tolerance; the second PV MMA rides on tensor-pipe slack.  The 16
-          // keys of K-step ks (S columns [16ks,16ks+16)) are overwritten in place by hi -> [16ks,16ks+8) and
-          // lo -> [16ks+8,16ks+16): only columns this thread has already consumed.
-          if constexpr (!P_HILO) {
-            // ---- exp sweep from registers: P = fp16(2^(s*scale*log2e - m)) over columns [0,32) of this S buffer
-            // (16 keys of K-step ks -> packed columns [8ks, 8ks+8)); every S column is already in registers.
-            uint32_t pk[8];
-            if (cls != TILE_MIX) {
-              // one predicate per row: bias -m (allowed) or -inf (row reads nothing from this tile -> p = 0)
-              const float nb = row_ok_cls ? -m_used : -INFINITY;
-#pragma unroll
-              for (int c = 0; c < BN / 16; ++c) {
-                softmax_chunk_f16<false>(c < 2 ? sa + 16 * c : sb + 16 * (c - 2), pk, sc, nb, 0u);
-                tmem_st8(tS + 8 * c, pk);
-              }
-            } else {
-              // boundary / ragged tile: evaluate allowed(q,k) per element on 16-bit slices of the mask words
-              const float nb = -m_used;
-#pragma unroll
-              for (int c = 0; c < BN / 16; ++c) {
-                const int kbase = j * BN + 16 * c;
-                const int rem = p.s_kv - kbase;
-                const uint32_t valid = rem >= 16 ? 0xffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
-                uint32_t kb = 0xffffu;
-                if (sg.kmask >= 0 && !uniform && rem > 0) {
-                  if (sg.prefix) {
-                    const int t = sg.T - kbase;
-                    kb = t >= 16 ? 0xffffu : (t <= 0 ? 0u : ((1u << t) - 1u));
-                  } else {
-                    kb = (__ldg(p.bitmasks + (size_t)sg.kmask * p.mask_words + (kbase >> 5)) >> (kbase & 31)) & 0xffffu;
-                  }
-                  if (flip) kb = ~kb;
-                }
-                softmax_chunk_f16<true>(c < 2 ? sa + 16 * c : sb + 16 * (c - 2), pk, sc, nb, kb & valid);
-                tmem_st8(tS + 8 * c, pk);
-              }
-            }
-          } else
+          // ---- p = 2^(s*scale*log2e - m) for my 32 keys, packed for the tensor core over my own S columns
+          // [32*half, 32*half+32):  fp16: K-step ks=2*half+jj -> packed columns 32*half + 8*jj + [0,8);
+          // hi/lo bf16: K-step ks -> hi at 16*ks + [0,8), lo at 16*ks + [8,16).
+          const float nb = (cls == TILE_MIX || row_ok_cls) ? -m_used : -INFINITY;   // -inf: p = 0 for the whole row
+          uint32_t pk[P_HILO ? 32 : 16];
           if (cls != TILE_MIX) {
-            // one predicate per row: bias -m (allowed) or -inf (row reads nothing from this tile -> p = 0)
-            const float nb = row_ok_cls ? -m_used : -INFINITY;
-            float ca[16], cb[16];
-            uint32_t hl[16];
-            tmem_ld16(tS, ca);
-            tmem_wait_ld16(ca);
 #pragma unroll
-            for (int ks = 0; ks < BN / 16; ks += 2) {
-              tmem_ld16(tS + 16 * (ks + 1), cb);                          // in flight while chunk ks is processed
-              softmax_chunk<false>(ca, hl, sc, nb, 0u, la, lb);
-              tmem_st16(tS + 16 * ks, hl);
-              tmem_wait_ld16(cb);
-              if (ks + 2 < BN / 16) tmem_ld16(tS + 16 * (ks + 2), ca);
-              softmax_chunk<false>(cb, hl, sc, nb, 0u, la, lb);
-              tmem_st16(tS + 16 * (ks + 1), hl);
-              if (ks + 2 < BN / 16) tmem_wait_ld16(ca);
+            for (int jj = 0; jj < 2; ++jj) {
+              if constexpr (P_HILO) softmax_chunk_hilo<false>(sm + 16 * jj, pk + 16 * jj, sc, nb, 0u);
+              else softmax_chunk_f16<false>(sm + 16 * jj, pk + 8 * jj, sc, nb, 0u);
             }
           } else {
-            // boundary / ragged tile: evaluate allowed(q,k) per element on 16-bit slices of the mask words
-            const float nb = -m_used;
-#pragma unroll 1
-            for (int ks = 0; ks < BN / 16; ++ks) {
-              const int kbase = j * BN + 16 * ks;
-              const int rem = p.s_kv - kbase;
-              const uint32_t valid = rem >= 16 ? 0xffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
-              uint32_t kb = 0xffffu;
-              if (sg.kmask >= 0 && !uniform && rem > 0) {
-                if (sg.prefix) {
-                  const int t = sg.T - kbase;
-                  kb = t >= 16 ? 0xffffu : (t <= 0 ? 0u : ((1u << t) - 1u));
-                } else {
-                  kb = (__ldg(p.bitmasks + (size_t)sg.kmask * p.mask_words + (kbase >> 5)) >> (kbase & 31)) & 0xffffu;
-                }
-                if (flip) kb = ~kb;
-              }
-              float cs[16];
-              uint32_t hl[16];
-              tmem_ld16(tS + 16 * ks, cs);
-              tmem_wait_ld16(cs);
-              softmax_chunk<true>(cs, hl, sc, nb, kb & valid, la, lb);
-              tmem_st16(tS + 16 * ks, hl);
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+              const uint32_t bits = (kb_mine >> (16 * jj)) & 0xffffu;
+              if constexpr (P_HILO) softmax_chunk_hilo<true>(sm + 16 * jj, pk + 16 * jj, sc, nb, bits);
+              else softmax_chunk_f16<true>(sm + 16 * jj, pk + 8 * jj, sc, nb, bits);
             }
+          }
+          // the other warpgroup has read my columns
+          named_bar_sync(1 + 2 * (it & 1) + (half ^ 1), 32 * NUM_SOFTMAX_WARPS);
+          if constexpr (P_HILO) {
+            tmem_st16(tS + 32 * half, *reinterpret_cast<const uint32_t(*)[16]>(pk));
+            tmem_st16(tS + 32 * half + 16, *reinterpret_cast<const uint32_t(*)[16]>(pk + 16));
+          } else {
+            tmem_st16(tS + 32 * half, *reinterpret_cast<const uint32_t(*)[16]>(pk));
           }
           tmem_wait_st();
           tc_fence_before();
-          mbar_arrive(bar_p + 8 * (it & 1));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_p + 8 * (it & 1));
           FF_TRACE(it, 34);
           first = false;
           ++it;
@@ -833,61 +839,53 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         }
       }
       if (first) continue;     // (defensive) no tile of this pass was processed: nothing to add
-      // ---- end of pass: acc += weight * roww / l * O
+      // ---- end of pass: acc += weight * roww / l * O   (l = the ones-column of P.V)
       FF_TRACE(it, 35);
       mbar_wait(bar_s + 8 * ((it + 1) & 1), ((it + 1) >> 1) & 1);   // s_full(L+2) => PV(L) of this pass's last tile L = it-1
       FF_TRACE(it, 36);
       tc_fence_after();
-      const float l = P_HILO ? (la.x + la.y) + (lb.x + lb.y) : tmem_ld1_wait(tlane + C::TMEM_O + p.head_dim);
+      const float l = tmem_ld1_wait(tlane + C::TMEM_O + p.head_dim);
       float coef = ps.weight;
       if (ps.flags & FF_PASS_ROW_WEIGHT) coef = rb ? coef : 0.f;
       coef = l > 0.f ? coef / l : 0.f;
 #pragma unroll
       for (int c = 0; c < DPAD / 16; ++c) {
-        float o[16];
+        if ((c & 1) != half) continue;
+        float o[16], a[16];
+        uint32_t ab[16];
         tmem_ld16(tlane + C::TMEM_O + 16 * c, o);
         tmem_wait_ld16(o);
-        if constexpr (C::ACC_TMEM) {
-          float a[16];
-          uint32_t ab[16];
-          if (acc_started) {
-            tmem_ld16(tlane + C::TMEM_ACC + 16 * c, a);
-            tmem_wait_ld16(a);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) a[i] = 0.f;
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) ab[i] = __float_as_uint(fmaf(coef, o[i], a[i]));
-          tmem_st16(tlane + C::TMEM_ACC + 16 * c, ab);
+        if (acc_started) {
+          tmem_ld16(tlane + C::TMEM_ACC + 16 * c, a);
+          tmem_wait_ld16(a);
         } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) acc[16 * c + i] = fmaf(coef, o[i], acc[16 * c + i]);
+          for (int i = 0; i < 16; ++i) a[i] = 0.f;
         }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) ab[i] = __float_as_uint(fmaf(coef, o[i], a[i]));
+        tmem_st16(tlane + C::TMEM_ACC + 16 * c, ab);
       }
-      if constexpr (C::ACC_TMEM) tmem_wait_st();
+      tmem_wait_st();
       acc_started = true;
     }
-    // ---- write the row: out[stream, row, head*d : (head+1)*d].  tcgen05.ld is warp-collective (.sync.aligned):
-    // every lane executes the TMEM loads, only the global stores are predicated on row < s_q.
+    // ---- write the row: out[stream, row, head*d : (head+1)*d], 16-channel chunks split between the two warpgroups.
+    // tcgen05.ld is warp-collective (.sync.aligned): every lane executes the TMEM loads, only the global stores are
+    // predicated on row < s_q.
     {
       const bool row_ok = row < p.s_q;
       const size_t o_off = ((size_t)stream * p.s_q + (row_ok ? row : 0)) * ((size_t)p.heads * p.head_dim) +
                            (size_t)head * p.head_dim;
 #pragma unroll
       for (int c = 0; c < DPAD / 16; ++c) {
+        if ((c & 1) != half) continue;
         float o[16];
-        if constexpr (C::ACC_TMEM) {
-          if (acc_started) {
-            tmem_ld16(tlane + C::TMEM_ACC + 16 * c, o);
-            tmem_wait_ld16(o);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = 0.f;
-          }
+        if (acc_started) {
+          tmem_ld16(tlane + C::TMEM_ACC + 16 * c, o);
+          tmem_wait_ld16(o);
         } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = acc[16 * c + i];
+          for (int i = 0; i < 16; ++i) o[i] = 0.f;
         }
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
@@ -913,7 +911,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   // ---- teardown: every tcgen05 op of this CTA has completed (softmax threads waited on o_done of the last tile)
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == NUM_SOFTMAX_WARPS) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)C::TMEM_COLS)
                  : "memory");
@@ -941,7 +939,7 @@ EncodeTiledFn get_encode_fn() {
 
 // [streams, S, heads, d] bf16 view of a dense [streams, S, heads*d] tensor; box = 64 channels x 1 head x 128 rows.
 // Channels >= d of a box are out of bounds in dimension 0 and therefore zero-filled.
-// For the staged fp16 V, d = v_head_stride (real channels + ones column + zero padding, all in bounds).
+// For the staged V, d = v_head_stride (real channels + ones column + zero padding, all in bounds).
 int make_map(CUtensorMap* map, const void* base, int streams, int S, int heads, int d, int box_rows,
              bool f16 = false) {
   EncodeTiledFn enc = get_encode_fn();
@@ -990,8 +988,8 @@ extern "C" int ff_debug_set_trace(void* device_visible_ptr) {
   return FF_OK;
 }
 
-// Channels per head of the staged fp16 V: head_dim real channels, a ones column at channel head_dim, zeros above;
-// equals Cfg<DPAD,false>::DPV of the instantiation ff_attn_masked_kv picks for this head_dim.
+// Channels per head of the staged V: head_dim real channels, a ones column at channel head_dim, zeros above;
+// equals Cfg<DPAD,*>::DPV of the instantiation ff_attn_masked_kv picks for this head_dim.
 extern "C" int ff_attn_v_head_stride(int32_t head_dim) {
   if (head_dim <= 8) return Cfg<16, false>::DPV;
   if (head_dim <= 40) return Cfg<48, false>::DPV;
@@ -1028,13 +1026,10 @@ extern "C" int ff_attn_masked_kv(const FFAttnArgs* a, void* stream) {
   if ((rc = make_map(&mq, a->q, a->n_streams, a->s_q, a->heads, a->head_dim, BM)) != FF_OK) return rc;
   if ((rc = make_map(&mk, a->k, a->n_kv_streams, a->s_kv, a->heads, a->head_dim, BN)) != FF_OK) return rc;
   const bool v_f16 = a->v_dtype == FF_DT_F16;
-  if (v_f16)
-    FF_REQUIRE(a->v_head_stride == ff_attn_v_head_stride(a->head_dim),
-               "ff_attn_masked_kv: fp16 V must be staged by ff_kv_gather_cast (v_head_stride=%d, expected %d)",
-               a->v_head_stride, ff_attn_v_head_stride(a->head_dim));
-  if ((rc = make_map(&mv, a->v, a->n_kv_streams, a->s_kv, a->heads, v_f16 ? a->v_head_stride : a->head_dim, BN,
-                     v_f16)) != FF_OK)
-    return rc;
+  FF_REQUIRE(a->v_head_stride == ff_attn_v_head_stride(a->head_dim),
+             "ff_attn_masked_kv: V must be staged by ff_kv_gather_cast (v_head_stride=%d, expected %d)",
+             a->v_head_stride, ff_attn_v_head_stride(a->head_dim));
+  if ((rc = make_map(&mv, a->v, a->n_kv_streams, a->s_kv, a->heads, a->v_head_stride, BN, v_f16)) != FF_OK) return rc;
 
   KParams kp;
   kp.plan = a->plan;
@@ -1051,14 +1046,15 @@ extern "C" int ff_attn_masked_kv(const FFAttnArgs* a, void* stream) {
   kp.scale_log2 = a->scale * 1.4426950408889634f;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int d = a->head_dim;
-  if (v_f16) {   // thresholds leave room for the ones column at channel d inside DPV (see ff_attn_v_head_stride)
+  // thresholds leave room for the ones column at channel d inside DPV (see ff_attn_v_head_stride)
+  if (v_f16) {
     if (d <= 8) return launch<16, false>(mq, mk, mv, kp, a->n_streams, st);
     if (d <= 40) return launch<48, false>(mq, mk, mv, kp, a->n_streams, st);
     if (d <= 80) return launch<80, false>(mq, mk, mv, kp, a->n_streams, st);
     return launch<160, false>(mq, mk, mv, kp, a->n_streams, st);
   }
-  if (d <= 16) return launch<16, true>(mq, mk, mv, kp, a->n_streams, st);
-  if (d <= 48) return launch<48, true>(mq, mk, mv, kp, a->n_streams, st);
+  if (d <= 8) return launch<16, true>(mq, mk, mv, kp, a->n_streams, st);
+  if (d <= 40) return launch<48, true>(mq, mk, mv, kp, a->n_streams, st);
   if (d <= 80) return launch<80, true>(mq, mk, mv, kp, a->n_streams, st);
   return launch<160, true>(mq, mk, mv, kp, a->n_streams, st);
 }

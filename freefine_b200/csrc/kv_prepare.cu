@@ -21,6 +21,7 @@ __device__ __forceinline__ uint32_t bf16x2_to_f16x2_sat(uint32_t b) {
 
 // One thread per 16-byte chunk.  K: rows * (heads*d/8) chunks, plain gather.  V: rows * heads * (vhs/8) chunks of the
 // padded layout [rows, heads, vhs]: chunks below d come from V, the chunk at d holds {1,0,..,0}, the rest zeros.
+template <bool F16>
 __global__ void __launch_bounds__(256)
 kv_gather_cast_kernel(const uint4* __restrict__ k, const uint4* __restrict__ v, const long long* __restrict__ idx,
                       uint4* __restrict__ k_out, uint4* __restrict__ v_out, long long rows, int heads, int dv, int vv) {
@@ -36,13 +37,17 @@ kv_gather_cast_kernel(const uint4* __restrict__ k, const uint4* __restrict__ v, 
     if (w < dv) {
       const long long src = idx ? __ldg(idx + r) : r;
       const uint4 x = __ldg(v + src * krow + h * dv + w);
-      o.x = bf16x2_to_f16x2_sat(x.x);
-      o.y = bf16x2_to_f16x2_sat(x.y);
-      o.z = bf16x2_to_f16x2_sat(x.z);
-      o.w = bf16x2_to_f16x2_sat(x.w);
+      if (F16) {
+        o.x = bf16x2_to_f16x2_sat(x.x);
+        o.y = bf16x2_to_f16x2_sat(x.y);
+        o.z = bf16x2_to_f16x2_sat(x.z);
+        o.w = bf16x2_to_f16x2_sat(x.w);
+      } else {
+        o = x;
+      }
       if (k_out) k_out[r * krow + h * dv + w] = __ldg(k + src * krow + h * dv + w);
     } else if (w == dv) {
-      o.x = 0x00003c00u;   // fp16 1.0 at channel head_dim
+      o.x = F16 ? 0x00003c00u : 0x00003f80u;   // 1.0 (fp16 / bf16) at channel head_dim
     }
     v_out[i] = o;
   }
@@ -50,9 +55,11 @@ kv_gather_cast_kernel(const uint4* __restrict__ k, const uint4* __restrict__ v, 
 
 }  // namespace
 
-extern "C" int ff_kv_gather_cast(const void* k, const void* v, const int64_t* row_index, void* k_out, void* v_out_f16,
-                                 int64_t rows, int32_t heads, int32_t head_dim, void* stream) {
-  FF_REQUIRE(v && v_out_f16, "ff_kv_gather_cast: null pointer");
+extern "C" int ff_kv_gather_cast(const void* k, const void* v, const int64_t* row_index, void* k_out, void* v_out,
+                                 int32_t v_out_dtype, int64_t rows, int32_t heads, int32_t head_dim, void* stream) {
+  void* v_out_f16 = v_out;
+  FF_REQUIRE(v && v_out, "ff_kv_gather_cast: null pointer");
+  FF_REQUIRE(v_out_dtype == FF_DT_F16 || v_out_dtype == FF_DT_BF16, "ff_kv_gather_cast: v_out_dtype must be f16 or bf16");
   FF_REQUIRE((k == nullptr) == (k_out == nullptr), "ff_kv_gather_cast: k and k_out go together");
   FF_REQUIRE(rows > 0 && heads > 0 && head_dim >= 8 && head_dim % 8 == 0 && head_dim <= 160,
              "ff_kv_gather_cast: rows=%lld heads=%d head_dim=%d (head_dim must be a multiple of 8, <= 160)",
@@ -63,8 +70,13 @@ extern "C" int ff_kv_gather_cast(const void* k, const void* v, const int64_t* ro
   const long long total = rows * heads * (vhs / 8);
   long long grid = (total + 255) / 256;
   if (grid > 148 * 16) grid = 148 * 16;
-  kv_gather_cast_kernel<<<(int)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint4*>(k), static_cast<const uint4*>(v), reinterpret_cast<const long long*>(row_index),
-      static_cast<uint4*>(k_out), static_cast<uint4*>(v_out_f16), rows, heads, head_dim / 8, vhs / 8);
+  if (v_out_dtype == FF_DT_F16)
+    kv_gather_cast_kernel<true><<<(int)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(k), static_cast<const uint4*>(v), reinterpret_cast<const long long*>(row_index),
+        static_cast<uint4*>(k_out), static_cast<uint4*>(v_out), rows, heads, head_dim / 8, vhs / 8);
+  else
+    kv_gather_cast_kernel<false><<<(int)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(k), static_cast<const uint4*>(v), reinterpret_cast<const long long*>(row_index),
+        static_cast<uint4*>(k_out), static_cast<uint4*>(v_out), rows, heads, head_dim / 8, vhs / 8);
   return ff::check_launch("ff_kv_gather_cast");
 }

@@ -211,22 +211,26 @@ def mask_downsample_pack(masks, h, w, bits=None, popcount=None):
 # (a) attention
 # ---------------------------------------------------------------------------------------------------------------
 class StagedV:
-    """fp16 staging of V for ff_attn_masked_kv (ff_kv_gather_cast): data [Bk, Skv, heads, v_head_stride] fp16 with a ones
-    column at channel head_dim."""
+    """Staging of V for ff_attn_masked_kv (ff_kv_gather_cast): data [Bk, Skv, heads, v_head_stride] fp16 or bf16 with a
+    ones column at channel head_dim."""
     __slots__ = ("data", "heads", "head_dim")
 
     def __init__(self, data, heads, head_dim):
         self.data, self.heads, self.head_dim = data, heads, head_dim
 
     def values(self):
-        """[Bk, Skv, heads*head_dim] fp16 view-copy of the real channels (tests)."""
+        """[Bk, Skv, heads*head_dim] copy of the real channels (tests)."""
         return self.data[..., : self.head_dim].reshape(self.data.shape[0], self.data.shape[1], -1)
 
 
-def kv_gather_cast(k, v, heads, row_index=None, gather_k=True):
+P_OPERAND_DTYPE = {"f16": torch.float16, "bf16x2": torch.bfloat16}
+
+
+def kv_gather_cast(k, v, heads, row_index=None, gather_k=True, p_operand="f16"):
     """K/V staging in one pass: rows gathered by `row_index` (int64 over the flattened [Bk*Skv] rows, None = identity),
-    V converted bf16 -> fp16 (saturating) into the padded per-head layout of the single-operand P.V path.  Returns
-    (k_sorted bf16, StagedV); K is returned untouched when there is no gather."""
+    V written into the padded per-head layout the kernel reads -- as fp16 (p_operand "f16": one fp16 P operand, the
+    fast path; saturating) or bf16 ("bf16x2": hi+lo bf16 P pair).  Returns (k_sorted bf16, StagedV); K is returned
+    untouched when there is no gather."""
     _chk(k, torch.bfloat16, "k", 3)
     _chk(v, torch.bfloat16, "v", 3)
     if v.shape != k.shape or k.shape[2] % heads:
@@ -241,35 +245,35 @@ def kv_gather_cast(k, v, heads, row_index=None, gather_k=True):
     vhs = lib.ff_attn_v_head_stride(d)
     do_k = gather_k and row_index is not None
     k_out = torch.empty_like(k) if do_k else None
-    v_out = torch.empty((Bk, Sk, heads, vhs), dtype=torch.float16, device=v.device)
+    vdt = P_OPERAND_DTYPE[p_operand]
+    v_out = torch.empty((Bk, Sk, heads, vhs), dtype=vdt, device=v.device)
     rc = lib.ff_kv_gather_cast(_ptr(k) if do_k else None, _ptr(v), _ptr(row_index), _ptr(k_out), _ptr(v_out),
-                               Bk * Sk, heads, d, _stream())
+                               _lib.FF_DT_F16 if vdt == torch.float16 else FF_DT_BF16, Bk * Sk, heads, d, _stream())
     _lib.check(rc, "ff_kv_gather_cast")
     _count("ff_kv_gather_cast")
     return (k_out if do_k else k), StagedV(v_out, heads, d)
 
 
-def attn_masked_kv(q, k, v, plan, heads, scale, bitmasks=None, popcount=None, out_dtype=None, out=None):
-    """q [B,Sq,C], k [Bk,Skv,C] bf16, v a StagedV (fast path: one fp16 P operand, see kv_gather_cast) or bf16 [Bk,Skv,C]
-    (hi+lo bf16 P pair); plan: uint8 CUDA tensor holding FFAttnHeadPlan[B*heads] (plans.to_device);
+def attn_masked_kv(q, k, v, plan, heads, scale, bitmasks=None, popcount=None, out_dtype=None, out=None,
+                   p_operand="f16"):
+    """q [B,Sq,C], k [Bk,Skv,C] bf16; v a StagedV (kv_gather_cast) or a bf16 [Bk,Skv,C] tensor, which is staged here
+    according to `p_operand`; plan: uint8 CUDA tensor holding FFAttnHeadPlan[B*heads] (plans.to_device);
     bitmasks int32 [n_masks, words], popcount int32 [n_masks].  Returns [B,Sq,C] in out_dtype (default bf16)."""
     _chk(q, torch.bfloat16, "q", 3)
     _chk(k, torch.bfloat16, "k", 3)
     B, Sq, Cc = q.shape
     Bk, Skv, Ck = k.shape
-    staged = isinstance(v, StagedV)
-    if staged:
-        vt = v.data
-        _chk(vt, torch.float16, "v", 4)
-        if vt.shape[:3] != (Bk, Skv, heads) or v.head_dim * heads != Ck:
-            raise ValueError(f"staged V {tuple(vt.shape)} does not match k{tuple(k.shape)} heads={heads}")
-    else:
-        vt = v
+    if Ck != Cc or Cc % heads:
+        raise ValueError(f"bad shapes q{tuple(q.shape)} k{tuple(k.shape)} heads={heads}")
+    if not isinstance(v, StagedV):
         _chk(v, torch.bfloat16, "v", 3)
         if v.shape != k.shape:
             raise ValueError(f"bad shapes k{tuple(k.shape)} v{tuple(v.shape)}")
-    if Ck != Cc or Cc % heads:
-        raise ValueError(f"bad shapes q{tuple(q.shape)} k{tuple(k.shape)} heads={heads}")
+        v = kv_gather_cast(k, v, heads, None, p_operand=p_operand)[1]
+    vt = v.data
+    _chk(vt, vt.dtype if vt.dtype in (torch.float16, torch.bfloat16) else torch.float16, "v", 4)
+    if tuple(vt.shape[:3]) != (Bk, Skv, heads) or v.head_dim * heads != Ck:
+        raise ValueError(f"staged V {tuple(vt.shape)} does not match k{tuple(k.shape)} heads={heads}")
     _chk(plan, torch.uint8, "plan")
     if plan.numel() != B * heads * _lib.PLAN_BYTES:
         raise ValueError(f"plan holds {plan.numel()} bytes, expected {B * heads * _lib.PLAN_BYTES}")
@@ -291,8 +295,8 @@ def attn_masked_kv(q, k, v, plan, heads, scale, bitmasks=None, popcount=None, ou
     a.s_q, a.s_kv = Sq, Skv
     a.out_dtype = _DT[out_dtype]
     a.scale = float(scale)
-    a.v_dtype = _lib.FF_DT_F16 if staged else FF_DT_BF16
-    a.v_head_stride = vt.shape[3] if staged else 0
+    a.v_dtype = _lib.FF_DT_F16 if vt.dtype == torch.float16 else FF_DT_BF16
+    a.v_head_stride = vt.shape[3]
     prof = PROFILE
     if prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

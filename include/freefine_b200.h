@@ -94,7 +94,7 @@ typedef struct FFAttnHeadPlan {
 typedef struct FFAttnArgs {
   const void* q;              /* bf16 [n_streams, s_q,  heads*head_dim]                                   */
   const void* k;              /* bf16 [n_kv_streams, s_kv, heads*head_dim]                                */
-  const void* v;              /* bf16 [n_kv_streams, s_kv, heads*head_dim], or the fp16 staging of ff_kv_gather_cast */
+  const void* v;              /* v_dtype [n_kv_streams, s_kv, heads, v_head_stride]: the staging of ff_kv_gather_cast */
   void* out;                  /* out_dtype [n_streams, s_q, heads*head_dim]                               */
   const FFAttnHeadPlan* plan; /* DEVICE array [n_streams*heads], index stream*heads+head                  */
   const uint32_t* bitmasks;   /* DEVICE [n_masks, mask_words] bit i of word i/32 <=> token i; may be NULL */
@@ -104,26 +104,25 @@ typedef struct FFAttnArgs {
   int32_t n_masks, mask_words;                      /* mask_words >= ceil(max(s_q,s_kv)/32)               */
   int32_t out_dtype;                                /* FF_DT_BF16 or FF_DT_F32                            */
   float scale;                                      /* softmax scale (head_dim^-0.5)                      */
-  int32_t v_dtype;   /* FF_DT_F16: fast path -- V as staged by ff_kv_gather_cast ([.., heads, v_head_stride] fp16   */
-                     /* with a ones column), P = ONE fp16 tensor-core operand, softmax denominator from the tensor  */
-                     /* core; FF_DT_BF16: V as is, P = hi+lo bf16 operand pair (2x PV tensor work, ~3e-5 error)     */
-  int32_t v_head_stride; /* FF_DT_F16 only: must equal ff_attn_v_head_stride(head_dim)                           */
+  int32_t v_dtype;   /* FF_DT_F16: P = ONE fp16 tensor-core operand (fast path, ~3e-4 max-abs vs fp32);          */
+                     /* FF_DT_BF16: P = hi+lo bf16 operand pair (2x PV tensor work, ~3e-5)                         */
+  int32_t v_head_stride; /* must equal ff_attn_v_head_stride(head_dim)                                            */
 } FFAttnArgs;
 
 int ff_attn_masked_kv(const FFAttnArgs* h_args, void* stream);
 
-/* Channels per head of the fp16 V staging for a given head_dim (48 for 40, 96 for 80, 176 for 160). */
+/* Channels per head of the V staging for a given head_dim (48 for 40, 96 for 80, 176 for 160). */
 int ff_attn_v_head_stride(int32_t head_dim);
 
 /* K/V staging for ff_attn_masked_kv in one pass over HBM: optional row gather (row_index[r] = source token row of
  * output row r, over the flattened [n_kv_streams*s_kv] rows; NULL = identity) of K (bf16 copy; k and k_out may both
- * be NULL to skip it) and V, with V converted bf16 -> fp16 (saturating at +-65504) into the FF_DT_F16 layout
- * v_out_f16 [rows, heads, ff_attn_v_head_stride(head_dim)]: channels [0,head_dim) = V, channel head_dim = 1.0 (its
- * P.V column is the softmax denominator), channels above = 0.
+ * be NULL to skip it) and V, with V (bf16 in) written as v_out_dtype -- FF_DT_F16 (saturating at +-65504) or
+ * FF_DT_BF16 -- into the layout the kernel reads: v_out [rows, heads, ff_attn_v_head_stride(head_dim)], channels
+ * [0,head_dim) = V, channel head_dim = 1.0 (its P.V column is the softmax denominator), channels above = 0.
  * The gather is how the host sorts the keys of a masked stream "source-mask keys first" (FF_PASS_KEY_PREFIX); the
  * reference has no counterpart (it materialises [B*H,S,S] masks instead, attention.py:856-889).               */
-int ff_kv_gather_cast(const void* k, const void* v, const int64_t* row_index, void* k_out, void* v_out_f16,
-                      int64_t rows, int32_t heads, int32_t head_dim, void* stream);
+int ff_kv_gather_cast(const void* k, const void* v, const int64_t* row_index, void* k_out, void* v_out,
+                      int32_t v_out_dtype, int64_t rows, int32_t heads, int32_t head_dim, void* stream);
 
 /* Nearest-neighbour down-sample of n full-resolution uint8 masks [n,H,W] to [h,w] and bit-packing.
  * Replaces process_mask_before_attention (attention.py:841-855) + the flatten that follows: index

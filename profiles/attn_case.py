@@ -28,11 +28,7 @@ for S, d in ((4096, 40), (1024, 80)):
         shifts = torch.arange(32, device=dev, dtype=torch.int32)
         key_bits = ((bits[:, :, None] >> shifts) & 1).reshape(bits.shape[0], -1)[:, :S]
         idx = plans.kv_sort_index(key_bits, [2 * (s // 4) if s % 2 else -1 for s in range(4 * E)])
-    if os.environ.get("FF_P", "f16") == "f16":           # V staged as fp16: single-operand P.V
-        k, v = ops.kv_gather_cast(k, v, heads, idx)
-    elif idx is not None:
-        k = k.view(-1, heads * d).index_select(0, idx).view(4 * E, S, heads * d)
-        v = v.view(-1, heads * d).index_select(0, idx).view(4 * E, S, heads * d)
+    k, v = ops.kv_gather_cast(k, v, heads, idx, p_operand=os.environ.get("FF_P", "f16"))
     flops = plans.algorithmic_flops(plan_np, S, S, d, pop.cpu().numpy())
     out = ops.attn_masked_kv(q, k, v, plan, heads, d ** -0.5, bits, pop)
     torch.cuda.synchronize()

@@ -14,7 +14,7 @@ print("P operand:", P_OP)
 
 def _v(v, heads):
     v = v.to(dev).bfloat16().contiguous()
-    return ops.kv_gather_cast(v, v, heads, None)[1] if P_OP == "f16" else v
+    return ops.kv_gather_cast(v, v, heads, None, p_operand=P_OP)[1]
 
 
 def run(name, B, S, Skv, heads, d, q=None, k=None, v=None):

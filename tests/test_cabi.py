@@ -31,7 +31,7 @@ def test_header_symbols_exported(lib):
 def test_struct_layout():
     assert C.sizeof(_lib.FFAttnPass) == 32
     assert C.sizeof(_lib.FFAttnHeadPlan) == 16 + 4 * 32
-    assert _lib.FFAttnArgs.n_streams.offset == 56 and C.sizeof(_lib.FFAttnArgs) == 96
+    assert _lib.FFAttnArgs.n_streams.offset == 56 and C.sizeof(_lib.FFAttnArgs) == 104
     from freefine_b200 import plans
     assert plans.PLAN_DTYPE.itemsize == C.sizeof(_lib.FFAttnHeadPlan)
     assert plans.PLAN_DTYPE.fields["passes"][1] == _lib.FFAttnHeadPlan.passes.offset

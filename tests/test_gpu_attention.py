@@ -42,12 +42,8 @@ def _run(dev, q, k, v, plan, heads, scale, flat_masks=None, out_dtype=torch.floa
     idx = None
     if sort_streams is not None:
         idx = plans.kv_sort_index(torch.from_numpy(np.stack([np.asarray(m) != 0 for m in flat_masks])), sort_streams)
-    if P_OPERAND == "f16":
-        k, v = ops.kv_gather_cast(k.to(dev).bfloat16().contiguous(), v.to(dev).bfloat16().contiguous(), heads,
-                                  None if idx is None else idx.to(dev))
-    elif idx is not None:
-        k = k.reshape(-1, k.shape[-1])[idx].reshape(k.shape)
-        v = v.reshape(-1, v.shape[-1])[idx].reshape(v.shape)
+    k, v = ops.kv_gather_cast(k.to(dev).bfloat16().contiguous(), v.to(dev).bfloat16().contiguous(), heads,
+                              None if idx is None else idx.to(dev), p_operand=P_OPERAND)
     bm = pc = None
     if flat_masks is not None:
         words = ops.mask_words(S)
@@ -58,9 +54,7 @@ def _run(dev, q, k, v, plan, heads, scale, flat_masks=None, out_dtype=torch.floa
         bm = torch.from_numpy(arr.view(np.int32)).to(dev)
         pc = torch.tensor([int((np.asarray(m) != 0).sum()) for m in flat_masks], dtype=torch.int32, device=dev)
     pl = ops.to_device_bytes(plan, dev)
-    vv = v if isinstance(v, ops.StagedV) else v.to(dev).bfloat16()
-    out = ops.attn_masked_kv(q.to(dev).bfloat16(), k.to(dev).bfloat16(), vv, pl, heads, scale, bm, pc,
-                             out_dtype=out_dtype)
+    out = ops.attn_masked_kv(q.to(dev).bfloat16(), k, v, pl, heads, scale, bm, pc, out_dtype=out_dtype)
     torch.cuda.synchronize()
     return out.float().cpu()
 
@@ -185,7 +179,8 @@ def test_full_size_properties(dev):
     out1 = _run(dev, q, k, v, plan, heads, d ** -0.5, flat, sort_streams=sort)
     out2 = _run(dev, q, k, (2 * v), plan, heads, d ** -0.5, flat, sort_streams=sort)
     out_bits = _run(dev, q, k, v, plans.tca_plan(E, heads, "tca", 0.4, lambda e: 2 * e, lambda e: 2 * e + 1), heads, d ** -0.5, flat)
-    assert float((out_bits - out1).abs().max()) < 1e-4       # bit-vector mode == sorted-key mode
+    # bit-vector mode == sorted-key mode up to the rounding of P (key order differs): fp16 P ~1e-3, hi+lo bf16 ~1e-5
+    assert float((out_bits - out1).abs().max()) < (TOL if P_OPERAND == "f16" else 2e-4)
     assert float((out2 - 2 * out1).abs().max()) < 1e-4
     assert bool(torch.isfinite(out1).all())
     e = 3

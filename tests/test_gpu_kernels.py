@@ -183,3 +183,6 @@ def test_kv_gather_cast_bit_exact(dev):
         assert bool((pad[..., 0] == 1).all()) and bool((pad[..., 1:] == 0).all())
         k2, v2 = ops.kv_gather_cast(k, v, heads, None)
         assert k2 is k and torch.equal(v2.values(), v.float().clamp(-65504, 65504).half())
+        k3, v3 = ops.kv_gather_cast(k, v, heads, idx, p_operand="bf16x2")          # bf16 staging: plain copy + ones column
+        assert v3.data.dtype == torch.bfloat16 and torch.equal(v3.values().view(600, C), v.view(600, C)[idx])
+        assert bool((v3.data[..., d] == 1).all()) and bool((v3.data[..., d + 1:] == 0).all())

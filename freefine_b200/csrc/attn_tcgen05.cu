@@ -34,7 +34,11 @@ constexpr int BN = 64;                  // keys per tile (S is double-buffered i
 constexpr int BOX_COLS = 64;            // channels per TMA box (128 bytes of bf16 = one swizzle-128B row)
 constexpr int TILE_BYTES = BM * 128;    // Q box: 128 rows x 128 B = 16 KiB
 constexpr int KV_BYTES = BN * 128;      // K / V box: 64 rows x 128 B = 8 KiB
-constexpr int NUM_SOFTMAX_WARPS = 8;
+#ifndef FF_SOFTMAX_WG
+#define FF_SOFTMAX_WG 1
+#endif
+constexpr int NH = FF_SOFTMAX_WG;       // softmax warpgroups per CTA: each owns 64/NH key columns of every tile
+constexpr int NUM_SOFTMAX_WARPS = 4 * NH;
 constexpr int NUM_THREADS = 32 * (NUM_SOFTMAX_WARPS + 2);
 // P operand of the PV contraction (template parameter HILO), fixed by the dtype of the staged V -- tcgen05.mma
 // kind::f16 wants A and B in the SAME 16-bit format (an f16 A with a bf16 B raises an illegal-instruction fault):
@@ -101,6 +105,18 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
       : "memory");
   return done;
 }
+// non-blocking probe of a phase (used to hide the ~90-cycle fast-path latency of try_wait behind useful work)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try(bar, parity)) {
@@ -114,17 +130,20 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
 }
-// non-blocking probe of a phase (used to hide the ~90-cycle fast-path latency of try_wait behind useful work)
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(done)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return done != 0;
+// Optional busy-polling wait per role (FF_SPIN_MASK bit 0: softmax warps, bit 1: MMA issuer, bit 2: TMA producer);
+// measured within noise of the hardware-sleep wait once the MMA issuer loop became warp-uniform, so off by default.
+// Bounded: a protocol bug falls through to the loud time-out of mbar_wait_slow.
+#ifndef FF_SPIN_MASK
+#define FF_SPIN_MASK 0
+#endif
+template <int ROLE_BIT>
+__device__ __forceinline__ void mbar_wait_hot(uint32_t bar, uint32_t parity) {
+  if constexpr ((FF_SPIN_MASK >> ROLE_BIT) & 1) {
+    for (uint32_t n = 0; !mbar_test(bar, parity); ++n)
+      if (n > (1u << 24)) { mbar_wait_slow(bar, parity); return; }
+  } else {
+    mbar_wait(bar, parity);
+  }
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
                                             uint32_t bar) {
@@ -150,6 +169,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) {
     case 3: asm volatile("bar.sync 3, %0;" ::"r"(count) : "memory"); break;
     default: asm volatile("bar.sync 4, %0;" ::"r"(count) : "memory"); break;
   }
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -251,9 +275,13 @@ __device__ __forceinline__ void tmem_wait_ld32(float (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float fast_exp2(float x) {
+#ifdef FF_KO_MUFU   // timing experiment only (wrong results): how much of the tile time is the MUFU unit?
+  return x;
+#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 
 // Shared-memory matrix descriptor, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor layout:
@@ -281,6 +309,18 @@ __device__ __forceinline__ void trace(uint32_t* tr, int role, uint32_t it, uint3
     __threadfence_system();
   }
 }
+
+// Timeline probe (build with -DFF_TIMELINE, ff_debug_set_timeline): clock64 stamps of two CTAs, per role and tile.
+#ifdef FF_TIMELINE
+__device__ unsigned long long* g_timeline = nullptr;
+#define FF_TL_TILES 64
+#define FF_TL(role_, tile_, site_)                                                                      \
+  do {                                                                                                  \
+    if (tl && (tile_) < FF_TL_TILES) tl[(((size_t)tl_cta * 2 + (role_)) * FF_TL_TILES + (tile_)) * 8 + (site_)] = clock64(); \
+  } while (0)
+#else
+#define FF_TL(role_, tile_, site_) do { } while (0)
+#endif
 
 struct KParams {
   const FFAttnHeadPlan* plan;
@@ -525,12 +565,18 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   const uint32_t tmem = *tmem_slot_ptr;
 #ifdef FF_ENABLE_TRACE   // build with FF_TRACE=1 (csrc/build.py); off in the product build
   uint32_t* const tr = g_trace;
-  const int trole = warp == NUM_SOFTMAX_WARPS ? 0 : (warp == NUM_SOFTMAX_WARPS + 1 ? 1 : (threadIdx.x == 0 ? 2 : (threadIdx.x == 224 ? 3 : -1)));
+  const int trole = warp == NUM_SOFTMAX_WARPS ? 0 : (warp == NUM_SOFTMAX_WARPS + 1 ? 1 : (threadIdx.x == 0 ? 2 : (threadIdx.x == 32 * NUM_SOFTMAX_WARPS - 32 ? 3 : -1)));
 #define FF_TRACE(it_, site_) do { if (tr && trole >= 0 && (warp < NUM_SOFTMAX_WARPS || lane == 0)) trace(tr, trole, (uint32_t)(it_), (site_)); } while (0)
 #else
 #define FF_TRACE(it_, site_) do { } while (0)
 #endif
   FF_TRACE(0, 1);
+#ifdef FF_TIMELINE
+  const int tl_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  const int tl_cta = tl_lin == 4000 ? 0 : 1;
+  unsigned long long* const tl = ((tl_lin == 4000 || tl_lin == 4101) && lane == 0 &&
+                                  (warp == 0 || warp == NUM_SOFTMAX_WARPS + 1)) ? g_timeline : nullptr;
+#endif
 
   if (warp == NUM_SOFTMAX_WARPS) {
     // ===================================== TMA producer =====================================
@@ -557,10 +603,13 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             for (int j = jb; j < j1; ++j) {
             const int stage = it % C::NSTAGE, use = it / C::NSTAGE;
             FF_TRACE(it, 10);
-            if (use > 0) mbar_wait(bar_kv_empty + 8 * stage, (use - 1) & 1);
+            if (use > 0) mbar_wait_hot<2>(bar_kv_empty + 8 * stage, (use - 1) & 1);
             FF_TRACE(it, 11);
             const uint32_t full = bar_kv_full + 8 * stage;
             const uint32_t sK = sKV + stage * C::SMEM_STAGE, sV = sK + C::NKT * KV_BYTES;
+#ifdef FF_KO_TMA     // timing experiment only (wrong results): no K/V traffic after the ring is primed
+            if (it >= C::NSTAGE) { mbar_arrive(full); ++it; continue; }
+#endif
             mbar_expect_tx(full, 2 * C::NKT * KV_BYTES);
             for (int kt = 0; kt < C::NKT; ++kt) {
               tma_load_4d(sK + kt * KV_BYTES, &tm_k, kt * BOX_COLS, head, j * BN, sg.kv, full);
@@ -574,41 +623,54 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     }
   } else if (warp == NUM_SOFTMAX_WARPS + 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
+    // The WHOLE warp runs this warp-uniform loop, so that descriptors, barrier addresses and counters live in uniform
+    // registers; only the elected lane executes tcgen05.mma / tcgen05.commit.  (Running the loop inside `if (lane == 0)`
+    // made every MMA operand a divergent-context ELECT + R2UR.BROADCAST chain: ~150 serial instructions, ~1500 cycles
+    // per tile -- the bound of the whole kernel, above the MUFU unit.)
+    {
+      const bool leader = elect_one();
       constexpr uint32_t idesc_qk = make_idesc(BN, 0);
       constexpr uint32_t idesc_pv = make_idesc(C::DPV, 1, !P_HILO);
+      // descriptor address fields are (byte address >> 4) in the low 14 bits: offsets are plain additions
+      const uint64_t qdesc0 = smem_desc_sw128(sQ, 16);
+      const uint64_t kdesc0 = smem_desc_sw128(sKV, 16);
+      const uint64_t vdesc0 = smem_desc_sw128(sKV + C::NKT * KV_BYTES, KV_BYTES);
       FF_TRACE(0, 20);
       mbar_wait(bar_q, 0);
       int it = 0;
+      uint32_t stage = 0, kv_phase = 0;
       // PV(t) is issued one tile late: QK(t+1) -> S[(t+1)&1] goes first so that it runs while the softmax warps are
       // still busy with tile t (S is double-buffered); the tensor pipe executes this thread's MMAs in issue order, so
       // QK(t+2), which overwrites the S/P buffer of tile t, is always behind PV(t).
       bool pend = false, pend_first = false;
-      int pend_stage = 0;
-      auto issue_pv = [&](int t, int stage, bool first_of_pass) {
-        const uint32_t sV = sKV + stage * C::SMEM_STAGE + C::NKT * KV_BYTES;
+      uint32_t pend_stage = 0;
+      auto issue_pv = [&](int t, uint32_t st, bool first_of_pass) {
         FF_TRACE(t, 23);
-        mbar_wait(bar_p + 8 * (t & 1), (t >> 1) & 1);
+        mbar_wait_hot<1>(bar_p + 8 * (t & 1), (t >> 1) & 1);
+        FF_TL(1, t, 3);
         FF_TRACE(t, 24);
         tc_fence_after();
-        // O (+)= P_hi V + P_lo V : A = P halves (bf16 in TMEM, 8 columns per 16 keys: K-step ks keeps hi in columns
-        // [16ks,16ks+8) and lo in [16ks+8,16ks+16) of its S buffer), B = V tile, MN-major; 16 keys = 2048 B per
-        // K-step, 64-channel groups KV_BYTES apart (LBO)
+        // O (+)= P V : A = P in TMEM over the S columns of tile t, B = V tile, MN-major; 16 keys = 2048 B per K-step,
+        // 64-channel groups KV_BYTES apart (LBO).  hi/lo bf16: K-step ks keeps hi in columns [16ks,16ks+8) and lo in
+        // [16ks+8,16ks+16); fp16: 8 packed columns at 32*(ks/2) + 8*(ks%2).
+        const uint64_t vd = vdesc0 + ((st * (uint32_t)C::SMEM_STAGE) >> 4);
+        const uint32_t pbase = tmem + C::TMEM_S + BN * (t & 1);
+        if (leader) {
 #pragma unroll
-        for (int ks = 0; ks < BN / 16; ++ks) {
-          const uint64_t vdesc = smem_desc_sw128(sV + ks * 2048, KV_BYTES);
-          if constexpr (P_HILO) {
-            const uint32_t a_hi = tmem + C::TMEM_S + BN * (t & 1) + 16 * ks;
-            mma_ts(tmem + C::TMEM_O, a_hi, vdesc, idesc_pv, (!first_of_pass || ks > 0) ? 1u : 0u);
-            mma_ts(tmem + C::TMEM_O, a_hi + 8, vdesc, idesc_pv, 1u);
-          } else {
-            // single fp16 P: the 16 keys of K-step ks are 8 packed columns inside the S columns of the warpgroup
-            // that owns them: 32*(ks/2) + 8*(ks%2)
-            mma_ts(tmem + C::TMEM_O, tmem + C::TMEM_S + BN * (t & 1) + 32 * (ks >> 1) + 8 * (ks & 1), vdesc, idesc_pv,
-                   (!first_of_pass || ks > 0) ? 1u : 0u);
+          for (int ks = 0; ks < BN / 16; ++ks) {
+            const uint64_t vdesc = vd + ((ks * 2048) >> 4);
+            if constexpr (P_HILO) {
+              mma_ts(tmem + C::TMEM_O, pbase + 16 * ks, vdesc, idesc_pv, (!first_of_pass || ks > 0) ? 1u : 0u);
+              mma_ts(tmem + C::TMEM_O, pbase + 16 * ks + 8, vdesc, idesc_pv, 1u);
+            } else {
+              mma_ts(tmem + C::TMEM_O, pbase + 32 * (ks >> 1) + 8 * (ks & 1), vdesc, idesc_pv,
+                     (!first_of_pass || ks > 0) ? 1u : 0u);
+            }
           }
+          tc_commit(bar_kv_empty + 8 * st);
         }
-        tc_commit(bar_kv_empty + 8 * stage);
+        __syncwarp();
+        FF_TL(1, t, 4);
       };
 #pragma unroll 1
       for (int ip = 0; ip < n_pass; ++ip) {
@@ -627,41 +689,50 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             if (tile_skip(cx, sg, cls, p.s_kv)) continue;
 #pragma unroll 1
             for (int j = jb; j < j1; ++j) {
-            const int stage = it % C::NSTAGE, use = it / C::NSTAGE;
-            const uint32_t sK = sKV + stage * C::SMEM_STAGE;
-            FF_TRACE(it, 21);
-            mbar_wait(bar_kv_full + 8 * stage, use & 1);
-            FF_TRACE(it, 22);
-            tc_fence_after();
-            // S[it&1] = Q K^T
+              FF_TRACE(it, 21);
+              FF_TL(1, it, 0);
+              mbar_wait_hot<1>(bar_kv_full + 8 * stage, kv_phase);
+              FF_TL(1, it, 1);
+              FF_TRACE(it, 22);
+              tc_fence_after();
+              // S[it&1] = Q K^T
+              const uint64_t kd = kdesc0 + ((stage * (uint32_t)C::SMEM_STAGE) >> 4);
+              const uint32_t sbuf = tmem + C::TMEM_S + BN * (it & 1);
+              if (leader) {
 #pragma unroll
-            for (int ks = 0; ks < DPAD / 16; ++ks) {
-              const uint32_t qoff = (ks >> 2) * TILE_BYTES + (ks & 3) * 32;   // 16 channels = 32 B inside the row
-              const uint32_t koff = (ks >> 2) * KV_BYTES + (ks & 3) * 32;
-              mma_ss(tmem + C::TMEM_S + BN * (it & 1), smem_desc_sw128(sQ + qoff, 16), smem_desc_sw128(sK + koff, 16),
-                     idesc_qk, ks > 0);
-            }
-            tc_commit(bar_s + 8 * (it & 1));
-            if (pend) issue_pv(it - 1, pend_stage, pend_first);
-            pend = true;
-            pend_stage = stage;
-            pend_first = first;
-            first = false;
-            ++it;
+                for (int ks = 0; ks < DPAD / 16; ++ks) {
+                  constexpr int dummy = 0; (void)dummy;
+                  const uint32_t qoff = (ks >> 2) * TILE_BYTES + (ks & 3) * 32;   // 16 channels = 32 B inside the row
+                  const uint32_t koff = (ks >> 2) * KV_BYTES + (ks & 3) * 32;
+                  mma_ss(sbuf, qdesc0 + (qoff >> 4), kd + (koff >> 4), idesc_qk, ks > 0);
+                }
+                tc_commit(bar_s + 8 * (it & 1));
+              }
+              __syncwarp();
+              FF_TL(1, it, 2);
+              if (pend) issue_pv(it - 1, pend_stage, pend_first);
+              pend = true;
+              pend_stage = stage;
+              pend_first = first;
+              first = false;
+              ++it;
+              if (++stage == (uint32_t)C::NSTAGE) { stage = 0; kv_phase ^= 1u; }
             }
           }
         }
       }
       // two virtual s_full commits stand in for the QK(n), QK(n+1) that do not exist, so that "s_full(t+1) => PV(t-1)"
       // and "s_full(t+2) => PV(t)" also hold for the last tiles of the CTA
-      tc_commit(bar_s + 8 * (it & 1));
+      if (leader) tc_commit(bar_s + 8 * (it & 1));
+      __syncwarp();
       if (pend) issue_pv(it - 1, pend_stage, pend_first);
-      tc_commit(bar_s + 8 * ((it + 1) & 1));
+      if (leader) tc_commit(bar_s + 8 * ((it + 1) & 1));
+      __syncwarp();
     }
   } else {
     // ===================================== softmax + epilogue ===============================
     const int wq = warp & 3;        // TMEM lane quarter of this warp (hardware rule: warp w reaches lanes 32*(w%4)..+31)
-    const int half = warp >> 2;     // key columns [32*half, 32*half+32) of every tile; O / accumulator chunks of parity half
+    const int half = NH == 2 ? warp >> 2 : 0;   // NH=2: key columns [32*half, +32) of every tile, O chunks of parity half
     const int row = q0 + 32 * wq + lane;
     const uint32_t tlane = tmem + ((uint32_t)(wq * 32) << 16);
     bool acc_started = false;       // has any pass been added to the TMEM accumulator yet (uniform across the CTA)
@@ -694,7 +765,9 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 #pragma unroll 1
           for (int j = jb; j < j1; ++j) {
           FF_TRACE(it, 30);
-          mbar_wait(bar_s + 8 * (it & 1), (it >> 1) & 1);
+          FF_TL(0, it, 0);
+          mbar_wait_hot<0>(bar_s + 8 * (it & 1), (it >> 1) & 1);
+          FF_TL(0, it, 1);
           FF_TRACE(it, 31);
           tc_fence_after();
           const uint32_t tS = tlane + C::TMEM_S + BN * (it & 1);     // this tile's S / P buffer
@@ -723,10 +796,10 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           // ---- row max over the ALLOWED keys of the tile (the fp16 P operand has a narrow exponent range: the
           // reference point must not come from keys this row does not read).  The other warpgroup's half is reduced
           // first and dropped (registers: two CTAs x 320 threads leave 96 per thread), mine stays for the exp sweep.
-          float mt, sm[32];
+          float mt, sm[32], so[32];     // NH=2: so is dead after its max; NH=1: this thread exponentiates both blocks
           {
-            float so[32];
             tmem_ld32(tS + 32 * (half ^ 1), so);
+            if constexpr (NH == 1) tmem_ld32(tS + 32 * half, sm);     // registers allow both loads in flight
             tmem_wait_ld32(so);
             float m0, m1;
             if (cls != TILE_MIX) {
@@ -748,10 +821,11 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             mt = fmaxf(m0, m1);
           }
           {
-            tmem_ld32(tS + 32 * half, sm);
+            if constexpr (NH == 2) tmem_ld32(tS + 32 * half, sm);
             tmem_wait_ld32(sm);
+            FF_TL(0, it, 2);
             // "this warpgroup has read the tile": the other one may now overwrite ITS columns (read above for the max)
-            named_bar_arrive(1 + 2 * (it & 1) + half, 32 * NUM_SOFTMAX_WARPS);
+            if constexpr (NH == 2) named_bar_arrive(1 + 2 * (it & 1) + half, 32 * NUM_SOFTMAX_WARPS);
             float m0, m1;
             if (cls != TILE_MIX) {
               m0 = fmaxf(sm[0], sm[1]);
@@ -771,6 +845,9 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             }
             mt = fmaxf(mt, fmaxf(m0, m1));
             if (cls != TILE_MIX && !row_ok_cls) mt = -INFINITY;
+#ifdef FF_KO_MAX    // timing experiment only
+            mt = 0.f;
+#endif
           }
           const float mts = uniform ? 0.f : mt * p.scale_log2;     // (-inf: the row reads nothing from this tile)
           // ---- running reference point, lazy rescale of O (TMEM read-modify-write only when the max grew a lot).
@@ -784,14 +861,15 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             m_used = mts;
             grow = true;
           }
+          FF_TL(0, it, 3);
           if (__any_sync(0xffffffffu, grow)) {
             FF_TRACE(it, 32);
-            mbar_wait(bar_s + 8 * ((it + 1) & 1), ((it + 1) >> 1) & 1);   // s_full(it+1) => PV(it-1) finished writing O
+            mbar_wait_hot<0>(bar_s + 8 * ((it + 1) & 1), ((it + 1) >> 1) & 1);   // s_full(it+1) => PV(it-1) finished writing O
             FF_TRACE(it, 33);
             tc_fence_after();
 #pragma unroll
             for (int c = 0; c < C::DPV / 16; ++c) {      // (includes the denominator column); chunks split by parity
-              if ((c & 1) != half) continue;
+              if (NH == 2 && (c & 1) != half) continue;
               float o[16];
               uint32_t ob[16];
               tmem_ld16(tlane + C::TMEM_O + 16 * c, o);
@@ -821,17 +899,42 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             }
           }
           // the other warpgroup has read my columns
-          named_bar_sync(1 + 2 * (it & 1) + (half ^ 1), 32 * NUM_SOFTMAX_WARPS);
+          if constexpr (NH == 2) named_bar_sync(1 + 2 * (it & 1) + (half ^ 1), 32 * NUM_SOFTMAX_WARPS);
           if constexpr (P_HILO) {
             tmem_st16(tS + 32 * half, *reinterpret_cast<const uint32_t(*)[16]>(pk));
             tmem_st16(tS + 32 * half + 16, *reinterpret_cast<const uint32_t(*)[16]>(pk + 16));
           } else {
             tmem_st16(tS + 32 * half, *reinterpret_cast<const uint32_t(*)[16]>(pk));
           }
+          if constexpr (NH == 1) {      // one warpgroup: the same thread also owns block 1 (columns [32,64))
+            if (cls != TILE_MIX) {
+#pragma unroll
+              for (int jj = 0; jj < 2; ++jj) {
+                if constexpr (P_HILO) softmax_chunk_hilo<false>(so + 16 * jj, pk + 16 * jj, sc, nb, 0u);
+                else softmax_chunk_f16<false>(so + 16 * jj, pk + 8 * jj, sc, nb, 0u);
+              }
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 2; ++jj) {
+                const uint32_t bits = (kb_other >> (16 * jj)) & 0xffffu;
+                if constexpr (P_HILO) softmax_chunk_hilo<true>(so + 16 * jj, pk + 16 * jj, sc, nb, bits);
+                else softmax_chunk_f16<true>(so + 16 * jj, pk + 8 * jj, sc, nb, bits);
+              }
+            }
+            if constexpr (P_HILO) {
+              tmem_st16(tS + 32, *reinterpret_cast<const uint32_t(*)[16]>(pk));
+              tmem_st16(tS + 48, *reinterpret_cast<const uint32_t(*)[16]>(pk + 16));
+            } else {
+              tmem_st16(tS + 32, *reinterpret_cast<const uint32_t(*)[16]>(pk));
+            }
+          }
+          FF_TL(0, it, 4);
           tmem_wait_st();
+          FF_TL(0, it, 5);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_p + 8 * (it & 1));
+          FF_TL(0, it, 6);
           FF_TRACE(it, 34);
           first = false;
           ++it;
@@ -841,7 +944,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       if (first) continue;     // (defensive) no tile of this pass was processed: nothing to add
       // ---- end of pass: acc += weight * roww / l * O   (l = the ones-column of P.V)
       FF_TRACE(it, 35);
-      mbar_wait(bar_s + 8 * ((it + 1) & 1), ((it + 1) >> 1) & 1);   // s_full(L+2) => PV(L) of this pass's last tile L = it-1
+      mbar_wait_hot<0>(bar_s + 8 * ((it + 1) & 1), ((it + 1) >> 1) & 1);   // s_full(L+2) => PV(L) of this pass's last tile L = it-1
       FF_TRACE(it, 36);
       tc_fence_after();
       const float l = tmem_ld1_wait(tlane + C::TMEM_O + p.head_dim);
@@ -850,7 +953,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       coef = l > 0.f ? coef / l : 0.f;
 #pragma unroll
       for (int c = 0; c < DPAD / 16; ++c) {
-        if ((c & 1) != half) continue;
+        if (NH == 2 && (c & 1) != half) continue;
         float o[16], a[16];
         uint32_t ab[16];
         tmem_ld16(tlane + C::TMEM_O + 16 * c, o);
@@ -878,7 +981,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                            (size_t)head * p.head_dim;
 #pragma unroll
       for (int c = 0; c < DPAD / 16; ++c) {
-        if ((c & 1) != half) continue;
+        if (NH == 2 && (c & 1) != half) continue;
         float o[16];
         if (acc_started) {
           tmem_ld16(tlane + C::TMEM_ACC + 16 * c, o);
@@ -979,6 +1082,18 @@ int launch(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, 
 
 // Debug hook (not part of the product path): device-visible pointer (e.g. cudaHostAlloc'ed, mapped) that receives
 // 8 uint32 per CTA: {producer it, site, mma it, site, softmax-row0 it, site, softmax-row96 it, site}; NULL disables.
+// Debug hook: device buffer of 2 CTAs x 2 roles x 64 tiles x 8 clock64 stamps (library built with -DFF_TIMELINE).
+extern "C" int ff_debug_set_timeline(void* device_ptr) {
+#ifdef FF_TIMELINE
+  cudaError_t e = cudaMemcpyToSymbol(g_timeline, &device_ptr, sizeof(void*));
+  if (e != cudaSuccess) return ff::fail(FF_E_CUDA, "ff_debug_set_timeline: %s", cudaGetErrorString(e));
+  return FF_OK;
+#else
+  (void)device_ptr;
+  return ff::fail(FF_E_UNSUPPORTED, "ff_debug_set_timeline: library built without -DFF_TIMELINE");
+#endif
+}
+
 extern "C" int ff_debug_set_trace(void* device_visible_ptr) {
 #ifndef FF_ENABLE_TRACE
   if (device_visible_ptr) return ff::fail(FF_E_UNSUPPORTED, "ff_debug_set_trace: library built without FF_TRACE=1");

@@ -190,6 +190,8 @@ int ff_cross_region_blend(void* hs, const uint32_t* bitmasks, int32_t mask_words
 /* Debugging aid, not used by the product path: progress trace of ff_attn_masked_kv into a device-visible buffer of
  * 8 uint32 per CTA (see csrc/attn_tcgen05.cu); NULL switches it off.                                              */
 int ff_debug_set_trace(void* device_visible_ptr);
+/* Debugging aid (library built with -DFF_TIMELINE only): per-tile clock64 stamps of two CTAs, 2 x 2 x 64 x 8 uint64. */
+int ff_debug_set_timeline(void* device_ptr);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,7 @@
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_attention.py -q -m gpu > gpurun_out/r48_pytest.txt 2>&1; tail -4 gpurun_out/r48_pytest.txt
+for v in "" _nospin _spin1 _spin2 _poly25 _poly37 _poly50 _koboth; do
+  echo "== variant '$v'" >> gpurun_out/r48_attn_case.txt
+  FREEFINE_B200_LIB=$PWD/freefine_b200/lib/libfreefine_b200$v.so timeout 120 python profiles/attn_case.py 5 >> gpurun_out/r48_attn_case.txt 2>&1
+done
+cat gpurun_out/r48_attn_case.txt

@@ -6,8 +6,8 @@
 // the warped image, the warped mask and the blended result never make a round trip through HBM.
 //
 // Mapping: one CTA produces a 64x16 output tile for a chunk of channels.  The affine image of that tile is a
-// parallelogram; its bounding box in the source is staged in shared memory with 16-byte cp.async copies, double
-// buffered over channel pairs (the copies of channels c+2,c+3 are in flight while c,c+1 are resampled), so each
+// parallelogram; its bounding box in the source is staged in shared memory with 16-byte cp.async copies through a
+// ring of 2-4 channel-pair buffer sets (as many as fit 88 KB: up to 3 later pairs are in flight while one is resampled), so each
 // source texel is read from HBM/L2 once per tile instead of up to 4 times and the 4 bilinear taps are LDS.  The
 // background tile is read and the result written as 128-bit vectors.  If the bounding box does not fit (strong
 // minification) or the layout is not 16-byte friendly, the taps go straight to global memory -- same arithmetic,
@@ -21,9 +21,9 @@ namespace {
 
 constexpr int TILE_X = 64, TILE_Y = 16, PX = 4;           // 4 consecutive output pixels per thread
 constexpr int THREADS = (TILE_X / PX) * TILE_Y;           // 256
-constexpr int STAGE_BYTES = 22 * 1024;                    // staging buffer per channel
 constexpr int CH_PER_ITER = 2;                            // channels per pipeline stage
-constexpr int SMEM_BYTES = 2 * CH_PER_ITER * STAGE_BYTES; // double buffered: 88 KB -> 2 CTAs / SM
+constexpr int SMEM_BYTES = 88 * 1024;                     // staging ring: 88 KB -> 2 CTAs / SM
+constexpr int MAX_SETS = 4;                               // ring depth: as many channel-pair sets as fit (2..4)
 
 template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
@@ -49,32 +49,81 @@ __device__ __forceinline__ Coord src_coord(int x, int y, int dW, int dH, int W, 
   return c;
 }
 
-// Fetch functors: texel (xi, yi) of the current channel, zero outside the image.
-template <typename T> struct GlobalFetch {
-  const T* p; int W, H;
-  __device__ __forceinline__ float operator()(int xi, int yi) const {
-    return (xi >= 0 && xi < W && yi >= 0 && yi < H) ? to_f<T>(__ldg(p + (size_t)yi * W + xi)) : 0.f;
-  }
-};
-template <typename T> struct SmemFetch {
-  const T* s; int bx0, by0, bw, bh;   // staged box (clipped to the image; outside = zero padding)
-  __device__ __forceinline__ float operator()(int xi, int yi) const {
-    const int u = xi - bx0, v = yi - by0;
-    return (u >= 0 && u < bw && v >= 0 && v < bh) ? to_f<T>(s[v * bw + u]) : 0.f;
-  }
+// Taps of one output pixel, computed ONCE per pixel and reused by every channel: offset of the north-west tap inside
+// the fetch domain (the staged box or the whole image, row pitch `pitch`), which of the 4 taps fall inside the domain
+// (outside = the zero padding of grid_sample), and the 4 bilinear weights in ATen's operation order
+// (nw = (x1-ix)*(y1-iy), ne = (ix-x0)*(y1-iy), sw = (x1-ix)*(iy-y0), se = (ix-x0)*(iy-y0)).  mode 1 (nearest): one tap.
+struct Taps {
+  int off;
+  uint32_t valid;   // bit0 nw, bit1 ne, bit2 sw, bit3 se
+  float w[4];
 };
 
-template <typename F> __device__ __forceinline__ float sample(const F& f, Coord c, int mode) {
-  if (mode == 1) return f(__float2int_rn(c.ix), __float2int_rn(c.iy));
+__device__ __forceinline__ Taps make_taps(Coord c, int mode, int dx0, int dy0, int dw, int dh, int pitch) {
+  Taps t;
+  if (mode == 1) {
+    const int u = __float2int_rn(c.ix) - dx0, v = __float2int_rn(c.iy) - dy0;
+    t.off = v * pitch + u;
+    t.valid = (u >= 0 && u < dw && v >= 0 && v < dh) ? 1u : 0u;
+    t.w[0] = 1.f; t.w[1] = t.w[2] = t.w[3] = 0.f;
+    return t;
+  }
   const float x0 = floorf(c.ix), y0 = floorf(c.iy);
   const float x1 = __fadd_rn(x0, 1.f), y1 = __fadd_rn(y0, 1.f);
   const float wx1 = __fsub_rn(x1, c.ix), wx0 = __fsub_rn(c.ix, x0);
   const float wy1 = __fsub_rn(y1, c.iy), wy0 = __fsub_rn(c.iy, y0);
-  const int xi = (int)x0, yi = (int)y0;
-  float o = __fmul_rn(f(xi, yi), __fmul_rn(wx1, wy1));                           // nw
-  o = __fadd_rn(o, __fmul_rn(f(xi + 1, yi), __fmul_rn(wx0, wy1)));               // ne
-  o = __fadd_rn(o, __fmul_rn(f(xi, yi + 1), __fmul_rn(wx1, wy0)));               // sw
-  o = __fadd_rn(o, __fmul_rn(f(xi + 1, yi + 1), __fmul_rn(wx0, wy0)));           // se
+  t.w[0] = __fmul_rn(wx1, wy1);
+  t.w[1] = __fmul_rn(wx0, wy1);
+  t.w[2] = __fmul_rn(wx1, wy0);
+  t.w[3] = __fmul_rn(wx0, wy0);
+  const int u = (int)x0 - dx0, v = (int)y0 - dy0;
+  t.off = v * pitch + u;
+  const bool ux0 = u >= 0 && u < dw, ux1 = u + 1 >= 0 && u + 1 < dw;
+  const bool vy0 = v >= 0 && v < dh, vy1 = v + 1 >= 0 && v + 1 < dh;
+  t.valid = (ux0 && vy0 ? 1u : 0u) | (ux1 && vy0 ? 2u : 0u) | (ux0 && vy1 ? 4u : 0u) | (ux1 && vy1 ? 8u : 0u);
+  return t;
+}
+
+// out = nw*w_nw + ne*w_ne + sw*w_sw + se*w_se, products rounded separately, summed left to right (ATen's order)
+template <typename T, typename P>
+__device__ __forceinline__ float apply_taps(P base, const Taps& t, int pitch, int mode) {
+  const float nw = (t.valid & 1u) ? to_f<T>(base[t.off]) : 0.f;
+  if (mode == 1) return nw;
+  const float ne = (t.valid & 2u) ? to_f<T>(base[t.off + 1]) : 0.f;
+  const float sw = (t.valid & 4u) ? to_f<T>(base[t.off + pitch]) : 0.f;
+  const float se = (t.valid & 8u) ? to_f<T>(base[t.off + pitch + 1]) : 0.f;
+  float o = __fmul_rn(nw, t.w[0]);
+  o = __fadd_rn(o, __fmul_rn(ne, t.w[1]));
+  o = __fadd_rn(o, __fmul_rn(sw, t.w[2]));
+  o = __fadd_rn(o, __fmul_rn(se, t.w[3]));
+  return o;
+}
+
+// Staged form of the taps: one absolute offset per tap inside the channel's staging buffer; taps that fall outside the
+// box point at a zeroed slot behind the box (`zero_off`), so the per-channel work is 4 LDS + 4 FMUL + 3 FADD with no
+// predicates.  Same products, same summation order as apply_taps.
+struct STaps {
+  int o[4];
+  float w[4];
+};
+__device__ __forceinline__ STaps to_staged(const Taps& t, int pitch, int zero_off, int mode) {
+  STaps r;
+  r.o[0] = (t.valid & 1u) ? t.off : zero_off;
+  r.o[1] = (mode == 0 && (t.valid & 2u)) ? t.off + 1 : zero_off;
+  r.o[2] = (mode == 0 && (t.valid & 4u)) ? t.off + pitch : zero_off;
+  r.o[3] = (mode == 0 && (t.valid & 8u)) ? t.off + pitch + 1 : zero_off;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r.w[i] = t.w[i];
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ float apply_staged(const T* s, const STaps& t, int mode) {
+  const float nw = to_f<T>(s[t.o[0]]);
+  if (mode == 1) return nw;
+  float o = __fmul_rn(nw, t.w[0]);
+  o = __fadd_rn(o, __fmul_rn(to_f<T>(s[t.o[1]]), t.w[1]));
+  o = __fadd_rn(o, __fmul_rn(to_f<T>(s[t.o[2]]), t.w[2]));
+  o = __fadd_rn(o, __fmul_rn(to_f<T>(s[t.o[3]]), t.w[3]));
   return o;
 }
 
@@ -96,7 +145,6 @@ warp_affine_blend_kernel(const T* __restrict__ src, const float* __restrict__ th
   extern __shared__ __align__(16) uint8_t stage_raw[];
   __shared__ float th[6];
   constexpr int VEC = 16 / (int)sizeof(T);                 // elements per 16-byte copy
-  constexpr int STAGE_ELEMS = STAGE_BYTES / (int)sizeof(T);
   const int n = blockIdx.z;
   const int tile = blockIdx.x;
   const int tx0 = (tile % tiles_x) * TILE_X, ty0 = (tile / tiles_x) * TILE_Y;
@@ -145,18 +193,54 @@ warp_affine_blend_kernel(const T* __restrict__ src, const float* __restrict__ th
   bw = ((bw + VEC - 1) / VEC) * VEC;
   if (bx0 + bw > W) bw = W - bx0;               // ragged right edge (W % VEC != 0): scalar staging
   const bool empty_box = (bx1 < bx0) || (by1 < by0);
-  const bool staged = !empty_box && (long long)bw * bh <= STAGE_ELEMS;
+  // ring of n_sets buffer sets (one set = CH_PER_ITER boxes); the deeper the ring, the more copies are in flight
+  const int box_elems = ((bw * bh + VEC - 1) / VEC) * VEC;
+  const int stage_elems = box_elems + VEC;                  // + a zeroed slot: the target of out-of-box taps
+  const long long set_bytes = (long long)CH_PER_ITER * stage_elems * (long long)sizeof(T);
+  const int n_sets = empty_box ? 0 : (int)min((long long)MAX_SETS, (long long)SMEM_BYTES / max(set_bytes, 1LL));
+  const bool staged = n_sets >= 2;
   const bool vec_stage = vec_ok && (bw % VEC == 0) && (W % VEC == 0);
 
-  auto stage_ptr = [&](int set, int cc) { return reinterpret_cast<T*>(stage_raw) + (size_t)(set * CH_PER_ITER + cc) * STAGE_ELEMS; };
+  // per-pixel taps in the fetch domain of this CTA: the staged box (row pitch bw) or the whole image (row pitch W)
+  Taps tp[PX];
+  STaps sp4[PX];
+#pragma unroll
+  for (int j = 0; j < PX; ++j) {
+    tp[j] = staged ? make_taps(cd[j], mode, bx0, by0, bw, bh, bw) : make_taps(cd[j], mode, 0, 0, W, H, W);
+    sp4[j] = to_staged(tp[j], bw, box_elems, mode);
+  }
+
+  auto stage_ptr = [&](int set, int cc) { return reinterpret_cast<T*>(stage_raw) + (size_t)(set * CH_PER_ITER + cc) * stage_elems; };
+  // Copy assignments of this thread are the same for every channel: the (row, 16-byte column) -> (source offset,
+  // staging offset) index math is done ONCE here, the per-channel staging loop is then address adds + cp.async only
+  // (the generic div/mod loop it replaces was 20% of all issued instructions).
+  constexpr int KMAX = 4;                                   // covers boxes up to 4*256 vectors (a whole 64x64 fp32 channel)
+  int cp_src[KMAX], cp_dst[KMAX];
+  const int bwv = bw / VEC;
+  const bool fast_stage = staged && vec_stage && bwv * bh <= KMAX * THREADS;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const int i = threadIdx.x + k * THREADS;
+    cp_src[k] = -1;
+    cp_dst[k] = 0;
+    if (fast_stage && i < bwv * bh) {
+      const int v = i / bwv, u = (i - v * bwv) * VEC;
+      cp_src[k] = (by0 + v) * W + bx0 + u;
+      cp_dst[k] = v * bw + u;
+    }
+  }
+  const size_t plane = (size_t)H * W;
   // asynchronous staging of channels [c0, c0+nc) into buffer set `set` (one cp.async group)
   auto issue = [&](int c0, int set) {
     const int nc = min(CH_PER_ITER, c_end - c0);
     for (int cc = 0; cc < nc; ++cc) {
-      const T* p = src + ((size_t)n * C + c0 + cc) * H * W;
+      const T* p = src + ((size_t)n * C + c0 + cc) * plane;
       T* s = stage_ptr(set, cc);
-      if (vec_stage) {
-        const int bwv = bw / VEC;
+      if (fast_stage) {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+          if (cp_src[k] >= 0) cp_async16(s + cp_dst[k], p + cp_src[k]);
+      } else if (vec_stage) {
         for (int i = threadIdx.x; i < bwv * bh; i += THREADS) {
           const int v = i / bwv, u = (i - v * bwv) * VEC;
           cp_async16(s + v * bw + u, p + (size_t)(by0 + v) * W + bx0 + u);
@@ -171,51 +255,65 @@ warp_affine_blend_kernel(const T* __restrict__ src, const float* __restrict__ th
     cp_async_commit();
   };
 
-  if (staged) issue(c_begin, 0);
+  if (staged) {                                             // zero slots (never touched by the copies)
+    for (int i = threadIdx.x; i < n_sets * CH_PER_ITER * VEC; i += THREADS)
+      stage_ptr(0, 0)[(size_t)(i / VEC) * stage_elems + box_elems + (i % VEC)] = from_f<T>(0.f);
+  }
+  // prologue: n_sets-1 channel pairs in flight (empty groups keep the group count uniform at the tail)
+  if (staged)
+    for (int k = 0; k < n_sets - 1; ++k) {
+      if (c_begin + k * CH_PER_ITER < c_end) issue(c_begin + k * CH_PER_ITER, k);
+      else cp_async_commit();
+    }
   int it = 0;
+  using V = typename Vec4<T>::type;
+  const bool vec_io = vec_ok && ox + PX <= dW;
+  const size_t oplane = (size_t)dH * dW;
+  const size_t opix = (size_t)oy * dW + ox;                 // this thread's pixel offset inside an output plane
   for (int c0 = c_begin; c0 < c_end; c0 += CH_PER_ITER, ++it) {
     const int nc = min(CH_PER_ITER, c_end - c0);
-    using V = typename Vec4<T>::type;
-    const bool vec_io = vec_ok && ox + PX <= dW;
+    const size_t obase0 = ((size_t)n * C + c0) * oplane + opix;
     // background vectors first: these loads are in flight while we wait for the staged copies
     T b[CH_PER_ITER][PX];
     if (active && mask_src != nullptr) {
 #pragma unroll
       for (int cc = 0; cc < CH_PER_ITER; ++cc) {
         if (cc < nc) {
-          const size_t obase = (((size_t)n * C + c0 + cc) * dH + oy) * dW + ox;
+          const size_t obase = obase0 + cc * oplane;
           if (vec_io) *reinterpret_cast<V*>(b[cc]) = __ldg(reinterpret_cast<const V*>(bg + obase));
           else
             for (int j = 0; j < PX && ox + j < dW; ++j) b[cc][j] = bg[obase + j];
         }
       }
     }
+    const int cur = staged ? it % n_sets : 0;
     if (staged) {
-      if (c0 + CH_PER_ITER < c_end) {
-        issue(c0 + CH_PER_ITER, (it + 1) & 1);      // prefetch the next channel pair into the other buffer set
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
-      }
-      __syncthreads();                              // copies of set it&1 are visible to every thread
+      // refill the set consumed in the previous iteration with the pair n_sets-1 ahead, then wait for the current one
+      const int ahead = c0 + (n_sets - 1) * CH_PER_ITER;
+      if (ahead < c_end) issue(ahead, (it + n_sets - 1) % n_sets);
+      else cp_async_commit();
+      if (n_sets == 2) cp_async_wait<1>();
+      else if (n_sets == 3) cp_async_wait<2>();
+      else cp_async_wait<3>();
+      __syncthreads();                              // copies of set `cur` are visible to every thread
     }
     if (active) {
 #pragma unroll
       for (int cc = 0; cc < CH_PER_ITER; ++cc) {
         if (cc < nc) {
-          const size_t obase = (((size_t)n * C + c0 + cc) * dH + oy) * dW + ox;
+          const size_t obase = obase0 + cc * oplane;
           float r[PX];
           if (empty_box) {
 #pragma unroll
             for (int j = 0; j < PX; ++j) r[j] = 0.f;
           } else if (staged) {
-            SmemFetch<T> f{stage_ptr(it & 1, cc), bx0, by0, bw, bh};
+            const T* sp = stage_ptr(cur, cc);
 #pragma unroll
-            for (int j = 0; j < PX; ++j) r[j] = sample(f, cd[j], mode);
+            for (int j = 0; j < PX; ++j) r[j] = apply_staged<T>(sp, sp4[j], mode);
           } else {
-            GlobalFetch<T> f{src + ((size_t)n * C + c0 + cc) * H * W, W, H};
+            const T* gp = src + ((size_t)n * C + c0 + cc) * plane;
 #pragma unroll
-            for (int j = 0; j < PX; ++j) r[j] = sample(f, cd[j], mode);
+            for (int j = 0; j < PX; ++j) r[j] = apply_taps<T>(gp, tp[j], W, mode);
           }
           if (vec_io) {
             T o[PX];
@@ -228,7 +326,7 @@ warp_affine_blend_kernel(const T* __restrict__ src, const float* __restrict__ th
         }
       }
     }
-    if (staged) __syncthreads();                    // set it&1 may be refilled by the next iteration's prefetch
+    if (staged) __syncthreads();                    // set `cur` may be refilled by the next iteration's prefetch
   }
 }
 

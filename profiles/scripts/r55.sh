@@ -1,0 +1,2 @@
+mkdir -p gpurun_out
+timeout 300 ncu --set full --import-source on --clock-control none -k regex:warp_affine -c 1 -s 2 -o gpurun_out/r55_warp_full -f python profiles/warp_case.py > gpurun_out/r55_ncu.log 2>&1; tail -2 gpurun_out/r55_ncu.log

@@ -5,23 +5,24 @@
 // style-align / plain variants; see include/freefine_b200.h for the per-(stream,head) plan semantics.
 //
 // One CTA = one 128-row query tile of one (stream, head).  Ten warps:
-//   warps 0-7  softmax + epilogue, two warpgroups on the SAME tile: thread (w, lane) owns query row 32*(w%4)+lane ==
-//              its TMEM lane (tcgen05.ld/st 32x32b) and the key columns [32*(w/4), 32*(w/4)+32) of every 64-key tile.
-//              Four softmax warps per SM sub-partition (two CTAs per SM) keep the MUFU unit, the bound of the d=40
-//              layers, busy while the others wait on barriers / TMEM.
+//   warps 0-7  softmax + epilogue as TWO warpgroups: warpgroup wg owns the 64-key K/V tiles of parity wg -- its own S/P
+//              buffer, its own O accumulator in TMEM, its own running reference point.  Thread (w, lane) owns query row
+//              32*(w%4)+lane == its TMEM lane (tcgen05.ld/st 32x32b).  Four softmax warps per SM sub-partition (two
+//              CTAs per SM) keep the MUFU unit -- the bound of the d=40 layers -- fed while others wait on barriers /
+//              TMEM.  The two partial softmaxes of a pass are merged at its end (one exchange of the reference points
+//              through shared memory), the cross-pass accumulator sum_p w_p*roww_p(q)*O_p/l_p lives in shared memory.
 //   warp  8    TMA producer (one elected lane): Q once, then a ring of K/V tiles (64 keys x 64 channels boxes,
 //              SWIZZLE_128B, channels beyond head_dim zero-filled by the TMA bounds check), + TMEM alloc/dealloc
-//   warp  9    MMA issuer (one elected lane):  S = Q K^T  (SS, M128 N64 K16 x DPAD/16, both operands K-major)
-//                                              O += P V   (TS: P from TMEM, V MN-major from the box)
-// Per K/V tile:  QK^T -> [s_full] -> softmax: every thread loads BOTH halves of its row of S (the row max needs all 64
-// scores; computing it twice is cheaper than exchanging it), exponentiates its own half and writes P over its own S
-// columns once the other warpgroup has read them (named barriers) -> [p_full] -> PV -> [kv_empty].  The running
-// reference point is only refreshed when the row max grows by more than 2^8 / 2^24 (lazy rescale: O stays in TMEM,
-// read-modify-written only then).  V is ALWAYS the staging of ff_kv_gather_cast, whose ones column makes P.V also
-// produce the softmax denominator: no row-sum arithmetic in the softmax warps, numerator and denominator see the same
-// rounded P.  Region masks are bit-vectors; `allowed(q,k)` is evaluated in registers on 32-bit words, nothing
-// [S,S]-shaped exists anywhere.  Every pass of a plan has its own softmax; pass results are combined as
-// sum_p weight_p*roww_p(q)*O_p/l_p in a third TMEM region.
+//   warp  9    MMA issuer (warp-uniform loop, one elected lane issues):
+//                  S_par = Q K^T  (SS, M128 N64 K16 x DPAD/16, both operands K-major)
+//                  O_par += P V   (TS: P from TMEM over the S columns it came from, V MN-major from the box)
+// Per K/V tile t:  QK^T -> [s_full] -> softmax (row max over the allowed keys, 37% of the exp2 on the FMA pipe as a
+// degree-3 polynomial, P packed for the tensor core and written over S) -> [p_full] -> PV(t) and QK(t+2) back to back
+// -> [kv_empty, s_full].  The running reference point is only refreshed when the row max grows by more than 2^8 / 2^24
+// (lazy rescale: O stays in TMEM, read-modify-written only then).  V is ALWAYS the staging of ff_kv_gather_cast, whose
+// ones column makes P.V also produce the softmax denominator: no row-sum arithmetic in the softmax warps, numerator
+// and denominator see the same rounded P.  Region masks are bit-vectors; `allowed(q,k)` is evaluated in registers on
+// 32-bit words, nothing [S,S]-shaped exists anywhere.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -34,11 +35,7 @@ constexpr int BN = 64;                  // keys per tile (S is double-buffered i
 constexpr int BOX_COLS = 64;            // channels per TMA box (128 bytes of bf16 = one swizzle-128B row)
 constexpr int TILE_BYTES = BM * 128;    // Q box: 128 rows x 128 B = 16 KiB
 constexpr int KV_BYTES = BN * 128;      // K / V box: 64 rows x 128 B = 8 KiB
-#ifndef FF_SOFTMAX_WG
-#define FF_SOFTMAX_WG 1
-#endif
-constexpr int NH = FF_SOFTMAX_WG;       // softmax warpgroups per CTA: each owns 64/NH key columns of every tile
-constexpr int NUM_SOFTMAX_WARPS = 4 * NH;
+constexpr int NUM_SOFTMAX_WARPS = 8;    // two warpgroups: warps 0-3 take the even K/V tiles, warps 4-7 the odd ones
 constexpr int NUM_THREADS = 32 * (NUM_SOFTMAX_WARPS + 2);
 // P operand of the PV contraction (template parameter HILO), fixed by the dtype of the staged V -- tcgen05.mma
 // kind::f16 wants A and B in the SAME 16-bit format (an f16 A with a bf16 B raises an illegal-instruction fault):
@@ -50,8 +47,9 @@ constexpr int NUM_THREADS = 32 * (NUM_SOFTMAX_WARPS + 2);
 template <bool HILO> constexpr float rescale_threshold() { return HILO ? 24.f : 8.f; }
 // exp2 of pair i (mod 8) of every 16-score chunk goes to the FMA pipe (degree-3 polynomial) instead of the MUFU unit
 // when bit i of this pattern is set: the softmax of the d=40 layers is bound by the 16 ex2/clk/SM of the MUFU unit.
+// 0x92 = 3 pairs of 8 (37.5%): measured best on the S=4096 d=40 launch (2.49 -> 2.37 ms; 25% and 50% are slower).
 #ifndef FF_POLY_PATTERN
-#define FF_POLY_PATTERN 0x00
+#define FF_POLY_PATTERN 0x92
 #endif
 
 // DPAD: head_dim padded to the K-step of Q K^T (a multiple of 16).  DPV: channels per head of the staged V = columns
@@ -61,21 +59,21 @@ template <int DPAD, bool HILO> struct Cfg {
   static constexpr int DPV = DPAD == 16 ? 16 : (DPAD == 48 ? 48 : DPAD + 16);
   static constexpr int NKT = (DPAD + BOX_COLS - 1) / BOX_COLS;          // 64-channel boxes per operand tile
   static_assert((DPV + BOX_COLS - 1) / BOX_COLS == NKT, "V tile must span as many boxes as the K tile");
-#ifdef FF_DBG_NSTAGE
-  static constexpr int NSTAGE = FF_DBG_NSTAGE;
-#else
-  static constexpr int NSTAGE = DPAD <= 48 ? 4 : (DPAD <= 80 ? 3 : 2);  // K/V ring depth
-#endif
-  static constexpr int TMEM_S = 0, TMEM_O = 2 * BN, TMEM_ACC = 2 * BN + DPV;   // S buffers at columns 0 and BN
-  static constexpr int TMEM_USED = 2 * BN + DPV + DPAD;   // S x2, O, cross-pass accumulator
+  static constexpr int NSTAGE = DPAD <= 48 ? 4 : (DPAD <= 80 ? 3 : 2);  // K/V ring depth (what fits beside the accumulator)
+  static_assert(NSTAGE >= 2, "QK(t+1) is issued before PV(t): tile t+1 must fit beside tile t");
+  // TMEM: S buffer 0 / 1 (= tile parity), then one O accumulator PER PARITY (each warpgroup runs its own online
+  // softmax over its tiles; the two are merged at the end of a pass)
+  static constexpr int TMEM_S = 0, TMEM_O = 2 * BN;                     // O of parity b at TMEM_O + b * DPV
+  static constexpr int TMEM_USED = 2 * BN + 2 * DPV;
   static constexpr int TMEM_COLS = TMEM_USED <= 256 ? 256 : 512;
   static constexpr int SMEM_Q = NKT * TILE_BYTES;
   static constexpr int SMEM_STAGE = 2 * NKT * KV_BYTES;                 // K tiles then V tiles
-#ifdef FF_DBG_ONE_CTA
-  static constexpr int SMEM_BYTES = SMEM_Q + NSTAGE * SMEM_STAGE + 1024 + 256 + 60 * 1024;   // force 1 CTA / SM
-#else
-  static constexpr int SMEM_BYTES = SMEM_Q + NSTAGE * SMEM_STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
-#endif
+  // cross-pass accumulator sum_p w_p*roww_p*O_p/l_p: fp32 [128 rows][ACC_LD] in shared memory (TMEM is full)
+  static constexpr int ACC_LD = DPAD <= 80 ? DPAD + 4 : DPAD;          // (padding against bank conflicts where it fits)
+  static constexpr int SMEM_ACC = BM * ACC_LD * 4;
+  static constexpr int SMEM_MX = 2 * BM * 4;                            // running reference points of the two warpgroups
+  static constexpr int SMEM_BYTES = SMEM_Q + NSTAGE * SMEM_STAGE + SMEM_ACC + SMEM_MX + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static constexpr int MIN_CTAS = (SMEM_BYTES <= 113 * 1024 && TMEM_COLS == 256) ? 2 : 1;
 };
 
@@ -95,6 +93,15 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
   uint32_t done;
+#ifdef FF_TRYWAIT_NOHINT
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+#else
   // the suspend-time hint lets the thread sleep in hardware until the phase completes instead of spinning
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -103,6 +110,7 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
       : "=r"(done)
       : "r"(bar), "r"(parity), "r"(0x989680u)
       : "memory");
+#endif
   return done;
 }
 // non-blocking probe of a phase (used to hide the ~90-cycle fast-path latency of try_wait behind useful work)
@@ -139,8 +147,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 template <int ROLE_BIT>
 __device__ __forceinline__ void mbar_wait_hot(uint32_t bar, uint32_t parity) {
   if constexpr ((FF_SPIN_MASK >> ROLE_BIT) & 1) {
-    for (uint32_t n = 0; !mbar_test(bar, parity); ++n)
+    for (uint32_t n = 0; !mbar_test(bar, parity); ++n) {
+#ifdef FF_SPIN_SLEEP
+      __nanosleep(FF_SPIN_SLEEP);
+#endif
       if (n > (1u << 24)) { mbar_wait_slow(bar, parity); return; }
+    }
   } else {
     mbar_wait(bar, parity);
   }
@@ -519,18 +531,22 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B atoms are 1024-B aligned
   const uint32_t sQ = smem_base;
   const uint32_t sKV = smem_base + C::SMEM_Q;
-  const uint32_t bar_base = sKV + C::NSTAGE * C::SMEM_STAGE;
+  const uint32_t sACC = sKV + C::NSTAGE * C::SMEM_STAGE;                // fp32 [BM][ACC_LD] cross-pass accumulator
+  const uint32_t sMX = sACC + C::SMEM_ACC;                              // fp32 [2][BM] reference points (pass merge)
+  const uint32_t bar_base = sMX + C::SMEM_MX;
   const uint32_t bar_q = bar_base;
-  // [2] each, indexed by tile parity: s_full / p_full per S buffer.  There is deliberately NO "PV done" barrier that
-  // softmax threads wait on only occasionally: an mbarrier wait is exact only if the waiter has observed every earlier
-  // phase (parity aliasing otherwise -- a skipped-phase wait fell through on hardware while PV was still accumulating).
-  // "PV(t) has completed" is instead derived from s_full, which every softmax thread observes phase by phase:
-  // QK(t+2) is issued after PV(t), and a commit arrives only when ALL earlier MMAs of the issuing thread are done, so
-  // s_full of tile t+2 implies PV(t) (and s_full of tile t+1 implies PV(t-1)).
+  // [2] each, indexed by tile parity = S buffer = softmax warpgroup: s_full / p_full.  There is deliberately NO
+  // "PV done" barrier that softmax threads wait on only occasionally: an mbarrier wait is exact only if the waiter has
+  // observed every earlier phase (parity aliasing otherwise -- a skipped-phase wait fell through on hardware while PV
+  // was still accumulating).  "PV(t) has completed" is instead derived from s_full, which the warpgroup of that parity
+  // observes phase by phase: QK(t+2) is issued after PV(t), and a commit arrives only when ALL earlier MMAs of the
+  // issuing thread are done, so s_full of tile t+2 implies PV(t).
   const uint32_t bar_s = bar_base + 16, bar_p = bar_base + 32;
   const uint32_t bar_kv_full = bar_base + 48, bar_kv_empty = bar_base + 48 + 8 * C::NSTAGE;
   const uint32_t tmem_slot = bar_base + 48 + 16 * C::NSTAGE;            // u32 written by tcgen05.alloc
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  float* const acc_smem = reinterpret_cast<float*>(gen_base + (sACC - smem_base));
+  float* const mx_smem = reinterpret_cast<float*>(gen_base + (sMX - smem_base));
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
 
@@ -545,8 +561,8 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     mbar_init(bar_q, 1);
     mbar_init(bar_s, 1);
     mbar_init(bar_s + 8, 1);
-    mbar_init(bar_p, NUM_SOFTMAX_WARPS);        // one elected arrival per softmax warp
-    mbar_init(bar_p + 8, NUM_SOFTMAX_WARPS);
+    mbar_init(bar_p, NUM_SOFTMAX_WARPS / 2);    // one elected arrival per warp of the warpgroup that owns the parity
+    mbar_init(bar_p + 8, NUM_SOFTMAX_WARPS / 2);
     for (int i = 0; i < C::NSTAGE; ++i) {
       mbar_init(bar_kv_full + 8 * i, 1);
       mbar_init(bar_kv_empty + 8 * i, 1);
@@ -627,6 +643,13 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     // registers; only the elected lane executes tcgen05.mma / tcgen05.commit.  (Running the loop inside `if (lane == 0)`
     // made every MMA operand a divergent-context ELECT + R2UR.BROADCAST chain: ~150 serial instructions, ~1500 cycles
     // per tile -- the bound of the whole kernel, above the MUFU unit.)
+    //
+    // The issuer only needs tile COUNTS (which K/V tile sits in which ring stage is the producer's business), so the
+    // pass / run structure is reduced to cumulative tile counts once and the hot loop is flat:
+    //     wait p_full(t)  ->  PV(t), QK(t+2) back to back  ->  commits.
+    // A warpgroup owns ONE S buffer: its next tile t+2 can only start after PV(t) has consumed P(t), so everything that
+    // stands between its p_full arrival and s_full(t+2) is exposed latency; kv_full(t+2) is therefore waited for BEFORE
+    // p_full(t).
     {
       const bool leader = elect_one();
       constexpr uint32_t idesc_qk = make_idesc(BN, 0);
@@ -635,108 +658,128 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       const uint64_t qdesc0 = smem_desc_sw128(sQ, 16);
       const uint64_t kdesc0 = smem_desc_sw128(sKV, 16);
       const uint64_t vdesc0 = smem_desc_sw128(sKV + C::NKT * KV_BYTES, KV_BYTES);
+      // cumulative tile counts per pass (same decisions as the other roles)
+      int pe0 = 0, pe1 = 0, pe2 = 0, n_total = 0;     // tiles up to and including pass 0 / 1 / 2; all passes
+#pragma unroll
+      for (int ip = 0; ip < FF_MAX_PASS; ++ip) {
+        if (ip < n_pass) {
+          const FFAttnPass ps = plan->pass[ip];
+          const PassCtx cx = make_ctx(ps, p, q0);
+          if (cx.active) {
+#pragma unroll 1
+            for (int seg = 0; seg < 2; ++seg) {
+              const SegCtx sg = seg ? cx.s1 : cx.s0;
+              if (sg.kv < 0) continue;
+#pragma unroll 1
+              for (int j0 = 0; j0 < n_kv_tiles;) {
+                const int cls = tile_class(sg, j0, p), j1 = run_end(sg, j0, cls, p), jb = j0;
+                j0 = j1;
+                if (!tile_skip(cx, sg, cls, p.s_kv)) n_total += j1 - jb;
+              }
+            }
+          }
+        }
+        if (ip == 0) pe0 = n_total;
+        if (ip == 1) pe1 = n_total;
+        if (ip == 2) pe2 = n_total;
+      }
       FF_TRACE(0, 20);
       mbar_wait(bar_q, 0);
-      int it = 0;
-      uint32_t stage = 0, kv_phase = 0;
-      // PV(t) is issued one tile late: QK(t+1) -> S[(t+1)&1] goes first so that it runs while the softmax warps are
-      // still busy with tile t (S is double-buffered); the tensor pipe executes this thread's MMAs in issue order, so
-      // QK(t+2), which overwrites the S/P buffer of tile t, is always behind PV(t).
-      bool pend = false, pend_first = false;
-      uint32_t pend_stage = 0;
-      auto issue_pv = [&](int t, uint32_t st, bool first_of_pass) {
-        FF_TRACE(t, 23);
+      int qk_t = 0;                                   // next tile whose S = Q K^T is to be issued
+      uint32_t q_stage = 0, q_phase = 0, p_stage = 0;
+      auto wait_kv = [&]() { mbar_wait_hot<1>(bar_kv_full + 8 * q_stage, q_phase); };
+      auto issue_qk = [&]() {                         // leader only; kv_full(qk_t) has been observed by the warp
+        const uint64_t kd = kdesc0 + ((q_stage * (uint32_t)C::SMEM_STAGE) >> 4);
+        const uint32_t sbuf = tmem + C::TMEM_S + BN * (qk_t & 1);
+#pragma unroll
+        for (int ks = 0; ks < DPAD / 16; ++ks) {
+          const uint32_t qoff = (ks >> 2) * TILE_BYTES + (ks & 3) * 32;   // 16 channels = 32 B inside the row
+          const uint32_t koff = (ks >> 2) * KV_BYTES + (ks & 3) * 32;
+          mma_ss(sbuf, qdesc0 + (qoff >> 4), kd + (koff >> 4), idesc_qk, ks > 0);
+        }
+        tc_commit(bar_s + 8 * (qk_t & 1));
+      };
+      auto advance_qk = [&]() {
+        ++qk_t;
+        if (++q_stage == (uint32_t)C::NSTAGE) { q_stage = 0; q_phase ^= 1u; }
+      };
+      // prologue: S of the first tile of each parity
+#pragma unroll 1
+      for (int k = 0; k < 2 && qk_t < n_total; ++k) {
+        wait_kv();
+        tc_fence_after();
+        if (leader) issue_qk();
+        __syncwarp();
+        advance_qk();
+      }
+#pragma unroll 1
+      for (int t = 0; t < n_total; ++t) {
+        const bool more = qk_t < n_total;
+        // everything that does not depend on P(t) is prepared BEFORE the wait: between the arrival of p_full(t) and
+        // s_full(t+2) the owning warpgroup idles.
+        // O_par (+)= P V : A = P in TMEM over the S columns of tile t, B = V tile, MN-major; 16 keys = 2048 B per K-step,
+        // 64-channel groups KV_BYTES apart (LBO).  hi/lo bf16: K-step ks keeps hi in columns [16ks,16ks+8) and lo in
+        // [16ks+8,16ks+16); fp16: 8 packed columns at 32*(ks/2) + 8*(ks%2).  The first tile of each parity in a pass
+        // starts its accumulator.
+        const int pstart = t >= pe2 ? pe2 : (t >= pe1 ? pe1 : (t >= pe0 ? pe0 : 0));
+        const bool first_of_parity = t - pstart < 2;
+        const uint64_t vd = vdesc0 + ((p_stage * (uint32_t)C::SMEM_STAGE) >> 4);
+        const uint32_t pbase = tmem + C::TMEM_S + BN * (t & 1);
+        const uint32_t obuf = tmem + C::TMEM_O + C::DPV * (t & 1);
+        // is the K/V tile of QK(t+2) already there?  (normally yes: the ring runs ahead; never with a two-stage ring,
+        // where tile t+2 reuses the stage PV(t) is about to release).  Warp-uniform answer.
+        bool kv_ready = more && __all_sync(0xffffffffu, mbar_test(bar_kv_full + 8 * q_stage, q_phase));
+        FF_TL(1, t, 0);
         mbar_wait_hot<1>(bar_p + 8 * (t & 1), (t >> 1) & 1);
         FF_TL(1, t, 3);
-        FF_TRACE(t, 24);
+        if (more && !kv_ready) kv_ready = __all_sync(0xffffffffu, mbar_test(bar_kv_full + 8 * q_stage, q_phase));
         tc_fence_after();
-        // O (+)= P V : A = P in TMEM over the S columns of tile t, B = V tile, MN-major; 16 keys = 2048 B per K-step,
-        // 64-channel groups KV_BYTES apart (LBO).  hi/lo bf16: K-step ks keeps hi in columns [16ks,16ks+8) and lo in
-        // [16ks+8,16ks+16); fp16: 8 packed columns at 32*(ks/2) + 8*(ks%2).
-        const uint64_t vd = vdesc0 + ((st * (uint32_t)C::SMEM_STAGE) >> 4);
-        const uint32_t pbase = tmem + C::TMEM_S + BN * (t & 1);
         if (leader) {
 #pragma unroll
           for (int ks = 0; ks < BN / 16; ++ks) {
             const uint64_t vdesc = vd + ((ks * 2048) >> 4);
             if constexpr (P_HILO) {
-              mma_ts(tmem + C::TMEM_O, pbase + 16 * ks, vdesc, idesc_pv, (!first_of_pass || ks > 0) ? 1u : 0u);
-              mma_ts(tmem + C::TMEM_O, pbase + 16 * ks + 8, vdesc, idesc_pv, 1u);
+              mma_ts(obuf, pbase + 16 * ks, vdesc, idesc_pv, (!first_of_parity || ks > 0) ? 1u : 0u);
+              mma_ts(obuf, pbase + 16 * ks + 8, vdesc, idesc_pv, 1u);
             } else {
-              mma_ts(tmem + C::TMEM_O, pbase + 32 * (ks >> 1) + 8 * (ks & 1), vdesc, idesc_pv,
-                     (!first_of_pass || ks > 0) ? 1u : 0u);
+              mma_ts(obuf, pbase + 32 * (ks >> 1) + 8 * (ks & 1), vdesc, idesc_pv,
+                     (!first_of_parity || ks > 0) ? 1u : 0u);
             }
           }
-          tc_commit(bar_kv_empty + 8 * st);
+          tc_commit(bar_kv_empty + 8 * p_stage);
+          // S of the same warpgroup's next tile right behind PV(t) in the pipe -- or, for the last tile of a parity, a
+          // virtual s_full commit in its place, so that "s_full(t+2) => PV(t) has completed" holds there too
+          if (kv_ready) issue_qk();
+          else if (!more) tc_commit(bar_s + 8 * (t & 1));
         }
         __syncwarp();
-        FF_TL(1, t, 4);
-      };
-#pragma unroll 1
-      for (int ip = 0; ip < n_pass; ++ip) {
-        const FFAttnPass ps = plan->pass[ip];
-        const PassCtx cx = make_ctx(ps, p, q0);
-        if (!cx.active) continue;
-        bool first = true;
-#pragma unroll 1
-        for (int seg = 0; seg < 2; ++seg) {
-          const SegCtx sg = seg ? cx.s1 : cx.s0;
-          if (sg.kv < 0) continue;
-#pragma unroll 1
-          for (int j0 = 0; j0 < n_kv_tiles;) {
-            const int cls = tile_class(sg, j0, p), j1 = run_end(sg, j0, cls, p), jb = j0;
-            j0 = j1;
-            if (tile_skip(cx, sg, cls, p.s_kv)) continue;
-#pragma unroll 1
-            for (int j = jb; j < j1; ++j) {
-              FF_TRACE(it, 21);
-              FF_TL(1, it, 0);
-              mbar_wait_hot<1>(bar_kv_full + 8 * stage, kv_phase);
-              FF_TL(1, it, 1);
-              FF_TRACE(it, 22);
-              tc_fence_after();
-              // S[it&1] = Q K^T
-              const uint64_t kd = kdesc0 + ((stage * (uint32_t)C::SMEM_STAGE) >> 4);
-              const uint32_t sbuf = tmem + C::TMEM_S + BN * (it & 1);
-              if (leader) {
-#pragma unroll
-                for (int ks = 0; ks < DPAD / 16; ++ks) {
-                  constexpr int dummy = 0; (void)dummy;
-                  const uint32_t qoff = (ks >> 2) * TILE_BYTES + (ks & 3) * 32;   // 16 channels = 32 B inside the row
-                  const uint32_t koff = (ks >> 2) * KV_BYTES + (ks & 3) * 32;
-                  mma_ss(sbuf, qdesc0 + (qoff >> 4), kd + (koff >> 4), idesc_qk, ks > 0);
-                }
-                tc_commit(bar_s + 8 * (it & 1));
-              }
-              __syncwarp();
-              FF_TL(1, it, 2);
-              if (pend) issue_pv(it - 1, pend_stage, pend_first);
-              pend = true;
-              pend_stage = stage;
-              pend_first = first;
-              first = false;
-              ++it;
-              if (++stage == (uint32_t)C::NSTAGE) { stage = 0; kv_phase ^= 1u; }
-            }
-          }
+        if (more && !kv_ready) {
+          wait_kv();
+          tc_fence_after();
+          if (leader) issue_qk();
+          __syncwarp();
         }
+        if (more) advance_qk();
+        FF_TL(1, t, 4);
+        if (++p_stage == (uint32_t)C::NSTAGE) p_stage = 0;
       }
-      // two virtual s_full commits stand in for the QK(n), QK(n+1) that do not exist, so that "s_full(t+1) => PV(t-1)"
-      // and "s_full(t+2) => PV(t)" also hold for the last tiles of the CTA
-      if (leader) tc_commit(bar_s + 8 * (it & 1));
-      __syncwarp();
-      if (pend) issue_pv(it - 1, pend_stage, pend_first);
-      if (leader) tc_commit(bar_s + 8 * ((it + 1) & 1));
       __syncwarp();
     }
   } else {
     // ===================================== softmax + epilogue ===============================
+    // Warpgroup wg (warps 4*wg .. 4*wg+3) owns the K/V tiles of parity wg: S buffer wg, accumulator O_wg, its own running
+    // reference point.  A thread = one query row (TMEM lane).  The two partial softmaxes are merged at the end of a pass.
     const int wq = warp & 3;        // TMEM lane quarter of this warp (hardware rule: warp w reaches lanes 32*(w%4)..+31)
-    const int half = NH == 2 ? warp >> 2 : 0;   // NH=2: key columns [32*half, +32) of every tile, O chunks of parity half
-    const int row = q0 + 32 * wq + lane;
+    const int wg = warp >> 2;       // tile parity of this warpgroup
+    const int rloc = 32 * wq + lane;
+    const int row = q0 + rloc;
     const uint32_t tlane = tmem + ((uint32_t)(wq * 32) << 16);
-    bool acc_started = false;       // has any pass been added to the TMEM accumulator yet (uniform across the CTA)
-    int it = 0;
+    const uint32_t tS = tlane + C::TMEM_S + BN * wg;                  // my S / P buffer
+    const uint32_t tO = tlane + C::TMEM_O + C::DPV * wg;              // my O accumulator
+    const uint32_t tOx = tlane + C::TMEM_O + C::DPV * (wg ^ 1);       // the other warpgroup's
+    float* const acc_row = acc_smem + (size_t)rloc * C::ACC_LD;
+    bool acc_started = false;       // has any pass been added to the accumulator yet (uniform across the CTA)
+    int it = 0;                     // global tile counter (all roles count alike)
 #pragma unroll 1
     for (int ip = 0; ip < n_pass; ++ip) {
       const FFAttnPass ps = plan->pass[ip];
@@ -747,8 +790,9 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       if (ps.row_mask >= 0 && row < p.s_q)
         rb = (__ldg(p.bitmasks + (size_t)ps.row_mask * p.mask_words + (row >> 5)) >> (row & 31)) & 1u;
       const bool rowflip = cx.rowxor && rb;
-      float m_used = 0.f;
-      bool first = true;
+      float m_used = -INFINITY;     // reference point of MY tiles (log2 units); -inf: nothing read so far
+      int n_mine = 0, last_mine = 0;
+      const int it_pass0 = it;
 #pragma unroll 1
       for (int seg = 0; seg < 2; ++seg) {
         const SegCtx sg = seg ? cx.s1 : cx.s0;
@@ -762,234 +806,233 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
           j0 = j1;
           if (tile_skip(cx, sg, cls, p.s_kv)) continue;
           const bool row_ok_cls = row_allowed(cls, flip, uniform);   // per-row predicate of this whole run
+          // my tiles of the run: those with global index parity wg
+          int j = jb + (((it ^ wg) & 1) ? 1 : 0);
+          int itj = it + (j - jb);
+          it += j1 - jb;
 #pragma unroll 1
-          for (int j = jb; j < j1; ++j) {
-          FF_TRACE(it, 30);
-          FF_TL(0, it, 0);
-          mbar_wait_hot<0>(bar_s + 8 * (it & 1), (it >> 1) & 1);
-          FF_TL(0, it, 1);
-          FF_TRACE(it, 31);
-          tc_fence_after();
-          const uint32_t tS = tlane + C::TMEM_S + BN * (it & 1);     // this tile's S / P buffer
-          // ---- allowed-key bits of this row for MIX tiles (boundary / ragged): bit i <=> key j*BN + i
-          uint32_t kb_lo = 0xffffffffu, kb_hi = 0xffffffffu;         // columns [0,32) / [32,64)
-          if (cls == TILE_MIX) {
-#pragma unroll
-            for (int w = 0; w < 2; ++w) {
-              const int kbase = j * BN + 32 * w;
-              const int rem = p.s_kv - kbase;
-              const uint32_t valid = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
-              uint32_t kb = 0xffffffffu;
-              if (sg.kmask >= 0 && !uniform && rem > 0) {
-                if (sg.prefix) {
-                  const int t = sg.T - kbase;
-                  kb = t >= 32 ? 0xffffffffu : (t <= 0 ? 0u : ((1u << t) - 1u));
-                } else {
-                  kb = __ldg(p.bitmasks + (size_t)sg.kmask * p.mask_words + (kbase >> 5));   // BN % 32 == 0
-                }
-                if (flip) kb = ~kb;
-              }
-              if (w == 0) kb_lo = kb & valid; else kb_hi = kb & valid;
-            }
-          }
-          const uint32_t kb_mine = half ? kb_hi : kb_lo, kb_other = half ? kb_lo : kb_hi;
-          // ---- row max over the ALLOWED keys of the tile (the fp16 P operand has a narrow exponent range: the
-          // reference point must not come from keys this row does not read).  The other warpgroup's half is reduced
-          // first and dropped (registers: two CTAs x 320 threads leave 96 per thread), mine stays for the exp sweep.
-          float mt, sm[32], so[32];     // NH=2: so is dead after its max; NH=1: this thread exponentiates both blocks
-          {
-            tmem_ld32(tS + 32 * (half ^ 1), so);
-            if constexpr (NH == 1) tmem_ld32(tS + 32 * half, sm);     // registers allow both loads in flight
-            tmem_wait_ld32(so);
-            float m0, m1;
-            if (cls != TILE_MIX) {
-              m0 = fmaxf(so[0], so[1]);
-              m1 = fmaxf(so[2], so[3]);
-#pragma unroll
-              for (int i = 4; i < 32; i += 4) {
-                m0 = fmaxf(m0, fmaxf(so[i], so[i + 1]));
-                m1 = fmaxf(m1, fmaxf(so[i + 2], so[i + 3]));
-              }
-            } else {
-              m0 = m1 = -INFINITY;
-#pragma unroll
-              for (int i = 0; i < 32; i += 2) {
-                m0 = fmaxf(m0, (kb_other >> i) & 1u ? so[i] : -INFINITY);
-                m1 = fmaxf(m1, (kb_other >> (i + 1)) & 1u ? so[i + 1] : -INFINITY);
-              }
-            }
-            mt = fmaxf(m0, m1);
-          }
-          {
-            if constexpr (NH == 2) tmem_ld32(tS + 32 * half, sm);
-            tmem_wait_ld32(sm);
-            FF_TL(0, it, 2);
-            // "this warpgroup has read the tile": the other one may now overwrite ITS columns (read above for the max)
-            if constexpr (NH == 2) named_bar_arrive(1 + 2 * (it & 1) + half, 32 * NUM_SOFTMAX_WARPS);
-            float m0, m1;
-            if (cls != TILE_MIX) {
-              m0 = fmaxf(sm[0], sm[1]);
-              m1 = fmaxf(sm[2], sm[3]);
-#pragma unroll
-              for (int i = 4; i < 32; i += 4) {
-                m0 = fmaxf(m0, fmaxf(sm[i], sm[i + 1]));
-                m1 = fmaxf(m1, fmaxf(sm[i + 2], sm[i + 3]));
-              }
-            } else {
-              m0 = m1 = -INFINITY;
-#pragma unroll
-              for (int i = 0; i < 32; i += 2) {
-                m0 = fmaxf(m0, (kb_mine >> i) & 1u ? sm[i] : -INFINITY);
-                m1 = fmaxf(m1, (kb_mine >> (i + 1)) & 1u ? sm[i + 1] : -INFINITY);
-              }
-            }
-            mt = fmaxf(mt, fmaxf(m0, m1));
-            if (cls != TILE_MIX && !row_ok_cls) mt = -INFINITY;
-#ifdef FF_KO_MAX    // timing experiment only
-            mt = 0.f;
-#endif
-          }
-          const float mts = uniform ? 0.f : mt * p.scale_log2;     // (-inf: the row reads nothing from this tile)
-          // ---- running reference point, lazy rescale of O (TMEM read-modify-write only when the max grew a lot).
-          // Both threads of a row take identical decisions (same data, same arithmetic).
-          float alpha = 1.f;
-          bool grow = false;
-          if (first) {
-            m_used = mts;
-          } else if (mts > m_used + rescale_threshold<P_HILO>()) {
-            alpha = fast_exp2(m_used - mts);       // (m_used = -inf, nothing read so far: alpha = 0, O is 0 anyway)
-            m_used = mts;
-            grow = true;
-          }
-          FF_TL(0, it, 3);
-          if (__any_sync(0xffffffffu, grow)) {
-            FF_TRACE(it, 32);
-            mbar_wait_hot<0>(bar_s + 8 * ((it + 1) & 1), ((it + 1) >> 1) & 1);   // s_full(it+1) => PV(it-1) finished writing O
-            FF_TRACE(it, 33);
+          for (; j < j1; j += 2, itj += 2) {
+            FF_TRACE(itj, 30);
+            FF_TL(0, itj, 0);
+            mbar_wait_hot<0>(bar_s + 8 * wg, (itj >> 1) & 1);        // also: PV(itj-2) has finished writing O_wg
+            FF_TL(0, itj, 1);
+            FF_TRACE(itj, 31);
             tc_fence_after();
+            // ---- allowed-key bits of this row for MIX tiles (boundary / ragged): bit i <=> key j*BN + i
+            uint32_t kb_lo = 0xffffffffu, kb_hi = 0xffffffffu;         // columns [0,32) / [32,64)
+            if (cls == TILE_MIX) {
 #pragma unroll
-            for (int c = 0; c < C::DPV / 16; ++c) {      // (includes the denominator column); chunks split by parity
-              if (NH == 2 && (c & 1) != half) continue;
-              float o[16];
-              uint32_t ob[16];
-              tmem_ld16(tlane + C::TMEM_O + 16 * c, o);
-              tmem_wait_ld16(o);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) ob[i] = __float_as_uint(o[i] * alpha);
-              tmem_st16(tlane + C::TMEM_O + 16 * c, ob);
-            }
-          }
-          // ---- p = 2^(s*scale*log2e - m) for my 32 keys, packed for the tensor core over my own S columns
-          // [32*half, 32*half+32):  fp16: K-step ks=2*half+jj -> packed columns 32*half + 8*jj + [0,8);
-          // hi/lo bf16: K-step ks -> hi at 16*ks + [0,8), lo at 16*ks + [8,16).
-          const float nb = (cls == TILE_MIX || row_ok_cls) ? -m_used : -INFINITY;   // -inf: p = 0 for the whole row
-          uint32_t pk[P_HILO ? 32 : 16];
-          if (cls != TILE_MIX) {
-#pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
-              if constexpr (P_HILO) softmax_chunk_hilo<false>(sm + 16 * jj, pk + 16 * jj, sc, nb, 0u);
-              else softmax_chunk_f16<false>(sm + 16 * jj, pk + 8 * jj, sc, nb, 0u);
-            }
-          } else {
-#pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
-              const uint32_t bits = (kb_mine >> (16 * jj)) & 0xffffu;
-              if constexpr (P_HILO) softmax_chunk_hilo<true>(sm + 16 * jj, pk + 16 * jj, sc, nb, bits);
-              else softmax_chunk_f16<true>(sm + 16 * jj, pk + 8 * jj, sc, nb, bits);
-            }
-          }
-          // the other warpgroup has read my columns
-          if constexpr (NH == 2) named_bar_sync(1 + 2 * (it & 1) + (half ^ 1), 32 * NUM_SOFTMAX_WARPS);
-          if constexpr (P_HILO) {
-            tmem_st16(tS + 32 * half, *reinterpret_cast<const uint32_t(*)[16]>(pk));
-            tmem_st16(tS + 32 * half + 16, *reinterpret_cast<const uint32_t(*)[16]>(pk + 16));
-          } else {
-            tmem_st16(tS + 32 * half, *reinterpret_cast<const uint32_t(*)[16]>(pk));
-          }
-          if constexpr (NH == 1) {      // one warpgroup: the same thread also owns block 1 (columns [32,64))
-            if (cls != TILE_MIX) {
-#pragma unroll
-              for (int jj = 0; jj < 2; ++jj) {
-                if constexpr (P_HILO) softmax_chunk_hilo<false>(so + 16 * jj, pk + 16 * jj, sc, nb, 0u);
-                else softmax_chunk_f16<false>(so + 16 * jj, pk + 8 * jj, sc, nb, 0u);
-              }
-            } else {
-#pragma unroll
-              for (int jj = 0; jj < 2; ++jj) {
-                const uint32_t bits = (kb_other >> (16 * jj)) & 0xffffu;
-                if constexpr (P_HILO) softmax_chunk_hilo<true>(so + 16 * jj, pk + 16 * jj, sc, nb, bits);
-                else softmax_chunk_f16<true>(so + 16 * jj, pk + 8 * jj, sc, nb, bits);
+              for (int w = 0; w < 2; ++w) {
+                const int kbase = j * BN + 32 * w;
+                const int rem = p.s_kv - kbase;
+                const uint32_t valid = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+                uint32_t kb = 0xffffffffu;
+                if (sg.kmask >= 0 && !uniform && rem > 0) {
+                  if (sg.prefix) {
+                    const int t = sg.T - kbase;
+                    kb = t >= 32 ? 0xffffffffu : (t <= 0 ? 0u : ((1u << t) - 1u));
+                  } else {
+                    kb = __ldg(p.bitmasks + (size_t)sg.kmask * p.mask_words + (kbase >> 5));   // BN % 32 == 0
+                  }
+                  if (flip) kb = ~kb;
+                }
+                if (w == 0) kb_lo = kb & valid; else kb_hi = kb & valid;
               }
             }
-            if constexpr (P_HILO) {
-              tmem_st16(tS + 32, *reinterpret_cast<const uint32_t(*)[16]>(pk));
-              tmem_st16(tS + 48, *reinterpret_cast<const uint32_t(*)[16]>(pk + 16));
-            } else {
-              tmem_st16(tS + 32, *reinterpret_cast<const uint32_t(*)[16]>(pk));
+            // ---- row max over the ALLOWED keys of the tile (the fp16 P operand has a narrow exponent range: the
+            // reference point must not come from keys this row does not read).  Columns [0,32) are reduced first and
+            // dropped (two CTAs x 320 threads leave ~100 registers per thread), then re-read for the exp sweep.
+            float mt, sb[32];
+            {
+              float sa[32];
+              tmem_ld32(tS, sa);
+              tmem_wait_ld32(sa);
+              float m0, m1;
+              if (cls != TILE_MIX) {
+                m0 = fmaxf(sa[0], sa[1]);
+                m1 = fmaxf(sa[2], sa[3]);
+#pragma unroll
+                for (int i = 4; i < 32; i += 4) {
+                  m0 = fmaxf(m0, fmaxf(sa[i], sa[i + 1]));
+                  m1 = fmaxf(m1, fmaxf(sa[i + 2], sa[i + 3]));
+                }
+              } else {
+                m0 = m1 = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                  m0 = fmaxf(m0, (kb_lo >> i) & 1u ? sa[i] : -INFINITY);
+                  m1 = fmaxf(m1, (kb_lo >> (i + 1)) & 1u ? sa[i + 1] : -INFINITY);
+                }
+              }
+              mt = fmaxf(m0, m1);
             }
-          }
-          FF_TL(0, it, 4);
-          tmem_wait_st();
-          FF_TL(0, it, 5);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_p + 8 * (it & 1));
-          FF_TL(0, it, 6);
-          FF_TRACE(it, 34);
-          first = false;
-          ++it;
+            {
+              tmem_ld32(tS + 32, sb);
+              tmem_wait_ld32(sb);
+              float m0, m1;
+              if (cls != TILE_MIX) {
+                m0 = fmaxf(sb[0], sb[1]);
+                m1 = fmaxf(sb[2], sb[3]);
+#pragma unroll
+                for (int i = 4; i < 32; i += 4) {
+                  m0 = fmaxf(m0, fmaxf(sb[i], sb[i + 1]));
+                  m1 = fmaxf(m1, fmaxf(sb[i + 2], sb[i + 3]));
+                }
+              } else {
+                m0 = m1 = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                  m0 = fmaxf(m0, (kb_hi >> i) & 1u ? sb[i] : -INFINITY);
+                  m1 = fmaxf(m1, (kb_hi >> (i + 1)) & 1u ? sb[i + 1] : -INFINITY);
+                }
+              }
+              mt = fmaxf(mt, fmaxf(m0, m1));
+              if (cls != TILE_MIX && !row_ok_cls) mt = -INFINITY;
+#ifdef FF_KO_MAX    // timing experiment only
+              mt = 0.f;
+#endif
+            }
+            FF_TL(0, itj, 2);
+            const float mts = uniform ? 0.f : mt * p.scale_log2;     // (-inf: the row reads nothing from this tile)
+            // ---- running reference point, lazy rescale of O_wg (TMEM read-modify-write only when the max grew a lot)
+            float alpha = 1.f;
+            bool grow = false;
+            if (n_mine == 0) {
+              m_used = mts;
+            } else if (mts > m_used + rescale_threshold<P_HILO>()) {
+              alpha = fast_exp2(m_used - mts);       // (m_used = -inf, nothing read so far: alpha = 0, O is 0 anyway)
+              m_used = mts;
+              grow = true;
+            }
+            if (__any_sync(0xffffffffu, grow)) {
+#pragma unroll
+              for (int c = 0; c < C::DPV / 16; ++c) {      // (includes the denominator column)
+                float o[16];
+                uint32_t ob[16];
+                tmem_ld16(tO + 16 * c, o);
+                tmem_wait_ld16(o);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) ob[i] = __float_as_uint(o[i] * alpha);
+                tmem_st16(tO + 16 * c, ob);
+              }
+            }
+            FF_TL(0, itj, 3);
+            // ---- p = 2^(s*scale*log2e - m), packed for the tensor core over the S columns of the same keys:
+            // fp16: K-step ks -> packed columns 32*(ks/2) + 8*(ks%2) + [0,8); hi/lo bf16: hi at 16*ks + [0,8), lo at
+            // 16*ks + [8,16).  Columns [32,64) first (still in registers), then [0,32) re-read.
+            const float nb = (cls == TILE_MIX || row_ok_cls) ? -m_used : -INFINITY;   // -inf: p = 0 for the whole row
+            uint32_t pk[P_HILO ? 32 : 16];
+#pragma unroll
+            for (int hb = 1; hb >= 0; --hb) {
+              float sa[32];
+              if (hb == 0) {
+                tmem_ld32(tS, sa);
+                tmem_wait_ld32(sa);
+              }
+              const float* sv = hb ? sb : sa;
+              const uint32_t kbits = hb ? kb_hi : kb_lo;
+              if (cls != TILE_MIX) {
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                  if constexpr (P_HILO) softmax_chunk_hilo<false>(sv + 16 * jj, pk + 16 * jj, sc, nb, 0u);
+                  else softmax_chunk_f16<false>(sv + 16 * jj, pk + 8 * jj, sc, nb, 0u);
+                }
+              } else {
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                  const uint32_t bits = (kbits >> (16 * jj)) & 0xffffu;
+                  if constexpr (P_HILO) softmax_chunk_hilo<true>(sv + 16 * jj, pk + 16 * jj, sc, nb, bits);
+                  else softmax_chunk_f16<true>(sv + 16 * jj, pk + 8 * jj, sc, nb, bits);
+                }
+              }
+              if constexpr (P_HILO) {
+                tmem_st16(tS + 32 * hb, *reinterpret_cast<const uint32_t(*)[16]>(pk));
+                tmem_st16(tS + 32 * hb + 16, *reinterpret_cast<const uint32_t(*)[16]>(pk + 16));
+              } else {
+                tmem_st16(tS + 32 * hb, *reinterpret_cast<const uint32_t(*)[16]>(pk));
+              }
+            }
+            FF_TL(0, itj, 4);
+            tmem_wait_st();
+            FF_TL(0, itj, 5);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_p + 8 * wg);
+            FF_TL(0, itj, 6);
+            FF_TRACE(itj, 34);
+            ++n_mine;
+            last_mine = itj;
           }
         }
       }
-      if (first) continue;     // (defensive) no tile of this pass was processed: nothing to add
-      // ---- end of pass: acc += weight * roww / l * O   (l = the ones-column of P.V)
+      if (it == it_pass0) continue;     // (defensive) no tile of this pass was processed: nothing to add (CTA-uniform)
+      // ---- end of pass: merge the two partial softmaxes, acc += weight * roww / l * O.
+      // (1) my last PV has landed: s_full(last_mine + 2) -- a real tile of the next pass or one of the two virtual commits
       FF_TRACE(it, 35);
-      mbar_wait_hot<0>(bar_s + 8 * ((it + 1) & 1), ((it + 1) >> 1) & 1);   // s_full(L+2) => PV(L) of this pass's last tile L = it-1
+      if (n_mine > 0) mbar_wait_hot<0>(bar_s + 8 * wg, ((last_mine + 2) >> 1) & 1);
       FF_TRACE(it, 36);
+      // (2) exchange the reference points (row-wise, through shared memory)
+      mx_smem[wg * BM + rloc] = n_mine > 0 ? m_used : -INFINITY;
+      tc_fence_before();
+      named_bar_sync(1, 32 * NUM_SOFTMAX_WARPS);
       tc_fence_after();
-      const float l = tmem_ld1_wait(tlane + C::TMEM_O + p.head_dim);
+      const float m_other = mx_smem[(wg ^ 1) * BM + rloc];
+      const float m_all = fmaxf(m_used, m_other);          // (n_mine == 0 -> m_used = -inf by construction)
+      // tcgen05.ld is warp-collective: TMEM reads are guarded by CTA-uniform tile counts only (an accumulator that no
+      // PV of this pass wrote is not read); rows that read nothing (reference point -inf) get weight 0 per lane
+      const bool wrote_mine = n_mine > 0, wrote_other = (it - it_pass0) - n_mine > 0;
+      const float a_mine = (wrote_mine && m_used > -INFINITY) ? fast_exp2(m_used - m_all) : 0.f;
+      const float a_other = (wrote_other && m_other > -INFINITY) ? fast_exp2(m_other - m_all) : 0.f;
+      // (3) denominators from the ones column of each accumulator
+      float l = 0.f;
+      if (wrote_mine) l = a_mine * tmem_ld1_wait(tO + p.head_dim);
+      if (wrote_other) l = fmaf(a_other, tmem_ld1_wait(tOx + p.head_dim), l);
       float coef = ps.weight;
       if (ps.flags & FF_PASS_ROW_WEIGHT) coef = rb ? coef : 0.f;
       coef = l > 0.f ? coef / l : 0.f;
+      const float c_mine = coef * a_mine, c_other = coef * a_other;
+      // (4) my share of the channels: 16-channel chunks of parity wg, both accumulators
 #pragma unroll
       for (int c = 0; c < DPAD / 16; ++c) {
-        if (NH == 2 && (c & 1) != half) continue;
-        float o[16], a[16];
-        uint32_t ab[16];
-        tmem_ld16(tlane + C::TMEM_O + 16 * c, o);
-        tmem_wait_ld16(o);
-        if (acc_started) {
-          tmem_ld16(tlane + C::TMEM_ACC + 16 * c, a);
-          tmem_wait_ld16(a);
-        } else {
+        if ((c & 1) != wg) continue;
+        float r[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) a[i] = 0.f;
+        for (int i = 0; i < 16; ++i) r[i] = acc_started ? acc_row[16 * c + i] : 0.f;
+        if (wrote_mine) {
+          float o[16];
+          tmem_ld16(tO + 16 * c, o);
+          tmem_wait_ld16(o);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = fmaf(c_mine, o[i], r[i]);      // (c_mine = 0 for rows that read nothing)
+        }
+        if (wrote_other) {
+          float o[16];
+          tmem_ld16(tOx + 16 * c, o);
+          tmem_wait_ld16(o);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = fmaf(c_other, o[i], r[i]);
         }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) ab[i] = __float_as_uint(fmaf(coef, o[i], a[i]));
-        tmem_st16(tlane + C::TMEM_ACC + 16 * c, ab);
+        for (int i = 0; i < 16; i += 4)
+          *reinterpret_cast<float4*>(acc_row + 16 * c + i) = make_float4(r[i], r[i + 1], r[i + 2], r[i + 3]);
       }
-      tmem_wait_st();
       acc_started = true;
+      // (5) both accumulators have been read by everybody: the next pass may overwrite them
+      tc_fence_before();
+      named_bar_sync(2, 32 * NUM_SOFTMAX_WARPS);
+      tc_fence_after();
     }
-    // ---- write the row: out[stream, row, head*d : (head+1)*d], 16-channel chunks split between the two warpgroups.
-    // tcgen05.ld is warp-collective (.sync.aligned): every lane executes the TMEM loads, only the global stores are
-    // predicated on row < s_q.
+    // ---- write the row: out[stream, row, head*d : (head+1)*d]; each thread writes the chunks it accumulated
     {
       const bool row_ok = row < p.s_q;
       const size_t o_off = ((size_t)stream * p.s_q + (row_ok ? row : 0)) * ((size_t)p.heads * p.head_dim) +
                            (size_t)head * p.head_dim;
 #pragma unroll
       for (int c = 0; c < DPAD / 16; ++c) {
-        if (NH == 2 && (c & 1) != half) continue;
+        if ((c & 1) != wg) continue;
         float o[16];
-        if (acc_started) {
-          tmem_ld16(tlane + C::TMEM_ACC + 16 * c, o);
-          tmem_wait_ld16(o);
-        } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = 0.f;
-        }
+        for (int i = 0; i < 16; ++i) o[i] = acc_started ? acc_row[16 * c + i] : 0.f;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           if (row_ok && 16 * c + 8 * g < p.head_dim) {   // head_dim % 8 == 0

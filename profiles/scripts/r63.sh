@@ -1,0 +1,9 @@
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_attention.py -q -m gpu > gpurun_out/r63_pytest.txt 2>&1; tail -3 gpurun_out/r63_pytest.txt
+for v in "" _p37 _s1 _s3 _s3p37; do
+  echo "== variant '$v'" >> gpurun_out/r63_attn_case.txt
+  FREEFINE_B200_LIB=$PWD/freefine_b200/lib/libfreefine_b200$v.so timeout 120 python profiles/attn_case.py 5 >> gpurun_out/r63_attn_case.txt 2>&1
+done
+cat gpurun_out/r63_attn_case.txt
+FREEFINE_B200_LIB=$PWD/freefine_b200/lib/libfreefine_b200_tl.so timeout 120 python profiles/timeline.py > gpurun_out/r63_timeline.txt 2>&1
+sed -n 2,8p gpurun_out/r63_timeline.txt

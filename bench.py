@@ -121,7 +121,7 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": "edits/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "edits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def workload_config(args):
@@ -341,13 +341,28 @@ def run_ours(args):
                 "dtype": "bf16", "data": "synthetic", "config": workload_config(args), "clocks": clk.result,
                 "e2e": e2e, "gpu_launches": launches, "gpu_launches_by_entry": counts, "roofline": roofline,
                 "cpu_baseline": cpu, "output_finite": finite}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = sys.stdout
+
+
+def _emit(line: dict):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def main():
+    global _JSON_OUT
     args = parse()
+    # library chatter (e.g. the "NCCL version ..." banner some NCCL_DEBUG settings print on stdout) must not precede
+    # the JSON line: file descriptor 1 is pointed at stderr for the whole run, the JSON goes to a dup of the real stdout
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

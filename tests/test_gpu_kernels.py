@@ -105,7 +105,9 @@ def test_warp_blend_vs_oracle_shapes(dev):
     """Batched thetas, non-square / ragged sizes, resizing dsize, strong minification (global-tap path), bf16."""
     from freefine_b200 import ops
     rng = np.random.default_rng(5)
-    for (N, C, H, W, dH, dW) in ((2, 3, 64, 64, 64, 64), (1, 5, 37, 53, 41, 29), (1, 2, 256, 256, 32, 32), (3, 4, 16, 16, 16, 16)):
+    # (the even-channel, 16-byte-friendly shapes take the kernel's fast path, the others the general loop)
+    for (N, C, H, W, dH, dW) in ((2, 3, 64, 64, 64, 64), (1, 5, 37, 53, 41, 29), (1, 2, 256, 256, 32, 32), (3, 4, 16, 16, 16, 16),
+                                 (2, 8, 64, 64, 64, 64), (1, 6, 96, 96, 96, 96), (1, 4, 64, 64, 32, 48)):
         src = rng.standard_normal((N, C, H, W)).astype(np.float32)
         bg = rng.standard_normal((N, C, dH, dW)).astype(np.float32)
         th = np.stack([np.array([[np.cos(a) * s, np.sin(a) * s, tx], [-np.sin(a) * s, np.cos(a) * s, ty]], np.float32)
@@ -126,6 +128,15 @@ def test_warp_blend_vs_oracle_shapes(dev):
     out = ops.warp_affine_blend(sb, th)
     ref = O.warp_affine(sb.float().cpu().numpy(), th.numpy(), (32, 32), "bilinear")
     assert np.abs(out.float().cpu().numpy() - ref).max() < 2e-2
+    # bf16 masked blend (fast path): fp32 arithmetic on the bf16 values, one rounding on store; background copied exactly
+    bgb = torch.from_numpy(rng.standard_normal((1, 4, 32, 32)).astype(np.float32)).to(dev).bfloat16()
+    mk = cases.blob_mask(32, 77)
+    outb, mo = ops.warp_affine_blend(sb, th, mask_src=torch.from_numpy(mk)[None].to(dev), bg=bgb, want_mask=True)
+    wm = O.warp_affine(mk.astype(np.float32)[None, None], th.numpy(), (32, 32), "nearest")[0, 0] != 0
+    assert np.array_equal(mo[0].cpu().numpy() != 0, wm)
+    refb = np.where(wm[None, None], ref, bgb.float().cpu().numpy())
+    assert np.abs(outb.float().cpu().numpy() - refb).max() < 2e-2
+    assert np.array_equal(outb.float().cpu().numpy()[:, :, ~wm], bgb.float().cpu().numpy()[:, :, ~wm])
 
 
 def test_mask_downsample_pack_bit_exact(dev):

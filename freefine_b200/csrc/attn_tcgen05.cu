@@ -164,16 +164,8 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
       : "memory");
 }
-// Named barriers 1..4 (0 is __syncthreads): producer/consumer hand-shake between the two softmax warpgroups.
+// Named barriers 1, 2 (0 is __syncthreads): all-softmax-warps synchronisation at the end of a pass.
 // (immediate ids: with a register id ptxas reserves all 16 hardware barriers for the CTA)
-__device__ __forceinline__ void named_bar_arrive(int id, int count) {
-  switch (id) {
-    case 1: asm volatile("bar.arrive 1, %0;" ::"r"(count) : "memory"); break;
-    case 2: asm volatile("bar.arrive 2, %0;" ::"r"(count) : "memory"); break;
-    case 3: asm volatile("bar.arrive 3, %0;" ::"r"(count) : "memory"); break;
-    default: asm volatile("bar.arrive 4, %0;" ::"r"(count) : "memory"); break;
-  }
-}
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
   switch (id) {
     case 1: asm volatile("bar.sync 1, %0;" ::"r"(count) : "memory"); break;
@@ -246,12 +238,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
       : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }

@@ -58,3 +58,11 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), os.path.join(dp, f)
+
+
+def test_v_head_stride_host_function(lib):
+    """ff_attn_v_head_stride is pure host code: channels per head of the staged V (head_dim + ones column, padded to the
+    N granularity of the PV tensor-core instruction)."""
+    for d, want in ((8, 16), (16, 48), (40, 48), (48, 96), (80, 96), (88, 176), (160, 176)):
+        assert lib.ff_attn_v_head_stride(d) == want, d
+        assert want > d and want % 16 == 0

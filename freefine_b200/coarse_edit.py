@@ -109,6 +109,30 @@ def re_edit_2d(src_img, src_mask, edit_param, inp_cur, device="cuda"):
     return to_u8(out[0]), (wm[0] * 255).cpu().numpy(), to_u8(out[1])
 
 
+def re_edit_3d(src_img, src_mask, edit_param, inp_cur, ori_img_a, ori_mask_a, device="cuda"):
+    """reference vis_utils.py:275-339: the same affine coarse edit as re_edit_2d applied to the re-oriented object
+    (`src_img`/`src_mask` come from the depth / novel-view pre-step, out of scope here); the hole image is built from the
+    ORIGINAL image and mask (`ori_img_a` with `ori_mask_a` blanked, :316).  ori_mask_a: [H,W] or [H,W,1|3] (numpy
+    broadcasting against the HWC image, as in the reference).
+    -> (final_image u8 HWC, transformed_mask u8 0/255, trans_hole_image u8 HWC)."""
+    if src_mask.ndim == 3:
+        src_mask = src_mask[:, :, 0]
+    H, W = src_mask.shape[:2]
+    M = edit_matrix(src_mask, edit_param)
+    theta = torch.tensor(cv2_theta(M, W, H), dtype=torch.float32)[None]
+    img = torch.from_numpy(np.ascontiguousarray(src_img)).to(device).permute(2, 0, 1)[None].float().contiguous()
+    msk = torch.from_numpy((src_mask != 0).astype(np.uint8)).to(device)[None].contiguous()
+    om = np.asarray(ori_mask_a)
+    om = om[:, :, None] if om.ndim == 2 else om
+    hole_np = np.where(om, 0, ori_img_a)                                         # :316
+    hole = torch.from_numpy(np.ascontiguousarray(hole_np)).to(device).permute(2, 0, 1)[None].float()
+    bgs = torch.cat([torch.from_numpy(np.ascontiguousarray(inp_cur)).to(device).permute(2, 0, 1)[None].float(), hole])
+    out, wm = ops.warp_affine_blend(img.expand(2, -1, -1, -1).contiguous(), theta.expand(2, 2, 3),
+                                    mask_src=msk.expand(2, -1, -1).contiguous(), bg=bgs.contiguous(), want_mask=True)
+    to_u8 = lambda t: t.round().clamp(0, 255).to(torch.uint8).permute(1, 2, 0).cpu().numpy()
+    return to_u8(out[0]), (wm[0] * 255).cpu().numpy(), to_u8(out[1])
+
+
 def dilate_mask(mask, dilate_factor=15, device="cuda"):
     """reference vis_utils.py:340-347 (cv2.dilate, k x k ones, anchor k//2, outside = 0) as a device max-filter."""
     k = int(dilate_factor)

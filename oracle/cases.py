@@ -163,3 +163,18 @@ def compose_case_inputs(seed: int, res: int = 128):
     ori = ori_mask3[:, :, 0]
     return dict(coarse=img, imgs=[app_img, img], ori_masks=[app_mask3[:, :, 0].copy(), (1 - ori).astype(np.uint8)],
                 tgt_masks=[ori.copy()])
+
+
+# re_edit_3d (vis_utils.py:275-339): (seed, edit_param) -- translation only, and translation + rotation + anisotropic scale
+COARSE3D_CASES = {
+    "move": (31, (9, -6, 0, 1.0, 1.0)),
+    "move_rot_scale": (32, (-7, 5, 17.0, 0.85, 1.2)),
+}
+
+
+def coarse3d_case_inputs(seed: int, res: int = 128):
+    """(re-oriented object image, its mask [res,res,3] 0/1, background, original image, original mask [res,res,1] bool)."""
+    src, m3, _, _, _ = edit_case_inputs(seed, res)
+    ori, om3, _, _, _ = edit_case_inputs(seed + 50, res)
+    bg, _, _, _, _ = edit_case_inputs(seed + 70, res)
+    return src, m3, bg, ori, om3[:, :, :1].astype(bool)

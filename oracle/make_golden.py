@@ -242,6 +242,16 @@ def gen_pipeline(ref):
     np.savez_compressed(os.path.join(OUT, "pipeline.npz"), **out)
 
 
+def gen_coarse3d(ref):
+    """re_edit_3d of the UNMODIFIED reference (cv2.warpAffine) on seeded inputs."""
+    out = {}
+    for name, (seed, ep) in cases.COARSE3D_CASES.items():
+        src, m3, bg, ori, om = cases.coarse3d_case_inputs(seed)
+        final, tmask, hole = ref.vis_utils.re_edit_3d(src, m3, ep, bg, ori, om)
+        out[name + "/final"], out[name + "/tmask"], out[name + "/hole"] = final, tmask, hole
+    np.savez_compressed(os.path.join(OUT, "coarse3d.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_import.load()
@@ -253,6 +263,7 @@ def main():
     gen_warp(ref)
     gen_masks(ref, parts)
     gen_pipeline(ref)
+    gen_coarse3d(ref)
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

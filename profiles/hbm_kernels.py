@@ -2,7 +2,8 @@
 (at real sizes -- 128 KiB of latents per edit -- these launches are latency-bound, so the roofline is
 demonstrated at n_edits = 2048 / N*C = 32768).  CUDA-event timing, 3 warm-ups, inputs >> 126 MB L2.
 ALGORITHMIC bytes: (c) eps_u, eps_c, x, noise read + x_prev written (5 tensors of 2*4*h*w*4 B per edit) + 2*h*w mask bytes;
-(c-inv) eps, x read + x_next written; (b) src read once + bg read + out written + mask bytes."""
+(c-inv) eps, x read + x_next written; (b) src read once + bg read + out written + mask bytes; K/V staging: K, V read,
+K copy + padded fp16 V written + the int64 row index."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -54,5 +55,15 @@ for NC, label in ((32768, "warp_blend_large"), (2048, "warp_blend_l2_resident"))
     byt = 3 * src.numel() * 4 + 2 * 64 * 64
     res[label] = dict(NC=NC, bytes=byt, ms_best=best, ms_median=med, gbs=byt / best / 1e6, frac=byt / best / 1e6 / peak)
     del src, bg, outb
+# K/V staging: K gathered (bf16 copy), V gathered + converted into the padded fp16 layout (48 channels per 40)
+heads, d, S, B = 8, 40, 4096, 64
+kk = torch.randn(B, S, heads * d, device=dev).bfloat16()
+vv = torch.randn(B, S, heads * d, device=dev).bfloat16()
+idx = torch.randperm(B * S, device=dev)
+best, med = timeit(lambda: ops.kv_gather_cast(kk, vv, heads, idx))
+byt = 2 * kk.numel() * 2 + kk.numel() * 2 + B * S * heads * 48 * 2 + idx.numel() * 8
+res["kv_gather_cast"] = dict(rows=B * S, bytes=byt, ms_best=best, ms_median=med, gbs=byt / best / 1e6, frac=byt / best / 1e6 / peak,
+                             note="random row permutation (640-byte rows), output allocation inside the timed call")
+del kk, vv
 res["peak_hbm_gbs"] = peak
 print(json.dumps(res, indent=1))

@@ -193,6 +193,24 @@ def test_re_edit_2d_matches_cv2_reference(dev, golden):
         assert np.abs(final.astype(np.int32) - g[name + "/coarse"].astype(np.int32)).max() <= 1, name
 
 
+def test_re_edit_3d_matches_cv2_reference(dev, golden):
+    """re_edit_3d (vis_utils.py:275-339) on the warp kernel vs the outputs of the unmodified reference (cv2.warpAffine):
+    the nearest-warped mask bit-exact, images within cv2's 1/32-pixel fixed-point coordinate quantisation (+ uint8
+    rounding) -- incl. rotation + anisotropic scale, where the corrected theta of quirk Q11 matters."""
+    from freefine_b200.coarse_edit import re_edit_3d
+    g = golden["coarse3d"]
+    for name, (seed, ep) in cases.COARSE3D_CASES.items():
+        src, m3, bg, ori, om = cases.coarse3d_case_inputs(seed)
+        final, tmask, hole = re_edit_3d(src, m3, ep, bg, ori, om)
+        assert tmask.dtype == np.uint8 and set(np.unique(tmask)) <= {0, 255}
+        assert np.array_equal(tmask, g[name + "/tmask"]), name
+        tol = 1 if name == "move" else 3
+        assert np.abs(final.astype(np.int32) - g[name + "/final"].astype(np.int32)).max() <= tol, name
+        assert np.abs(hole.astype(np.int32) - g[name + "/hole"].astype(np.int32)).max() <= tol, name
+        out = tmask == 0                                  # outside the moved object: background / hole image, exact
+        assert np.array_equal(final[out], bg[out]) and np.array_equal(hole[out], np.where(om, 0, ori)[out]), name
+
+
 @pytest.mark.parametrize("name", list(cases.COMPOSE_CASES))
 def test_cross_image_composition_matches_reference(dev, golden, name, monkeypatch):
     """Composition / appearance transfer: register_attention_control_compose + the inner functions of

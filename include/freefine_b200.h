@@ -54,10 +54,12 @@ const char* ff_last_error(void);
  * doubled [K_self;K_ref] context of the SSA/SDSA variants) and
  *     kb(k)       = key_mask < 0 ? 1 : bit k of bitmask row key_mask
  *     rb(q)       = row_mask < 0 ? 0 : bit q of bitmask row row_mask
- *     allowed(q,k)= kb(k) ^ KEY_INVERT ^ (ROW_XOR & rb(q))
+ *     allowed(q,k)= key_mask < 0 ? 1 : kb(k) ^ KEY_INVERT ^ (ROW_XOR & rb(q))
+ *                   (a segment WITHOUT a key mask admits every key: KEY_INVERT / ROW_XOR act on masked segments only)
  *     roww(q)     = ROW_WEIGHT ? rb(q) : 1
  * A row whose allowed set is EMPTY attends uniformly to every key (reference quirk Q4: the additive fill is
- * finfo.min, not -inf, attention.py:857); the kernel derives emptiness from mask_popcount, no host sync needed.
+ * finfo.min, not -inf, attention.py:857); the kernel derives emptiness from mask_popcount, no host sync needed
+ * (single-segment passes; with a second segment the plan builders never produce an empty allowed set).
  * The host-side controller (freefine_b200/attention.py) encodes quirk Q0 (head-parity mask tiling,
  * attention.py:859,881) simply by which plan it gives to which (stream, head).
  * ------------------------------------------------------------------------------------------------------------ */

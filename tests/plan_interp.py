@@ -47,10 +47,11 @@ def run_plan(q, k, v, plan, heads, scale, bitmasks=None):
                     ks.append(kh[kv, :, h])
                     vs.append(vh[kv, :, h])
                     a = kbits(km, Skv, pfx)[None, :].expand(Sq, Skv)
-                    if inv:
-                        a = ~a
-                    if flags & FF_PASS_ROW_XOR:
-                        a = a ^ rb[:, None]
+                    if km >= 0:                      # a segment without a key mask admits every key, whatever the flags
+                        if inv:
+                            a = ~a
+                        if flags & FF_PASS_ROW_XOR:
+                            a = a ^ rb[:, None]
                     al.append(a)
                 kk, vv, allowed = torch.cat(ks), torch.cat(vs), torch.cat(al, 1)
                 sc = (qh[s, :, h] @ kk.T) * scale

@@ -198,6 +198,75 @@ def test_full_size_properties(dev):
     assert float((out1[s, :, :d] - ref).abs().max()) < TOL
 
 
+@pytest.mark.parametrize("seed", list(range(24)))
+def test_random_plans_vs_plan_interpreter(dev, seed):
+    """Fuzz: random shapes (ragged S_q / S_kv, 1..5 K/V tiles, every head-dim instantiation), random bit-vector masks
+    incl. empty and full ones, random multi-pass plans (1-3 passes, second K/V segment, KEY_INVERT / ROW_XOR /
+    ROW_WEIGHT) against the literal CPU reading of the plan semantics (tests/plan_interp.py).  Exercises single-tile
+    passes, passes in which only one of the two softmax warpgroups gets a tile, rows that read nothing from a tile."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from plan_interp import run_plan
+    from freefine_b200 import ops
+    if seed % 3 == 0:
+        # stale allocator contents must not matter: poison the free blocks the next allocations will reuse
+        junk = [torch.full((n,), float("nan"), device=dev) for n in (1 << 12, 1 << 15, 1 << 18, 1 << 21, 1 << 23)]
+        junk += [torch.full((n,), 0xFF, dtype=torch.uint8, device=dev) for n in (1 << 10, 1 << 14, 1 << 17)]
+        torch.cuda.synchronize()
+        del junk
+    rng = np.random.default_rng(9000 + seed)
+    B = int(rng.integers(1, 4))
+    heads = int(rng.choice([1, 2, 4]))
+    d = int(rng.choice([8, 16, 24, 40, 64, 80, 96, 160]))
+    Sq, Skv = int(rng.integers(1, 261)), int(rng.integers(1, 321))
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randn(B, Sq, heads * d, generator=g).bfloat16().float()
+    k = torch.randn(B, Skv, heads * d, generator=g).bfloat16().float()
+    v = (torch.randn(B, Skv, heads * d, generator=g) * 2).bfloat16().float()
+    S = max(Sq, Skv)
+    dens = [0.0, 1.0, float(rng.uniform(0.05, 0.95)), float(rng.uniform(0.3, 0.7))]
+    rng.shuffle(dens)
+    flat = [(rng.random(S) < p_).astype(np.uint8) for p_ in dens]
+    plan = plans._empty(B, heads)
+    for s_ in range(B):
+        for h in range(heads):
+            for _ in range(int(rng.integers(1, 4))):
+                kv = int(rng.integers(0, B))
+                km = int(rng.integers(-1, 4))
+                rm = int(rng.integers(-1, 4))
+                flags = 0
+                if km >= 0 and rng.random() < 0.4:
+                    flags |= plans.FF_PASS_KEY_INVERT
+                if km >= 0 and rm >= 0 and rng.random() < 0.5:
+                    flags |= plans.FF_PASS_ROW_XOR
+                if rm >= 0 and rng.random() < 0.3:
+                    flags |= plans.FF_PASS_ROW_WEIGHT
+                kv2, km2 = -1, -1
+                # second segment under the same softmax: every key of another stream (a segment WITHOUT a key mask admits
+                # every key whatever the flags say, so ROW_XOR passes stay single-segment here)
+                if not (flags & plans.FF_PASS_ROW_XOR) and rng.random() < 0.25:
+                    kv2 = int(rng.integers(0, B))
+                plans._add(plan, s_, h, kv, float(rng.uniform(0.1, 1.0)), key_mask=km, row_mask=rm, flags=flags, kv2=kv2,
+                           key_mask2=km2)
+    words = ops.mask_words(S)
+    arr = np.zeros((len(flat), words), np.uint32)
+    for i, m in enumerate(flat):
+        b = O.pack_bits(m != 0)
+        arr[i, : len(b)] = b
+    # (popcounts are over the first S_kv tokens: what the kernel's empty-set rule looks at)
+    flat_kv = [m.copy() for m in flat]
+    ref = run_plan(q, k, v, plan, heads, d ** -0.5, arr)
+    bm = torch.from_numpy(arr.view(np.int32)).to(dev)
+    pc = torch.tensor([int(m[:Skv].sum()) for m in flat_kv], dtype=torch.int32, device=dev)
+    kk, vv = ops.kv_gather_cast(k.to(dev).bfloat16().contiguous(), v.to(dev).bfloat16().contiguous(), heads, None,
+                                p_operand=P_OPERAND)
+    out = ops.attn_masked_kv(q.to(dev).bfloat16(), kk, vv, ops.to_device_bytes(plan, dev), heads, d ** -0.5, bm, pc,
+                             out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    err = float((out.cpu() - ref).abs().max())
+    assert err < TOL * 3.0, (err, B, heads, d, Sq, Skv)       # up to 3 passes of weight <= 1 each
+
+
 def test_error_paths(dev):
     from freefine_b200 import ops
     q = torch.zeros(4, 64, 64, device=dev, dtype=torch.bfloat16)

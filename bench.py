@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--channels-last", action="store_true", help="run the (library) UNet body in channels_last")
+    ap.add_argument("--plain-unet", action="store_true",
+                    help="A/B only: eager NCHW UNet body instead of the channels-last fast path (csrc/unet_glue.cu)")
     return ap.parse_args()
 
 
@@ -131,6 +133,8 @@ def workload_config(args):
             "start_step": args.start_step, "unet_calls_per_edit": f"{n} inversion (2 streams) + {n} sampling (4 streams)",
             "method": "tca", "guidance_scale": 7.5, "eta": 1.0, "use_auto_draw": True, "reduce_inp_artifacts": True,
             "network": f"random-init SD1.5-shaped stand-in UNet ({args.preset}), bf16",
+            "unet_body": "eager NCHW (A/B)" if getattr(args, "plain_unet", False) else
+                         "channels-last fast path: cuDNN/cuBLAS + fused GroupNorm/SiLU, bias+residual, GEGLU, LayerNorm kernels",
             "l2": "working set per step (UNet weights 1.7 GB + activations) exceeds the 126 MB L2; no explicit flush",
             "parallelism": "independent edits, one model replica per GPU, no collective on the hot path"}
 
@@ -206,6 +210,9 @@ def run_ours(args):
     torch.backends.cuda.matmul.allow_tf32 = True
     torch.backends.cudnn.allow_tf32 = True
 
+    if args.plain_unet:
+        import freefine_b200.standin as _standin
+        _standin.FAST_PATH = False
     parts = build_standin(args.preset, device=dev, dtype=torch.bfloat16)
     if args.channels_last:
         parts.unet.to(memory_format=torch.channels_last)

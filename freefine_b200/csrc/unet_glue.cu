@@ -1,0 +1,370 @@
+// Channels-last (NHWC) glue kernels of the UNet body between the library convolutions / GEMMs.
+//
+// The reference runs diffusers' UNet eagerly: per resnet half  conv -> (+bias) -> (+temb) -> GroupNorm (moments, apply)
+// -> SiLU, per transformer block  permute copy -> LayerNorm x3 -> GEGLU (gelu, mul), per conv a NCHW<->NHWC conversion
+// pair inside cuDNN.  ncu launch list of round 1: 29 % of a UNet call in non-vectorised at::elementwise_kernel, 8 % in
+// layout conversions, 6 % in RowwiseMoments, 6.5 % in layer norm -- all of it HBM-bound byte shuffling.  These kernels
+// keep every activation bf16 [N, H*W, C] (= torch channels_last = the token layout of the transformer blocks, so the
+// permutes become views) and touch each tensor the minimum number of times:
+//   ff_group_norm_nhwc     y = act(GroupNorm(x + add[n,c]))   2 reads (second one L2-resident) + 1 write, fp32 statistics,
+//                          conv bias + time embedding folded in as the per-(n,c) addend, SiLU fused
+//   ff_bias_residual_nhwc  out = h + bias[c] + res            conv bias + skip connection in one pass
+//   ff_geglu               out = x * gelu(gate)               1 read of [M,2F], 1 write of [M,F]
+//   ff_layer_norm          y = LayerNorm(x)                   1 read + 1 write, one warp per token row, row in registers
+// All accesses are 128-bit; sums are combined in a fixed order (bit-reproducible run to run).
+#include <cuda_bf16.h>
+
+#include "ff_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);            // bf16 -> fp32 is a shift
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 b = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<const uint32_t*>(&b);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+constexpr int GN_THREADS = 256;
+constexpr int GN_MAX_CHUNKS = 64;     // pixel chunks per image (partial statistics per chunk)
+
+// Thread layout shared by the two GroupNorm kernels: `cols` = min(C/8, 256) threads side by side over the 16-byte
+// channel vectors of a pixel, R = 256 / cols pixel rows in flight; a thread keeps ONE channel vector column at a time,
+// so per-channel constants / accumulators live in registers.
+struct GnLayout {
+  int CV, cols, R, col, r;
+  __device__ GnLayout(int C) {
+    CV = C >> 3;
+    cols = CV < GN_THREADS ? CV : GN_THREADS;
+    R = GN_THREADS / cols;
+    col = threadIdx.x % cols;
+    r = threadIdx.x / cols;        // r >= R: idle thread (256 is not a multiple of cols)
+  }
+};
+
+// partial[n][chunk][g] = (sum, sum of squares) of v = x + add over the pixels of the chunk and the channels of group g
+__global__ void __launch_bounds__(GN_THREADS)
+gn_stats_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_nc, float2* __restrict__ partial,
+                     int HW, int C, int G, int chunk_px, int n_chunks) {
+  extern __shared__ float sm[];                 // [R][2][C] per-row-slot channel sums, then reduced into slot 0
+  const GnLayout L(C);
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int p0 = chunk * chunk_px, p1 = min(HW, p0 + chunk_px);
+  if (L.r < L.R) {
+    for (int v = L.col; v < L.CV; v += L.cols) {
+      float a[8], s[8], ss[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a[j] = add_nc ? __ldg(add_nc + (size_t)n * C + 8 * v + j) : 0.f;
+        s[j] = ss[j] = 0.f;
+      }
+      const uint4* px = x + ((size_t)n * HW + p0 + L.r) * L.CV + v;
+      const size_t step = (size_t)L.R * L.CV;
+#pragma unroll 4
+      for (int p = p0 + L.r; p < p1; p += L.R, px += step) {
+        float f[8];
+        unpack8(__ldg(px), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float t = f[j] + a[j];
+          s[j] += t;
+          ss[j] = fmaf(t, t, ss[j]);
+        }
+      }
+      float* dst = sm + (size_t)L.r * 2 * C + 8 * v;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        dst[j] = s[j];
+        dst[C + j] = ss[j];
+      }
+    }
+  }
+  __syncthreads();
+  const int cpg = C / G;
+  for (int g = threadIdx.x; g < G; g += GN_THREADS) {
+    float S = 0.f, SS = 0.f;
+    for (int rr = 0; rr < L.R; ++rr) {          // fixed order: reproducible
+      const float* src = sm + (size_t)rr * 2 * C + g * cpg;
+      for (int c = 0; c < cpg; ++c) {
+        S += src[c];
+        SS += src[C + c];
+      }
+    }
+    partial[((size_t)n * n_chunks + chunk) * G + g] = make_float2(S, SS);
+  }
+}
+
+template <bool SILU>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_apply_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_nc,
+                     const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
+                     const float2* __restrict__ partial, uint4* __restrict__ y, int HW, int C, int G, int chunk_px,
+                     int n_chunks, float eps) {
+  extern __shared__ float sm[];                 // [G] mean, [G] rstd
+  float* mean = sm;
+  float* rstd = sm + G;
+  const GnLayout L(C);
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int cpg = C / G;
+  const float inv_cnt = 1.f / ((float)cpg * (float)HW);
+  for (int g = threadIdx.x; g < G; g += GN_THREADS) {
+    float S = 0.f, SS = 0.f;
+    for (int ch = 0; ch < n_chunks; ++ch) {     // fixed order: every CTA of image n derives identical statistics
+      const float2 t = __ldg(partial + ((size_t)n * n_chunks + ch) * G + g);
+      S += t.x;
+      SS += t.y;
+    }
+    const float m = S * inv_cnt;
+    const float var = fmaxf(SS * inv_cnt - m * m, 0.f);
+    mean[g] = m;
+    rstd[g] = 1.f / sqrtf(var + eps);
+  }
+  __syncthreads();
+  if (L.r >= L.R) return;
+  const int p0 = chunk * chunk_px, p1 = min(HW, p0 + chunk_px);
+  for (int v = L.col; v < L.CV; v += L.cols) {
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = 8 * v + j, g = c / cpg;
+      const float a = add_nc ? __ldg(add_nc + (size_t)n * C + c) : 0.f;
+      sc[j] = rstd[g] * __bfloat162float(gamma[c]);
+      sh[j] = fmaf(a - mean[g], sc[j], __bfloat162float(beta[c]));     // y = (x + a - mean) * rstd * gamma + beta
+    }
+    const size_t off = ((size_t)n * HW + p0 + L.r) * L.CV + v;
+    const uint4* px = x + off;
+    uint4* py = y + off;
+    const size_t step = (size_t)L.R * L.CV;
+#pragma unroll 4
+    for (int p = p0 + L.r; p < p1; p += L.R, px += step, py += step) {
+      float f[8];
+      unpack8(__ldg(px), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = fmaf(f[j], sc[j], sh[j]);
+        if (SILU) t = t / (1.f + __expf(-t));
+        f[j] = t;
+      }
+      *py = pack8(f);
+    }
+  }
+}
+
+// out[m, c] = h[m, c] + bias[c] + res[m, c]   (bias / res optional), CV = C/8 vectors per row
+__global__ void __launch_bounds__(256)
+bias_residual_kernel(const uint4* __restrict__ h, const __nv_bfloat16* __restrict__ bias,
+                     const uint4* __restrict__ res, uint4* __restrict__ out, long long total, int CV) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    float f[8];
+    unpack8(__ldg(h + i), f);
+    if (bias) {
+      const int v = (int)(i % CV);
+      float b[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(bias) + v), b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += b[j];
+    }
+    if (res) {
+      float r[8];
+      unpack8(__ldg(res + i), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += r[j];
+    }
+    out[i] = pack8(f);
+  }
+}
+
+// out[m, f] = x * gelu(gate), x = h[m, f], gate = h[m, F + f]; gelu = erf form, in ATen's operation order and with
+// ATen's intermediate bf16 rounding of gelu(gate) (eager: F.gelu -> bf16 tensor, then a bf16 multiply).
+__global__ void __launch_bounds__(256)
+geglu_kernel(const uint4* __restrict__ h, uint4* __restrict__ out, long long total, int FV) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / FV;
+    const int v = (int)(i - m * FV);
+    const uint4* row = h + m * 2 * FV;
+    float x[8], g[8];
+    unpack8(__ldg(row + v), x);
+    unpack8(__ldg(row + FV + v), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float ge = bf16_round(g[j] * 0.5f * (1.f + erff(g[j] * 0.70710678118654752440f)));
+      x[j] *= ge;
+    }
+    out[i] = pack8(x);
+  }
+}
+
+// One warp per row of C = 8*CV channels (CV <= 32*VPL): the row stays in registers, mean then centred variance.
+template <int VPL>
+__global__ void __launch_bounds__(256)
+layer_norm_kernel(const uint4* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
+                  const __nv_bfloat16* __restrict__ beta, uint4* __restrict__ y, long long M, int CV, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const uint4* px = x + row * CV;
+  float f[VPL][8];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int v = lane + 32 * k;
+    if (v < CV) {
+      unpack8(__ldg(px + v), f[k]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += f[k][j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[k][j] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float inv_c = 1.f / (float)(8 * CV);
+  const float mean = s * inv_c;
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    if (lane + 32 * k < CV) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = f[k][j] - mean;
+        ss = fmaf(d, d, ss);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rstd = 1.f / sqrtf(ss * inv_c + eps);
+  uint4* py = y + row * CV;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int v = lane + 32 * k;
+    if (v < CV) {
+      float ga[8], be[8], o[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + v), ga);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(beta) + v), be);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf((f[k][j] - mean) * rstd, ga[j], be[j]);
+      py[v] = pack8(o);
+    }
+  }
+}
+
+int gn_chunks(int HW, int* chunk_px) {
+  int n_chunks = (HW + 127) / 128;
+  if (n_chunks > GN_MAX_CHUNKS) n_chunks = GN_MAX_CHUNKS;
+  if (n_chunks < 1) n_chunks = 1;
+  *chunk_px = (HW + n_chunks - 1) / n_chunks;
+  n_chunks = (HW + *chunk_px - 1) / *chunk_px;
+  return n_chunks;
+}
+
+int grid_for(long long total) {
+  long long grid = (total + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  return (int)(grid < 1 ? 1 : grid);
+}
+
+}  // namespace
+
+extern "C" int64_t ff_group_norm_ws_bytes(int32_t N, int32_t G) {
+  if (N <= 0 || G <= 0) return 0;
+  return (int64_t)N * GN_MAX_CHUNKS * G * (int64_t)sizeof(float2);
+}
+
+extern "C" int ff_group_norm_nhwc(const void* x, const float* add_nc, const void* gamma, const void* beta, void* y,
+                                  void* workspace, int32_t N, int32_t HW, int32_t C, int32_t G, float eps, int32_t silu,
+                                  void* stream) {
+  FF_REQUIRE(x && gamma && beta && y && workspace, "ff_group_norm_nhwc: null pointer");
+  FF_REQUIRE(N > 0 && HW > 0 && C > 0 && G > 0, "ff_group_norm_nhwc: bad shape");
+  FF_REQUIRE(N <= 65535, "ff_group_norm_nhwc: N must be <= 65535");
+  FF_REQUIRE(C % 8 == 0 && C % G == 0, "ff_group_norm_nhwc: C must be a multiple of 8 and of G (C=%d G=%d)", C, G);
+  FF_REQUIRE(ff::aligned16(x) && ff::aligned16(y) && ff::aligned16(workspace),
+             "ff_group_norm_nhwc: x / y / workspace must be 16-byte aligned");
+  int chunk_px = 0;
+  const int n_chunks = gn_chunks(HW, &chunk_px);
+  const int CV = C / 8, cols = CV < GN_THREADS ? CV : GN_THREADS, R = GN_THREADS / cols;
+  const size_t smem_stats = (size_t)R * 2 * C * sizeof(float);
+  FF_REQUIRE(smem_stats <= 48 * 1024, "ff_group_norm_nhwc: C=%d too large", C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const dim3 grid(n_chunks, N);
+  gn_stats_nhwc_kernel<<<grid, GN_THREADS, smem_stats, st>>>(static_cast<const uint4*>(x), add_nc,
+                                                             static_cast<float2*>(workspace), HW, C, G, chunk_px,
+                                                             n_chunks);
+  int rc = ff::check_launch("ff_group_norm_nhwc (statistics)");
+  if (rc != FF_OK) return rc;
+  const size_t smem_apply = (size_t)2 * G * sizeof(float);
+  if (silu)
+    gn_apply_nhwc_kernel<true><<<grid, GN_THREADS, smem_apply, st>>>(
+        static_cast<const uint4*>(x), add_nc, static_cast<const __nv_bfloat16*>(gamma),
+        static_cast<const __nv_bfloat16*>(beta), static_cast<const float2*>(workspace), static_cast<uint4*>(y), HW, C, G,
+        chunk_px, n_chunks, eps);
+  else
+    gn_apply_nhwc_kernel<false><<<grid, GN_THREADS, smem_apply, st>>>(
+        static_cast<const uint4*>(x), add_nc, static_cast<const __nv_bfloat16*>(gamma),
+        static_cast<const __nv_bfloat16*>(beta), static_cast<const float2*>(workspace), static_cast<uint4*>(y), HW, C, G,
+        chunk_px, n_chunks, eps);
+  return ff::check_launch("ff_group_norm_nhwc (apply)");
+}
+
+extern "C" int ff_bias_residual_nhwc(const void* h, const void* bias, const void* res, void* out, int64_t M, int32_t C,
+                                     void* stream) {
+  FF_REQUIRE(h && out, "ff_bias_residual_nhwc: null pointer");
+  FF_REQUIRE(M > 0 && C > 0 && C % 8 == 0, "ff_bias_residual_nhwc: C must be a positive multiple of 8");
+  FF_REQUIRE(ff::aligned16(h) && ff::aligned16(out) && ff::aligned16(bias) && ff::aligned16(res),
+             "ff_bias_residual_nhwc: pointers must be 16-byte aligned");
+  const long long total = (long long)M * (C / 8);
+  bias_residual_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(h), static_cast<const __nv_bfloat16*>(bias), static_cast<const uint4*>(res),
+      static_cast<uint4*>(out), total, C / 8);
+  return ff::check_launch("ff_bias_residual_nhwc");
+}
+
+extern "C" int ff_geglu(const void* h, void* out, int64_t M, int32_t F, void* stream) {
+  FF_REQUIRE(h && out, "ff_geglu: null pointer");
+  FF_REQUIRE(M > 0 && F > 0 && F % 8 == 0, "ff_geglu: F must be a positive multiple of 8");
+  FF_REQUIRE(ff::aligned16(h) && ff::aligned16(out), "ff_geglu: pointers must be 16-byte aligned");
+  const long long total = (long long)M * (F / 8);
+  geglu_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(h), static_cast<uint4*>(out), total, F / 8);
+  return ff::check_launch("ff_geglu");
+}
+
+extern "C" int ff_layer_norm(const void* x, const void* gamma, const void* beta, void* y, int64_t M, int32_t C,
+                             float eps, void* stream) {
+  FF_REQUIRE(x && gamma && beta && y, "ff_layer_norm: null pointer");
+  FF_REQUIRE(M > 0 && C > 0 && C % 8 == 0, "ff_layer_norm: C must be a positive multiple of 8");
+  FF_REQUIRE(C <= 8 * 32 * 8, "ff_layer_norm: C must be <= 2048");
+  FF_REQUIRE(ff::aligned16(x) && ff::aligned16(y) && ff::aligned16(gamma) && ff::aligned16(beta),
+             "ff_layer_norm: pointers must be 16-byte aligned");
+  const int CV = C / 8, vpl = (CV + 31) / 32;
+  const long long blocks = (M + 7) / 8;
+  FF_REQUIRE(blocks <= 2147483647LL, "ff_layer_norm: too many rows");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint4* xp = static_cast<const uint4*>(x);
+  const __nv_bfloat16* gp = static_cast<const __nv_bfloat16*>(gamma);
+  const __nv_bfloat16* bp = static_cast<const __nv_bfloat16*>(beta);
+  uint4* yp = static_cast<uint4*>(y);
+  if (vpl <= 1) layer_norm_kernel<1><<<(int)blocks, 256, 0, st>>>(xp, gp, bp, yp, M, CV, eps);
+  else if (vpl <= 2) layer_norm_kernel<2><<<(int)blocks, 256, 0, st>>>(xp, gp, bp, yp, M, CV, eps);
+  else if (vpl <= 3) layer_norm_kernel<3><<<(int)blocks, 256, 0, st>>>(xp, gp, bp, yp, M, CV, eps);
+  else if (vpl <= 5) layer_norm_kernel<5><<<(int)blocks, 256, 0, st>>>(xp, gp, bp, yp, M, CV, eps);
+  else layer_norm_kernel<8><<<(int)blocks, 256, 0, st>>>(xp, gp, bp, yp, M, CV, eps);
+  return ff::check_launch("ff_layer_norm");
+}

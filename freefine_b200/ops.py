@@ -328,6 +328,105 @@ def cross_region_blend(hs, bitmasks, region_ids):
     return hs
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# UNet-body glue in channels-last layout (csrc/unet_glue.cu).  bf16 only, no fallback.
+# ---------------------------------------------------------------------------------------------------------------
+def _nhwc_view(x: torch.Tensor, name: str):
+    """x: logical [N,C,H,W] with channels_last strides (or C == 1 / H*W == 1 ambiguity resolved by a dense NHWC
+    permutation) -> (N, HW, C); raises when the memory is not dense NHWC."""
+    if not x.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (freefine_b200 has no CPU path)")
+    if x.dtype != torch.bfloat16:
+        raise TypeError(f"{name} must be bfloat16, got {x.dtype}")
+    if x.dim() != 4:
+        raise ValueError(f"{name} must be [N,C,H,W], got {tuple(x.shape)}")
+    if not x.permute(0, 2, 3, 1).is_contiguous():
+        raise ValueError(f"{name} must be dense channels_last (NHWC) memory")
+    N, Cc, H, W = x.shape
+    return N, H * W, Cc
+
+
+_GN_WS: dict = {}
+
+
+def _gn_workspace(N: int, G: int, device) -> torch.Tensor:
+    """Statistics workspace of ff_group_norm_nhwc, one per (device, stream): consecutive calls on a stream are ordered,
+    so the buffer is safely reused."""
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    need = int(_lib.load().ff_group_norm_ws_bytes(N, G))
+    ws = _GN_WS.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=device)
+        _GN_WS[key] = ws
+    return ws
+
+
+def group_norm_nhwc(x, gamma, beta, groups, eps, add_nc=None, silu=False):
+    """act(GroupNorm(x + add_nc[:, :, None, None])) on a channels_last bf16 [N,C,H,W] tensor -> same shape / strides.
+    add_nc: fp32 [N,C] or None.  See ff_group_norm_nhwc."""
+    N, HW, Cc = _nhwc_view(x, "x")
+    _chk(gamma, torch.bfloat16, "gamma", 1)
+    _chk(beta, torch.bfloat16, "beta", 1)
+    if gamma.numel() != Cc or beta.numel() != Cc:
+        raise ValueError("gamma / beta must have C elements")
+    if add_nc is not None:
+        _chk(add_nc, torch.float32, "add_nc", 2)
+        if tuple(add_nc.shape) != (N, Cc):
+            raise ValueError(f"add_nc must be [{N},{Cc}], got {tuple(add_nc.shape)}")
+    y = torch.empty_like(x)             # preserves the channels_last strides
+    ws = _gn_workspace(N, groups, x.device)
+    rc = _lib.load().ff_group_norm_nhwc(_ptr(x), _ptr(add_nc), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(ws), N, HW, Cc,
+                                        groups, float(eps), int(bool(silu)), _stream())
+    _lib.check(rc, "ff_group_norm_nhwc")
+    _count("ff_group_norm_nhwc")
+    return y
+
+
+def bias_residual_nhwc(h, bias=None, res=None):
+    """h + bias[None,:,None,None] + res on channels_last bf16 [N,C,H,W] tensors, written in place into h."""
+    N, HW, Cc = _nhwc_view(h, "h")
+    if bias is not None:
+        _chk(bias, torch.bfloat16, "bias", 1)
+        if bias.numel() != Cc:
+            raise ValueError("bias must have C elements")
+    if res is not None:
+        if _nhwc_view(res, "res") != (N, HW, Cc):
+            raise ValueError("res must have the shape of h")
+    rc = _lib.load().ff_bias_residual_nhwc(_ptr(h), _ptr(bias), _ptr(res), _ptr(h), N * HW, Cc, _stream())
+    _lib.check(rc, "ff_bias_residual_nhwc")
+    _count("ff_bias_residual_nhwc")
+    return h
+
+
+def geglu(h):
+    """h bf16 [..., 2F] -> h[..., :F] * gelu(h[..., F:]) (erf gelu).  See ff_geglu."""
+    _chk(h, torch.bfloat16, "h")
+    F2 = h.shape[-1]
+    if F2 % 2:
+        raise ValueError("last dim must be even")
+    M = h.numel() // F2
+    out = torch.empty(*h.shape[:-1], F2 // 2, dtype=h.dtype, device=h.device)
+    rc = _lib.load().ff_geglu(_ptr(h), _ptr(out), M, F2 // 2, _stream())
+    _lib.check(rc, "ff_geglu")
+    _count("ff_geglu")
+    return out
+
+
+def layer_norm(x, gamma, beta, eps):
+    """LayerNorm over the last dim of a contiguous bf16 tensor.  See ff_layer_norm."""
+    _chk(x, torch.bfloat16, "x")
+    Cc = x.shape[-1]
+    _chk(gamma, torch.bfloat16, "gamma", 1)
+    _chk(beta, torch.bfloat16, "beta", 1)
+    if gamma.numel() != Cc or beta.numel() != Cc:
+        raise ValueError("gamma / beta must have C elements")
+    y = torch.empty_like(x)
+    rc = _lib.load().ff_layer_norm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), x.numel() // Cc, Cc, float(eps), _stream())
+    _lib.check(rc, "ff_layer_norm")
+    _count("ff_layer_norm")
+    return y
+
+
 def to_device_bytes(arr: np.ndarray, device) -> torch.Tensor:
     """numpy structured array -> uint8 CUDA tensor (pinned staging, asynchronous copy on the current stream)."""
     t = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1))

@@ -19,6 +19,53 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import ops
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Channels-last fast path.  On CUDA in bf16 every activation of the UNet body stays dense NHWC
+# (torch channels_last == the [B, S, C] token layout of the transformer blocks, so the permutes are views and cuDNN
+# runs its NHWC kernels without layout conversions), and the elementwise / normalisation traffic between the library
+# convolutions and GEMMs goes through the fused sm_100a kernels of csrc/unet_glue.cu.  Same weights, same dataflow;
+# the plain PyTorch forward below it is what runs on CPU (oracle side) and in fp32.
+# --------------------------------------------------------------------------------------------------------------
+FAST_PATH = True      # bench.py --plain-unet switches the fast path off for an A/B measurement
+
+
+def _fast(x: torch.Tensor) -> bool:
+    return FAST_PATH and x.is_cuda and x.dtype == torch.bfloat16
+
+
+def _gn(x, norm: nn.GroupNorm, add_nc=None, silu=False):
+    return ops.group_norm_nhwc(x, norm.weight, norm.bias, norm.num_groups, norm.eps, add_nc=add_nc, silu=silu)
+
+
+def _ln(x, norm: nn.LayerNorm):
+    return ops.layer_norm(x, norm.weight, norm.bias, norm.eps)
+
+
+def _conv(x, conv: nn.Conv2d, bias=True, res=None):
+    """cuDNN NHWC convolution without its separate bias pass; bias (+ skip connection) in one fused pass."""
+    if conv.out_channels % 8:          # conv_out (4 latent channels): rows are not 16-byte multiples, tiny tensor
+        h = F.conv2d(x, conv.weight, conv.bias if bias else None, conv.stride, conv.padding)
+        return h if res is None else h + res
+    h = F.conv2d(x, conv.weight, None, conv.stride, conv.padding)
+    if bias or res is not None:
+        h = ops.bias_residual_nhwc(h, conv.bias if bias else None, res)
+    return h
+
+
+def _tokens(x):
+    """channels_last [N,C,H,W] -> [N, H*W, C] view."""
+    n, c, h, w = x.shape
+    return x.permute(0, 2, 3, 1).reshape(n, h * w, c)
+
+
+def _image(t, h, w):
+    """[N, H*W, C] -> channels_last [N,C,H,W] view."""
+    n, _, c = t.shape
+    return t.reshape(n, h, w, c).permute(0, 3, 1, 2)
+
 
 # --------------------------------------------------------------------------------------------------------------
 # Attention (class name must be literally 'Attention': reference attention.py:434)
@@ -78,6 +125,8 @@ class GEGLU(nn.Module):
         self.proj = nn.Linear(dim_in, dim_out * 2)
 
     def forward(self, x):
+        if _fast(x):
+            return ops.geglu(self.proj(x))
         x, gate = self.proj(x).chunk(2, dim=-1)
         return x * F.gelu(gate)
 
@@ -104,6 +153,10 @@ class BasicTransformerBlock(nn.Module):
         self.ff = FeedForward(dim)
 
     def forward(self, x, encoder_hidden_states=None):
+        if _fast(x):
+            x = self.attn1(_ln(x, self.norm1)) + x
+            x = self.attn2(_ln(x, self.norm2), encoder_hidden_states=encoder_hidden_states) + x
+            return self.ff(_ln(x, self.norm3)) + x
         x = self.attn1(self.norm1(x)) + x
         x = self.attn2(self.norm2(x), encoder_hidden_states=encoder_hidden_states) + x
         x = self.ff(self.norm3(x)) + x
@@ -121,6 +174,13 @@ class Transformer2DModel(nn.Module):
 
     def forward(self, x, encoder_hidden_states=None):
         b, c, h, w = x.shape
+        if _fast(x):
+            # 1x1 convolutions are GEMMs over the token view (bias in the cuBLASLt epilogue); no permute copies
+            t = F.linear(_tokens(_gn(x, self.norm)), self.proj_in.weight.reshape(c, c), self.proj_in.bias)
+            for blk in self.transformer_blocks:
+                t = blk(t, encoder_hidden_states=encoder_hidden_states)
+            t = F.linear(t, self.proj_out.weight.reshape(c, c), self.proj_out.bias)
+            return _image(t, h, w) + x
         res = x
         x = self.proj_in(self.norm(x))
         x = x.permute(0, 2, 3, 1).reshape(b, h * w, c)
@@ -141,6 +201,14 @@ class ResnetBlock2D(nn.Module):
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
     def forward(self, x, temb):
+        if _fast(x):
+            h = _conv(_gn(x, self.norm1, silu=True), self.conv1, bias=False)
+            # conv1 bias + projected time embedding: one [N, C] addend folded into the statistics / apply of norm2
+            cb = (self.time_emb_proj(F.silu(temb)).float() + self.conv1.bias.float()).contiguous()
+            h = _gn(h, self.norm2, add_nc=cb, silu=True)
+            if self.conv_shortcut is not None:
+                x = _conv(x, self.conv_shortcut)
+            return _conv(h, self.conv2, res=x)
         h = self.conv1(F.silu(self.norm1(x)))
         h = h + self.time_emb_proj(F.silu(temb))[:, :, None, None]
         h = self.conv2(F.silu(self.norm2(h)))
@@ -155,7 +223,7 @@ class Downsample2D(nn.Module):
         self.conv = nn.Conv2d(ch, ch, 3, stride=2, padding=1)
 
     def forward(self, x):
-        return self.conv(x)
+        return _conv(x, self.conv) if _fast(x) else self.conv(x)
 
 
 class Upsample2D(nn.Module):
@@ -168,7 +236,7 @@ class Upsample2D(nn.Module):
             x = F.interpolate(x, scale_factor=2.0, mode="nearest")
         else:
             x = F.interpolate(x, size=tuple(output_size), mode="nearest")
-        return self.conv(x)
+        return _conv(x, self.conv) if _fast(x) else self.conv(x)
 
 
 class CrossAttnDownBlock2D(nn.Module):
@@ -372,7 +440,14 @@ class UNet2DConditionModel(nn.Module):
             timesteps = timesteps[None].to(sample.device)
         timesteps = timesteps.expand(sample.shape[0])
         emb = self.time_embedding(self.time_proj(timesteps).to(self.dtype))
-        sample = self.conv_in(sample)
+        fast = _fast(sample)
+        if fast:
+            if not getattr(self, "_nhwc_weights", False):       # once: 4-D weights to channels_last for cuDNN
+                self.to(memory_format=torch.channels_last)
+                self._nhwc_weights = True
+            sample = _conv(sample.contiguous(memory_format=torch.channels_last), self.conv_in)
+        else:
+            sample = self.conv_in(sample)
         res = (sample,)
         for blk in self.down_blocks:
             if blk.has_cross_attention:
@@ -389,6 +464,8 @@ class UNet2DConditionModel(nn.Module):
                              encoder_hidden_states=encoder_hidden_states)
             else:
                 sample = blk(hidden_states=sample, temb=emb, res_hidden_states_tuple=r)
+        if fast:
+            return _conv(_gn(sample, self.conv_norm_out, silu=True), self.conv_out).contiguous()   # NCHW for the caller
         return self.conv_out(self.conv_act(self.conv_norm_out(sample)))
 
 

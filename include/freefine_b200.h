@@ -189,6 +189,40 @@ int ff_ddim_inv_step(const float* eps, const float* x, float sqrt_1m_at, float s
 int ff_cross_region_blend(void* hs, const uint32_t* bitmasks, int32_t mask_words, const int32_t* region_mask,
                           int32_t n_edits, int32_t S, int32_t C, int32_t dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * UNet-body glue in channels-last layout ("bf16/channels_last UNet").  HBM-bound.
+ *
+ * The reference runs diffusers' UNet blocks eagerly (src/utils/attention.py:13-223 `override_forward` walks
+ * down_blocks / mid_block / up_blocks; diffusers ResnetBlock2D, Transformer2DModel, BasicTransformerBlock, GEGLU):
+ * conv -> +bias -> +temb -> GroupNorm -> SiLU, permute copies around every transformer, LayerNorm x3, gelu * x.
+ * These entry points fuse that elementwise / normalisation traffic; every activation is bf16 [N, H*W, C] with the
+ * channel index contiguous (torch channels_last == the [B, S, C] token layout of the attention layers).
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* y = act(GroupNorm_G(x + add_nc[n, c])) : x, y bf16 [N, HW, C]; add_nc fp32 [N, C] or NULL (conv bias + projected
+ * time embedding of ResnetBlock2D); gamma, beta bf16 [C]; fp32 statistics over (HW, C/G) per (n, group), biased
+ * variance, eps inside the square root (torch.nn.GroupNorm); silu != 0 fuses x*sigmoid(x).  `workspace`: at least
+ * ff_group_norm_ws_bytes(N, G) bytes, 16-byte aligned, contents irrelevant.  C % 8 == 0, C % G == 0.            */
+int64_t ff_group_norm_ws_bytes(int32_t N, int32_t G);
+int ff_group_norm_nhwc(const void* x, const float* add_nc, const void* gamma, const void* beta, void* y,
+                       void* workspace, int32_t N, int32_t HW, int32_t C, int32_t G, float eps, int32_t silu,
+                       void* stream);
+
+/* out[m, c] = h[m, c] + bias[c] + res[m, c] : bf16 [M, C]; bias bf16 [C] or NULL, res bf16 [M, C] or NULL (conv
+ * bias + skip connection of ResnetBlock2D / Down- / Upsample2D in one pass); out may alias h or res.            */
+int ff_bias_residual_nhwc(const void* h, const void* bias, const void* res, void* out, int64_t M, int32_t C,
+                          void* stream);
+
+/* GEGLU (diffusers attention.py GEGLU.forward: hidden, gate = proj(x).chunk(2, -1); hidden * gelu(gate)):
+ * h bf16 [M, 2F] -> out bf16 [M, F] = h[:, :F] * gelu_erf(h[:, F:]), gelu(gate) rounded to bf16 before the multiply
+ * exactly like the eager pair of kernels.  F % 8 == 0.                                                          */
+int ff_geglu(const void* h, void* out, int64_t M, int32_t F, void* stream);
+
+/* y = LayerNorm(x) over the last dim: x, y bf16 [M, C], gamma / beta bf16 [C], fp32 statistics, biased variance
+ * (torch.nn.LayerNorm).  C % 8 == 0, C <= 2048.                                                                 */
+int ff_layer_norm(const void* x, const void* gamma, const void* beta, void* y, int64_t M, int32_t C, float eps,
+                  void* stream);
+
 /* Debugging aid, not used by the product path: progress trace of ff_attn_masked_kv into a device-visible buffer of
  * 8 uint32 per CTA (see csrc/attn_tcgen05.cu); NULL switches it off.                                              */
 int ff_debug_set_trace(void* device_visible_ptr);

@@ -7,6 +7,7 @@ K copy + padded fp16 V written + the int64 row index."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+import torch.nn.functional as F
 from freefine_b200 import ops
 
 dev = torch.device("cuda:0")
@@ -65,5 +66,46 @@ byt = 2 * kk.numel() * 2 + kk.numel() * 2 + B * S * heads * 48 * 2 + idx.numel()
 res["kv_gather_cast"] = dict(rows=B * S, bytes=byt, ms_best=best, ms_median=med, gbs=byt / best / 1e6, frac=byt / best / 1e6 / peak,
                              note="random row permutation (640-byte rows), output allocation inside the timed call")
 del kk, vv
+# UNet-body glue (csrc/unet_glue.cu) at the sizes of one 32-stream sampling call of the 512^2 batch (E = 8 edits):
+# ALGORITHMIC bytes = each tensor once: GroupNorm x read + y written (the second read of x is meant to hit L2),
+# bias+residual h, res read + out written, GEGLU [M,2F] read + [M,F] written, LayerNorm x read + y written.
+def _nhwc(n, c, h, w):
+    return torch.randn(n, c, h, w, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+
+
+for (n, c, hh, ww, G) in ((32, 320, 64, 64, 32), (32, 640, 32, 32, 32), (32, 960, 64, 64, 32)):
+    xg = _nhwc(n, c, hh, ww)
+    ga, be = torch.ones(c, device=dev).bfloat16(), torch.zeros(c, device=dev).bfloat16()
+    add = torch.randn(n, c, device=dev)
+    best, med = timeit(lambda: ops.group_norm_nhwc(xg, ga, be, G, 1e-5, add_nc=add, silu=True))
+    byt = 2 * xg.numel() * 2
+    res[f"group_norm_silu_nhwc_{n}x{c}x{hh}x{ww}"] = dict(bytes=byt, ms_best=best, ms_median=med, gbs=byt / best / 1e6,
+                                                          frac=byt / best / 1e6 / peak, note="2 launches (statistics, apply); output allocation inside the timed call")
+    ref = lambda: F.silu(F.group_norm(xg, G, ga, be, 1e-5))
+    b2, _ = timeit(ref)
+    res[f"group_norm_silu_nhwc_{n}x{c}x{hh}x{ww}"]["eager_ms_best"] = b2
+    if c == 320:
+        r2 = _nhwc(n, c, hh, ww)
+        best, med = timeit(lambda: ops.bias_residual_nhwc(xg, ga, r2))
+        byt = 3 * xg.numel() * 2
+        res["bias_residual_nhwc"] = dict(bytes=byt, ms_best=best, ms_median=med, gbs=byt / best / 1e6, frac=byt / best / 1e6 / peak)
+        del r2
+    del xg
+hg = torch.randn(32, 4096, 2560, device=dev).bfloat16()
+best, med = timeit(lambda: ops.geglu(hg))
+byt = hg.numel() * 2 * 3 // 2
+res["geglu_32x4096x2560"] = dict(bytes=byt, ms_best=best, ms_median=med, gbs=byt / best / 1e6, frac=byt / best / 1e6 / peak)
+xa, ga2 = hg.chunk(2, dim=-1)
+b2, _ = timeit(lambda: xa * F.gelu(ga2))
+res["geglu_32x4096x2560"]["eager_ms_best"] = b2
+del hg, xa, ga2
+xl = torch.randn(32, 4096, 320, device=dev).bfloat16()
+ga, be = torch.ones(320, device=dev).bfloat16(), torch.zeros(320, device=dev).bfloat16()
+best, med = timeit(lambda: ops.layer_norm(xl, ga, be, 1e-5))
+byt = 2 * xl.numel() * 2
+res["layer_norm_32x4096x320"] = dict(bytes=byt, ms_best=best, ms_median=med, gbs=byt / best / 1e6, frac=byt / best / 1e6 / peak)
+b2, _ = timeit(lambda: F.layer_norm(xl, (320,), ga, be, 1e-5))
+res["layer_norm_32x4096x320"]["eager_ms_best"] = b2
+del xl
 res["peak_hbm_gbs"] = peak
 print(json.dumps(res, indent=1))

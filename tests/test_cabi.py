@@ -21,7 +21,7 @@ def lib():
 
 def test_header_symbols_exported(lib):
     hdr = open(os.path.join(ROOT, "include", "freefine_b200.h")).read()
-    declared = set(re.findall(r"^\s*(?:int|const char\*)\s+(ff_\w+)\s*\(", hdr, re.M))
+    declared = set(re.findall(r"^\s*(?:int|int64_t|const char\*)\s+(ff_\w+)\s*\(", hdr, re.M))
     assert declared == set(_lib.SIGNATURES), (declared, set(_lib.SIGNATURES))
     for name in declared:
         assert hasattr(lib, name), name

@@ -1,0 +1,155 @@
+"""sm_100a UNet-body glue kernels (csrc/unet_glue.cu) through the C ABI against torch restatements of their documented
+semantics (the same restatements that pin the host-side dataflow on CPU, tests/test_unet_fast_cpu.py), and the
+channels-last fast path of the stand-in UNet against its plain PyTorch forward.
+Tolerances: outputs are bf16 (half-ulp 2^-9 = 2e-3 relative) computed from fp32 statistics: rtol 8e-3 (two ulps), atol
+2e-3; the UNet fast path must be at least as close to the fp32 forward as the eager bf16 forward is."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from test_unet_fast_cpu import ref_bias_residual_nhwc, ref_geglu, ref_group_norm_nhwc, ref_layer_norm
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 8e-3, 2e-3
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from freefine_b200 import _lib
+    _lib.load()
+    return torch.device("cuda:0")
+
+
+def _nhwc(n, c, h, w, dev, seed, scale=1.0, shift=0.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = (torch.randn(n, c, h, w, generator=g) * scale + shift).to(dev).bfloat16()
+    return x.contiguous(memory_format=torch.channels_last)
+
+
+GN_SHAPES = [
+    # N, C, H, W, G
+    (2, 80, 8, 8, 16),        # tiny preset: 5 channels per group (vectors straddle groups)
+    (3, 240, 16, 16, 16),     # 15 per group
+    (2, 320, 64, 64, 32),     # SD1.5 64x64
+    (2, 2560, 8, 8, 32),      # up-block concat: more channel vectors than threads
+    (1, 960, 64, 64, 32),     # 30 per group
+    (2, 640, 24, 24, 32),     # ragged pixel chunks (768^2 mid resolution)
+    (1, 320, 96, 96, 32),     # 768^2: chunk count capped
+    (5, 1280, 1, 1, 32),      # single pixel
+]
+
+
+@pytest.mark.parametrize("shape", GN_SHAPES)
+@pytest.mark.parametrize("silu,with_add", [(False, False), (True, True), (True, False)])
+def test_group_norm_nhwc(dev, shape, silu, with_add):
+    from freefine_b200 import ops
+    n, c, h, w, G = shape
+    x = _nhwc(n, c, h, w, dev, 11, scale=1.7, shift=0.4)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    gamma = (1 + 0.3 * torch.randn(c, generator=g)).to(dev).bfloat16()
+    beta = (0.2 * torch.randn(c, generator=g)).to(dev).bfloat16()
+    add = (0.8 * torch.randn(n, c, generator=g)).to(dev) if with_add else None
+    x0 = x.clone()
+    got = ops.group_norm_nhwc(x, gamma, beta, G, 1e-5, add_nc=add, silu=silu)
+    want = ref_group_norm_nhwc(x, gamma, beta, G, 1e-5, add_nc=add, silu=silu)
+    assert torch.equal(x, x0)
+    assert got.shape == x.shape and got.stride() == x.stride() and got.dtype == torch.bfloat16
+    torch.testing.assert_close(got.float(), want.float(), rtol=RTOL, atol=ATOL)
+    # bit-reproducible run to run (fixed summation order)
+    assert torch.equal(got, ops.group_norm_nhwc(x, gamma, beta, G, 1e-5, add_nc=add, silu=silu))
+
+
+def test_group_norm_large_mean(dev):
+    """|mean| >> std: the one-pass E[x^2] - E[x]^2 statistics stay inside tolerance at the offsets bf16 inputs allow."""
+    from freefine_b200 import ops
+    x = _nhwc(2, 320, 32, 32, dev, 3, scale=1.0, shift=30.0)
+    w = torch.ones(320, device=dev).bfloat16()
+    b = torch.zeros(320, device=dev).bfloat16()
+    got = ops.group_norm_nhwc(x, w, b, 32, 1e-5)
+    want = ref_group_norm_nhwc(x, w, b, 32, 1e-5)
+    torch.testing.assert_close(got.float(), want.float(), rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("shape", [(2, 80, 8, 8), (3, 320, 64, 64), (2, 1280, 16, 16), (1, 2560, 8, 8)])
+@pytest.mark.parametrize("with_bias,with_res", [(True, True), (True, False), (False, True)])
+def test_bias_residual_nhwc(dev, shape, with_bias, with_res):
+    from freefine_b200 import ops
+    n, c, h, w = shape
+    hh = _nhwc(n, c, h, w, dev, 21)
+    res = _nhwc(n, c, h, w, dev, 22) if with_res else None
+    bias = torch.randn(c, device=dev).bfloat16() if with_bias else None
+    want = ref_bias_residual_nhwc(hh.clone(), bias, res)
+    got = ops.bias_residual_nhwc(hh, bias, res)
+    assert got.data_ptr() == hh.data_ptr()
+    torch.testing.assert_close(got.float(), want.float(), rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("M,Fdim", [(77, 320), (4096, 1280), (231, 640), (64, 5120), (3, 8)])
+def test_geglu(dev, M, Fdim):
+    from freefine_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(31)
+    h = (2.5 * torch.randn(2, M, 2 * Fdim, generator=g)).to(dev).bfloat16()
+    got = ops.geglu(h)
+    want = ref_geglu(h)
+    assert got.shape == (2, M, Fdim)
+    torch.testing.assert_close(got.float(), want.float(), rtol=RTOL, atol=ATOL)
+    # the eager pair of kernels this replaces (same operation order and intermediate rounding)
+    x, gate = h.chunk(2, dim=-1)
+    eager = x * F.gelu(gate)
+    torch.testing.assert_close(got.float(), eager.float(), rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("M,C", [(231, 80), (4096, 320), (1024, 640), (257, 1280), (16, 2048), (9, 8), (100, 160)])
+def test_layer_norm(dev, M, C):
+    from freefine_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(41)
+    x = (1.3 * torch.randn(2, M, C, generator=g) + 0.5).to(dev).bfloat16()
+    gamma = (1 + 0.3 * torch.randn(C, generator=g)).to(dev).bfloat16()
+    beta = (0.2 * torch.randn(C, generator=g)).to(dev).bfloat16()
+    got = ops.layer_norm(x, gamma, beta, 1e-5)
+    want = ref_layer_norm(x, gamma, beta, 1e-5)
+    torch.testing.assert_close(got.float(), want.float(), rtol=RTOL, atol=ATOL)
+
+
+def test_invalid_shapes_fail_loudly(dev):
+    from freefine_b200 import ops
+    x = _nhwc(2, 84, 8, 8, dev, 1)          # 84 channels: rows are not 16-byte multiples
+    w = torch.ones(84, device=dev).bfloat16()
+    with pytest.raises(RuntimeError):
+        ops.group_norm_nhwc(x, w, w, 4, 1e-5)
+    with pytest.raises(ValueError):
+        ops.group_norm_nhwc(x.contiguous(), w, w, 4, 1e-5)      # NCHW memory
+    with pytest.raises(TypeError):
+        ops.layer_norm(torch.zeros(4, 32, device=dev), w, w, 1e-5)
+
+
+@pytest.mark.parametrize("hw", [16, 32])
+def test_unet_fast_path_matches_plain(dev, hw, monkeypatch):
+    """bf16 channels-last fast path vs the fp32 plain forward of the same weights; the eager bf16 forward is the yard
+    stick (the fused kernels round less often than the eager chain, so they must not be further away)."""
+    from freefine_b200 import ops, standin
+    g = torch.Generator(device="cpu").manual_seed(9)
+    parts32 = standin.build_standin("tiny", device=dev)
+    parts16 = standin.build_standin("tiny", device=dev, dtype=torch.bfloat16)
+    x = torch.randn(4, 4, hw, hw, generator=g).to(dev)
+    enc = torch.randn(4, 77, 64, generator=g).to(dev)
+    t = torch.tensor(321, device=dev)
+    with torch.no_grad():
+        want = parts32.unet(x, t, enc)
+        before = dict(ops.COUNTS)
+        fast = parts16.unet(x.bfloat16(), t, enc.bfloat16())
+        launched = {k: ops.COUNTS.get(k, 0) - before.get(k, 0) for k in
+                    ("ff_group_norm_nhwc", "ff_bias_residual_nhwc", "ff_geglu", "ff_layer_norm")}
+        monkeypatch.setattr(standin, "_fast", lambda x: False)
+        eager = standin.build_standin("tiny", device=dev, dtype=torch.bfloat16).unet(x.bfloat16(), t, enc.bfloat16())
+    assert fast.is_contiguous() and fast.shape == want.shape
+    # 61 GroupNorms, 16 GEGLUs, 48 LayerNorms per UNet call went through the C ABI
+    assert launched["ff_group_norm_nhwc"] == 61 and launched["ff_geglu"] == 16 and launched["ff_layer_norm"] == 48
+    assert launched["ff_bias_residual_nhwc"] > 0
+    rel = lambda a: float((a.float() - want).norm() / want.norm())
+    e_fast, e_eager = rel(fast), rel(eager)
+    print(f"rel-L2 vs fp32: fast {e_fast:.3e}  eager bf16 {e_eager:.3e}")
+    assert e_fast < 3e-2 and e_fast <= 1.25 * e_eager + 1e-3, (e_fast, e_eager)

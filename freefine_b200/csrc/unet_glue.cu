@@ -94,17 +94,24 @@ gn_stats_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_
     }
   }
   __syncthreads();
-  const int cpg = C / G;
-  for (int g = threadIdx.x; g < G; g += GN_THREADS) {
+  // one warp per group: lanes stride over the (row slot, channel) pairs, butterfly reduction -- a fixed order, so the
+  // result is bit-reproducible
+  const int cpg = C / G, cnt = L.R * cpg;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int g = warp; g < G; g += GN_THREADS / 32) {
     float S = 0.f, SS = 0.f;
-    for (int rr = 0; rr < L.R; ++rr) {          // fixed order: reproducible
-      const float* src = sm + (size_t)rr * 2 * C + g * cpg;
-      for (int c = 0; c < cpg; ++c) {
-        S += src[c];
-        SS += src[C + c];
-      }
+    for (int i = lane; i < cnt; i += 32) {
+      const int rr = i / cpg, c = i - rr * cpg;
+      const float* src = sm + (size_t)rr * 2 * C + g * cpg + c;
+      S += src[0];
+      SS += src[C];
     }
-    partial[((size_t)n * n_chunks + chunk) * G + g] = make_float2(S, SS);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      S += __shfl_xor_sync(0xffffffffu, S, o);
+      SS += __shfl_xor_sync(0xffffffffu, SS, o);
+    }
+    if (lane == 0) partial[((size_t)n * n_chunks + chunk) * G + g] = make_float2(S, SS);
   }
 }
 
@@ -121,17 +128,29 @@ gn_apply_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_
   const int n = blockIdx.y, chunk = blockIdx.x;
   const int cpg = C / G;
   const float inv_cnt = 1.f / ((float)cpg * (float)HW);
-  for (int g = threadIdx.x; g < G; g += GN_THREADS) {
-    float S = 0.f, SS = 0.f;
-    for (int ch = 0; ch < n_chunks; ++ch) {     // fixed order: every CTA of image n derives identical statistics
-      const float2 t = __ldg(partial + ((size_t)n * n_chunks + ch) * G + g);
-      S += t.x;
-      SS += t.y;
+  {
+    // one warp per group, one chunk per lane (n_chunks <= 64), butterfly reduction: the loads are independent (one
+    // latency instead of n_chunks) and every CTA of image n derives bit-identical statistics
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int g = warp; g < G; g += GN_THREADS / 32) {
+      float S = 0.f, SS = 0.f;
+      for (int ch = lane; ch < n_chunks; ch += 32) {
+        const float2 t = __ldg(partial + ((size_t)n * n_chunks + ch) * G + g);
+        S += t.x;
+        SS += t.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        S += __shfl_xor_sync(0xffffffffu, S, o);
+        SS += __shfl_xor_sync(0xffffffffu, SS, o);
+      }
+      if (lane == 0) {
+        const float m = S * inv_cnt;
+        const float var = fmaxf(SS * inv_cnt - m * m, 0.f);
+        mean[g] = m;
+        rstd[g] = 1.f / sqrtf(var + eps);
+      }
     }
-    const float m = S * inv_cnt;
-    const float var = fmaxf(SS * inv_cnt - m * m, 0.f);
-    mean[g] = m;
-    rstd[g] = 1.f / sqrtf(var + eps);
   }
   __syncthreads();
   if (L.r >= L.R) return;
@@ -156,7 +175,7 @@ gn_apply_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float t = fmaf(f[j], sc[j], sh[j]);
-        if (SILU) t = t / (1.f + __expf(-t));
+        if (SILU) t = __fdividef(t, 1.f + __expf(-t));     // 2 MUFU ops; the IEEE division made this kernel ALU-bound
         f[j] = t;
       }
       *py = pack8(f);
@@ -189,8 +208,24 @@ bias_residual_kernel(const uint4* __restrict__ h, const __nv_bfloat16* __restric
   }
 }
 
-// out[m, f] = x * gelu(gate), x = h[m, f], gate = h[m, F + f]; gelu = erf form, in ATen's operation order and with
-// ATen's intermediate bf16 rounding of gelu(gate) (eager: F.gelu -> bf16 tensor, then a bf16 multiply).
+// out[m, f] = x * gelu(gate), x = h[m, f], gate = h[m, F + f]; gelu = erf form, with the intermediate bf16 rounding of
+// gelu(gate) of the eager pair of kernels (F.gelu -> bf16 tensor, then a bf16 multiply).
+// gelu(g) = g * Phi(g), Phi from erfc(z) = t*(a1 + t*(a2 + t*(a3 + t*(a4 + t*a5)))) * exp(-z^2), t = 1/(1 + p z), z =
+// |g|/sqrt(2)  (Abramowitz & Stegun 7.1.26, absolute error 1.5e-7 -- four orders below the bf16 rounding of the result):
+// 2 MUFU ops + ~12 FMA-pipe ops per element instead of libdevice erff's ~30, which made the kernel ALU-bound.
+__device__ __forceinline__ float gelu_erf(float g) {
+  const float z = fabsf(g) * 0.70710678118654752440f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
+  const float half_erfc = 0.5f * p * t * e;                                      // 0.5 * erfc(|g|/sqrt 2)
+  return g * (g >= 0.f ? 1.f - half_erfc : half_erfc);
+}
+
 __global__ void __launch_bounds__(256)
 geglu_kernel(const uint4* __restrict__ h, uint4* __restrict__ out, long long total, int FV) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -202,66 +237,71 @@ geglu_kernel(const uint4* __restrict__ h, uint4* __restrict__ out, long long tot
     unpack8(__ldg(row + v), x);
     unpack8(__ldg(row + FV + v), g);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float ge = bf16_round(g[j] * 0.5f * (1.f + erff(g[j] * 0.70710678118654752440f)));
-      x[j] *= ge;
-    }
+    for (int j = 0; j < 8; ++j) x[j] *= bf16_round(gelu_erf(g[j]));
     out[i] = pack8(x);
   }
 }
 
-// One warp per row of C = 8*CV channels (CV <= 32*VPL): the row stays in registers, mean then centred variance.
-template <int VPL>
+// One warp per ROWS consecutive rows of C = 8*CV channels (CV <= 32*VPL): all row loads are issued before the first
+// reduction (memory-level parallelism: a single 640-byte row per warp left the kernel latency-bound), each row stays in
+// registers for its mean, centred variance and output.
+template <int VPL, int ROWS>
 __global__ void __launch_bounds__(256)
 layer_norm_kernel(const uint4* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
                   const __nv_bfloat16* __restrict__ beta, uint4* __restrict__ y, long long M, int CV, float eps) {
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
-  const uint4* px = x + row * CV;
-  float f[VPL][8];
-  float s = 0.f;
+  const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS;
+  if (row0 >= M) return;
+  uint4 raw[ROWS][VPL];
 #pragma unroll
-  for (int k = 0; k < VPL; ++k) {
-    const int v = lane + 32 * k;
-    if (v < CV) {
-      unpack8(__ldg(px + v), f[k]);
+  for (int r = 0; r < ROWS; ++r) {
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int v = lane + 32 * k;
+      raw[r][k] = (row0 + r < M && v < CV) ? __ldg(x + (row0 + r) * CV + v) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  const float inv_c = 1.f / (float)(8 * CV);
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    if (row0 + r >= M) break;                    // warp-uniform
+    float f[VPL][8];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      unpack8(raw[r][k], f[k]);                  // (vectors beyond CV are zeros: they add nothing to the sum)
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += f[k][j];
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[k][j] = 0.f;
     }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float inv_c = 1.f / (float)(8 * CV);
-  const float mean = s * inv_c;
-  float ss = 0.f;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * inv_c;
+    float ss = 0.f;
 #pragma unroll
-  for (int k = 0; k < VPL; ++k) {
-    if (lane + 32 * k < CV) {
+    for (int k = 0; k < VPL; ++k) {
+      if (lane + 32 * k < CV) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = f[k][j] - mean;
-        ss = fmaf(d, d, ss);
+        for (int j = 0; j < 8; ++j) {
+          const float d = f[k][j] - mean;
+          ss = fmaf(d, d, ss);
+        }
       }
     }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  const float rstd = 1.f / sqrtf(ss * inv_c + eps);
-  uint4* py = y + row * CV;
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = 1.f / sqrtf(ss * inv_c + eps);
+    uint4* py = y + (row0 + r) * CV;
 #pragma unroll
-  for (int k = 0; k < VPL; ++k) {
-    const int v = lane + 32 * k;
-    if (v < CV) {
-      float ga[8], be[8], o[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + v), ga);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(beta) + v), be);
+    for (int k = 0; k < VPL; ++k) {
+      const int v = lane + 32 * k;
+      if (v < CV) {
+        float ga[8], be[8], o[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + v), ga);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(beta) + v), be);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaf((f[k][j] - mean) * rstd, ga[j], be[j]);
-      py[v] = pack8(o);
+        for (int j = 0; j < 8; ++j) o[j] = fmaf((f[k][j] - mean) * rstd, ga[j], be[j]);
+        py[v] = pack8(o);
+      }
     }
   }
 }
@@ -354,17 +394,18 @@ extern "C" int ff_layer_norm(const void* x, const void* gamma, const void* beta,
   FF_REQUIRE(ff::aligned16(x) && ff::aligned16(y) && ff::aligned16(gamma) && ff::aligned16(beta),
              "ff_layer_norm: pointers must be 16-byte aligned");
   const int CV = C / 8, vpl = (CV + 31) / 32;
-  const long long blocks = (M + 7) / 8;
-  FF_REQUIRE(blocks <= 2147483647LL, "ff_layer_norm: too many rows");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const uint4* xp = static_cast<const uint4*>(x);
   const __nv_bfloat16* gp = static_cast<const __nv_bfloat16*>(gamma);
   const __nv_bfloat16* bp = static_cast<const __nv_bfloat16*>(beta);
   uint4* yp = static_cast<uint4*>(y);
-  if (vpl <= 1) layer_norm_kernel<1><<<(int)blocks, 256, 0, st>>>(xp, gp, bp, yp, M, CV, eps);
-  else if (vpl <= 2) layer_norm_kernel<2><<<(int)blocks, 256, 0, st>>>(xp, gp, bp, yp, M, CV, eps);
-  else if (vpl <= 3) layer_norm_kernel<3><<<(int)blocks, 256, 0, st>>>(xp, gp, bp, yp, M, CV, eps);
-  else if (vpl <= 5) layer_norm_kernel<5><<<(int)blocks, 256, 0, st>>>(xp, gp, bp, yp, M, CV, eps);
-  else layer_norm_kernel<8><<<(int)blocks, 256, 0, st>>>(xp, gp, bp, yp, M, CV, eps);
+  const int rows_per_warp = vpl <= 1 ? 8 : (vpl <= 2 ? 4 : (vpl <= 3 ? 2 : 1));
+  const long long blocks = (M + 8LL * rows_per_warp - 1) / (8LL * rows_per_warp);
+  FF_REQUIRE(blocks <= 2147483647LL, "ff_layer_norm: too many rows");
+  if (vpl <= 1) layer_norm_kernel<1, 8><<<(int)blocks, 256, 0, st>>>(xp, gp, bp, yp, M, CV, eps);
+  else if (vpl <= 2) layer_norm_kernel<2, 4><<<(int)blocks, 256, 0, st>>>(xp, gp, bp, yp, M, CV, eps);
+  else if (vpl <= 3) layer_norm_kernel<3, 2><<<(int)blocks, 256, 0, st>>>(xp, gp, bp, yp, M, CV, eps);
+  else if (vpl <= 5) layer_norm_kernel<5, 1><<<(int)blocks, 256, 0, st>>>(xp, gp, bp, yp, M, CV, eps);
+  else layer_norm_kernel<8, 1><<<(int)blocks, 256, 0, st>>>(xp, gp, bp, yp, M, CV, eps);
   return ff::check_launch("ff_layer_norm");
 }

@@ -1,6 +1,6 @@
 """Achieved HBM bandwidth of the HBM-bound kernels (b) warp+blend and (c) CFG+DDIM step on L2-exceeding synthetic batches
 (at real sizes -- 128 KiB of latents per edit -- these launches are latency-bound, so the roofline is
-demonstrated at n_edits = 2048 / N*C = 32768).  CUDA-event timing, 3 warm-ups, inputs >> 126 MB L2.
+demonstrated at n_edits = 2048 / N*C = 32768).  CUDA-event timing of graph replays, 3 warm-ups, inputs >> 126 MB L2.
 ALGORITHMIC bytes: (c) eps_u, eps_c, x, noise read + x_prev written (5 tensors of 2*4*h*w*4 B per edit) + 2*h*w mask bytes;
 (c-inv) eps, x read + x_next written; (b) src read once + bg read + out written + mask bytes; K/V staging: K, V read,
 K copy + padded fp16 V written + the int64 row index."""
@@ -16,16 +16,42 @@ peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PE
 
 
 def timeit(fn, reps=10):
+    """Per-call device time: `reps` calls captured in ONE CUDA graph and replayed (3 warm-up replays, best / median of 5
+    timed replays, CUDA events on the replay stream), so that the Python / ctypes launch cost (~40 us per call, more than
+    the run time of the smaller kernels) stays outside the measurement.  The buffers are far larger than L2 or, where
+    stated, deliberately L2-sized."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
-    ev[0].record()
-    for i in range(reps):
-        fn()
-        ev[i + 1].record()
+    g = torch.cuda.CUDAGraph()
+    try:
+        with torch.cuda.graph(g):
+            for _ in range(reps):
+                fn()
+    except Exception as e:          # not capturable: eager loop (launch cost included)
+        sys.stderr.write(f"graph capture failed ({e}); eager timing\n")
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+        ev[0].record()
+        for i in range(reps):
+            fn()
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(reps))
+        return ms[0], ms[len(ms) // 2]
+    for _ in range(3):
+        g.replay()
     torch.cuda.synchronize()
-    ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(reps))
+    ms = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1) / reps)
+    ms.sort()
+    del g
     return ms[0], ms[len(ms) // 2]
 
 

@@ -62,7 +62,10 @@ gn_stats_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_
                      int HW, int C, int G, int chunk_px, int n_chunks) {
   extern __shared__ float sm[];                 // [R][2][C] per-row-slot channel sums, then reduced into slot 0
   const GnLayout L(C);
-  const int n = blockIdx.y, chunk = blockIdx.x;
+  // CTAs are dispatched in ascending linear order: the statistics pass walks the tensor from its END -- the part the
+  // producer (convolution / residual kernel) wrote last and most likely still holds in L2 -- towards its beginning, and
+  // the apply pass then walks forwards, starting with what this pass read last.
+  const int n = gridDim.y - 1 - blockIdx.y, chunk = gridDim.x - 1 - blockIdx.x;
   const int p0 = chunk * chunk_px, p1 = min(HW, p0 + chunk_px);
   if (L.r < L.R) {
     for (int v = L.col; v < L.CV; v += L.cols) {

@@ -126,6 +126,25 @@ def run_reference(args):
     _emit(line)
 
 
+def ncu_traffic(sq, skv, d, B):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r1_attn_ncu_summary.txt: the same launch shape, S=4096 d=40 32 streams, run alone by profiles/attn_case.py);
+    {} when the dominant launch of this run has another shape or the summary is absent."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_attn_ncu_summary.txt")
+    if (sq, skv, d, B) != (4096, 4096, 40, 32) or not os.path.exists(path):
+        return {}
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for line in open(path):
+        f = line.split()
+        if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and f[2] in unit:
+            tot += float(f[1]) * unit[f[2]]
+    if tot <= 0:
+        return {}
+    return {"traffic": tot, "traffic_unit": "bytes per launch (DRAM read + write, ncu --set full)",
+            "traffic_source": "profiles/r1_attn_ncu_summary.txt"}
+
+
 def workload_config(args):
     n = args.num_step - args.start_step
     return {"workload": "configs[1]: SD1.5 2D geometric edit (move/rotate/scale) 512x512, 50-step, batch 8 per GPU",
@@ -316,6 +335,7 @@ def run_ours(args):
                 "algorithmic_gflop_per_launch": dg["flops"] / max(dg["n"], 1) / 1e9,
                 "share_of_step": dg["ms"] / (t_dev * 1e3), "all_attention_share_of_step": attn_ms_total / (t_dev * 1e3),
                 "traffic": None}
+    roofline.update(ncu_traffic(sq, skv, d, B))
 
     # ---- B: end to end through the public API with host buffers ------------------------------------------------------
     e2e = None

@@ -4,7 +4,7 @@ import csv, io, os, re, subprocess, sys
 from collections import defaultdict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OUT, PRE = os.path.join(ROOT, "profiles"), os.path.join(ROOT, "gpurun_out", "p_")
+OUT, PRE = os.path.join(ROOT, "profiles"), os.path.join(ROOT, "gpurun_out", os.environ.get("FF_PRE", "p_"))
 TAG = sys.argv[1] if len(sys.argv) > 1 else "r1"
 
 
@@ -20,6 +20,7 @@ def launches():
         name = re.sub(r"\(.*", "", r[ki]).replace("void ", "").replace("<unnamed>::", "")
         name = re.sub(r"(attn_masked_kv_kernel<[^>]*>).*", r"\1", name)
         name = name if "attn_masked" in name or "warp_affine" in name else re.sub(r"<.*", "", name)
+        name = "at::layer_norm (eager)" if name.startswith("at::") and "layer_norm" in name else name
         tot[name][0] += v
         tot[name][1] += 1
     total = sum(v[0] for v in tot.values())
@@ -31,7 +32,8 @@ def launches():
              "# total %.1f ms over %d launches" % (total, n)]
     for name, (ms, c) in sorted(tot.items(), key=lambda kv: -kv[1][0])[:24]:
         lines.append("%9.3f ms %5.1f%%  x%4d  %s" % (ms, 100 * ms / total, c, name[:90]))
-    ours = {k: (round(v[0], 3), v[1]) for k, v in tot.items() if any(s in k for s in ("attn_masked", "warp_affine", "ddim_", "mask_downsample", "cross_region", "kv_gather"))}
+    ours = {k: (round(v[0], 3), v[1]) for k, v in tot.items() if any(s in k for s in ("attn_masked", "warp_affine", "ddim_", "mask_downsample", "cross_region", "kv_gather", "gn_stats", "gn_apply",
+                                                                                      "geglu_kernel", "layer_norm_kernel", "bias_residual"))}
     lines.append("# our kernels (ms, launches): %s" % ours)
     lines.append("# share of our kernels: %.1f%%   share of all ff_attn_masked_kv launches: %.1f%%" % (
         100 * sum(v[0] for v in ours.values()) / total, 100 * sum(v[0] for k, v in ours.items() if "attn_masked" in k) / total))
@@ -86,6 +88,10 @@ def full(rep, out, header):
 
 if __name__ == "__main__":
     launches()
+    if os.environ.get("FF_LAUNCHES_ONLY"):
+        cp = os.path.join(OUT, TAG + "_launches_bench.csv")
+        open(cp, "w").writelines(l for l in open(PRE + "launches_bench.csv") if not l.startswith("=="))
+        sys.exit(0)
     timing = open(PRE + "attn_case_timing.txt").read().strip()
     full(PRE + "attn_full.ncu-rep", os.path.join(OUT, TAG + "_attn_ncu_summary.txt"),
          ["# %s -- ncu --set full --clock-control none, kernel attn_masked_kv_kernel<48,false> of profiles/attn_case.py" % TAG,

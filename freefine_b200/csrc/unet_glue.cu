@@ -309,13 +309,16 @@ layer_norm_kernel(const uint4* __restrict__ x, const __nv_bfloat16* __restrict__
   }
 }
 
-int gn_chunks(int HW, int* chunk_px) {
-  int n_chunks = (HW + 127) / 128;
+// Pixel chunks per image: N * n_chunks CTAs should be ONE full wave (148 SMs x 4 resident CTAs at 64 registers x 256
+// threads) -- 1024 CTAs of 128 pixels ran as 1.7 waves -- with at least 32 pixels per chunk and at most GN_MAX_CHUNKS.
+int gn_chunks(int HW, int N, int* chunk_px) {
+  int n_chunks = (148 * 4 + N - 1) / N;
+  const int max_by_px = HW / 32 > 0 ? HW / 32 : 1;
+  if (n_chunks > max_by_px) n_chunks = max_by_px;
   if (n_chunks > GN_MAX_CHUNKS) n_chunks = GN_MAX_CHUNKS;
   if (n_chunks < 1) n_chunks = 1;
   *chunk_px = (HW + n_chunks - 1) / n_chunks;
-  n_chunks = (HW + *chunk_px - 1) / *chunk_px;
-  return n_chunks;
+  return (HW + *chunk_px - 1) / *chunk_px;
 }
 
 int grid_for(long long total) {
@@ -341,7 +344,7 @@ extern "C" int ff_group_norm_nhwc(const void* x, const float* add_nc, const void
   FF_REQUIRE(ff::aligned16(x) && ff::aligned16(y) && ff::aligned16(workspace),
              "ff_group_norm_nhwc: x / y / workspace must be 16-byte aligned");
   int chunk_px = 0;
-  const int n_chunks = gn_chunks(HW, &chunk_px);
+  const int n_chunks = gn_chunks(HW, N, &chunk_px);
   const int CV = C / 8, cols = CV < GN_THREADS ? CV : GN_THREADS, R = GN_THREADS / cols;
   const size_t smem_stats = (size_t)R * 2 * C * sizeof(float);
   FF_REQUIRE(smem_stats <= 48 * 1024, "ff_group_norm_nhwc: C=%d too large", C);

@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--channels-last", action="store_true", help="run the (library) UNet body in channels_last")
+    ap.add_argument("--cudnn-benchmark", action="store_true", help="A/B only: torch.backends.cudnn.benchmark = True")
     ap.add_argument("--plain-unet", action="store_true",
                     help="A/B only: eager NCHW UNet body instead of the channels-last fast path (csrc/unet_glue.cu)")
     return ap.parse_args()
@@ -228,6 +229,8 @@ def run_ours(args):
     _lib.load()
     torch.backends.cuda.matmul.allow_tf32 = True
     torch.backends.cudnn.allow_tf32 = True
+    if args.cudnn_benchmark:
+        torch.backends.cudnn.benchmark = True
 
     if args.plain_unet:
         import freefine_b200.standin as _standin

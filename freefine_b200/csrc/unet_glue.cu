@@ -14,6 +14,8 @@
 // All accesses are 128-bit; sums are combined in a fixed order (bit-reproducible run to run).
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "ff_common.cuh"
 
 namespace {
@@ -41,6 +43,8 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 
 constexpr int GN_THREADS = 256;
 constexpr int GN_MAX_CHUNKS = 64;     // pixel chunks per image (partial statistics per chunk)
+constexpr int GN_CHUNK_PX = 128;      // pixels per CTA, images of more than 1024 pixels
+constexpr int GN_CHUNK_PX_SMALL = 64;  // ... of at most 1024 pixels
 
 // Thread layout shared by the two GroupNorm kernels: `cols` = min(C/8, 256) threads side by side over the 16-byte
 // channel vectors of a pixel, R = 256 / cols pixel rows in flight; a thread keeps ONE channel vector column at a time,
@@ -309,13 +313,25 @@ layer_norm_kernel(const uint4* __restrict__ x, const __nv_bfloat16* __restrict__
   }
 }
 
-// Pixel chunks per image: 128 pixels per CTA (at most GN_MAX_CHUNKS chunks).  Measured alternative: sizing the chunks so
-// that N * n_chunks CTAs form ONE full wave (148 SMs x 4 resident CTAs) was 10-25 % SLOWER (86 vs 78 us at 32x320x64^2,
-// 266 vs 207 us at 32x960x64^2): with ~1.7 waves of short CTAs the load phase of one CTA overlaps the reduction /
-// write-back phase of another, a single lock-step wave does not.
+// Pixels per CTA (at most GN_MAX_CHUNKS chunks per image).  Measured with profiles/gn_case.py (graph replays, us, 32 images;
+// profiles/r1b_gn_chunk_sweep.txt):        chunk_px   320x64^2   960x64^2   640x32^2   1280x16^2
+//                                               256       76.4      197.1       83.9      125.5
+//                                               128       76.0      203.1       49.3       67.9
+//                                                64       96.3      209.5       43.1       38.9
+//                                                32     (=64: chunk cap)        45.1       25.9
+// Large images want ~128 pixels per CTA (per-CTA prologue: statistics butterfly + per-channel coefficients), small ones
+// want enough CTAs to fill 148 SMs.  Sizing the chunks for exactly ONE wave (148 x 4 CTAs) was 10-25 % slower than 1.7
+// waves of 128-pixel CTAs: the load phase of one CTA then no longer overlaps the reduction / write-back of another.
+// The product rule only uses the two sizes the whole parity suite has run with (64 and 128); FF_GN_CHUNK_PX overrides.
 int gn_chunks(int HW, int N, int* chunk_px) {
   (void)N;
-  int n_chunks = (HW + 127) / 128;
+  static const int forced = [] {
+    const char* e = getenv("FF_GN_CHUNK_PX");
+    const int v = e ? atoi(e) : 0;
+    return (v >= 16 && v <= 1024) ? v : 0;
+  }();
+  const int px = forced ? forced : (HW <= 1024 ? GN_CHUNK_PX_SMALL : GN_CHUNK_PX);
+  int n_chunks = (HW + px - 1) / px;
   if (n_chunks > GN_MAX_CHUNKS) n_chunks = GN_MAX_CHUNKS;
   if (n_chunks < 1) n_chunks = 1;
   *chunk_px = (HW + n_chunks - 1) / n_chunks;

@@ -1050,6 +1050,10 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   }
 }
 
+#ifdef FF_ONE_CTA
+#include "attn_onecta.cuh"      // experimental one-CTA-per-SM variant (not in the product build)
+#endif
+
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
@@ -1106,6 +1110,22 @@ int launch(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, 
   attn_masked_kv_kernel<DPAD, HILO><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(mq, mk, mv, kp);
   return ff::check_launch("ff_attn_masked_kv");
 }
+
+#ifdef FF_ONE_CTA
+int launch_onecta(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const KParams& kp, int n_streams,
+                  cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_onecta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OC::SMEM_BYTES);
+    if (e != cudaSuccess) return ff::fail(FF_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", OC::SMEM_BYTES,
+                                          cudaGetErrorString(e));
+    configured = true;
+  }
+  dim3 grid((kp.s_q + BM - 1) / BM, kp.heads, n_streams);
+  attn_onecta_kernel<<<grid, NUM_THREADS, OC::SMEM_BYTES, st>>>(mq, mk, mv, kp);
+  return ff::check_launch("ff_attn_masked_kv (one-CTA variant)");
+}
+#endif
 
 }  // namespace
 
@@ -1193,6 +1213,9 @@ extern "C" int ff_attn_masked_kv(const FFAttnArgs* a, void* stream) {
   // thresholds leave room for the ones column at channel d inside DPV (see ff_attn_v_head_stride)
   if (v_f16) {
     if (d <= 8) return launch<16, false>(mq, mk, mv, kp, a->n_streams, st);
+#ifdef FF_ONE_CTA
+    if (d <= 40) return launch_onecta(mq, mk, mv, kp, a->n_streams, st);
+#endif
     if (d <= 40) return launch<48, false>(mq, mk, mv, kp, a->n_streams, st);
     if (d <= 80) return launch<80, false>(mq, mk, mv, kp, a->n_streams, st);
     return launch<160, false>(mq, mk, mv, kp, a->n_streams, st);

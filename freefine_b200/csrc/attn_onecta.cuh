@@ -17,6 +17,9 @@
 //     an explicit per-warpgroup barrier o_done, waited for EVERY tile (an mbarrier wait is only exact when the waiter
 //     observes every phase) but late -- after the exp sweep -- when it has normally completed long ago;
 //   * K/V ring of 8 stages (tile t+4's K must be resident while tile t's V is still being read).
+// Next steps once it runs: (1) issue the tcgen05.ld of S(n+1) right after the P(n) store when s_full(n+1) has already
+// completed (mbar_test), so that the only exposed TMEM round trip per tile disappears too; (2) a d = 80 instantiation
+// (4 x 64 + 2 x 96 = 448 columns; a 4-stage K/V ring is what fits beside Q and the cross-pass accumulator).
 // Global tile index `it` (all roles count alike): warpgroup = it & 1, S/P buffer sb(it) = 2*(it&1) + ((it>>1)&1), and the
 // phase parity of s_full[sb] / p_full[sb] for tile it is (it>>2)&1.
 #pragma once

@@ -26,6 +26,9 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <atomic>
+#include <cstdlib>
+
 #include "ff_common.cuh"
 
 namespace {
@@ -48,6 +51,9 @@ template <bool HILO> constexpr float rescale_threshold() { return HILO ? 24.f : 
 // exp2 of pair i (mod 8) of every 16-score chunk goes to the FMA pipe (degree-3 polynomial) instead of the MUFU unit
 // when bit i of this pattern is set: the softmax of the d=40 layers is bound by the 16 ex2/clk/SM of the MUFU unit.
 // 0x92 = 3 pairs of 8 (37.5%): measured best on the S=4096 d=40 launch (2.49 -> 2.37 ms; 25% and 50% are slower).
+#ifndef FF_RING_DEFAULT
+#define FF_RING_DEFAULT 6
+#endif
 #ifndef FF_POLY_PATTERN
 #define FF_POLY_PATTERN 0x92
 #endif
@@ -326,6 +332,7 @@ struct KParams {
   const int32_t* popc;
   void* out;
   int heads, head_dim, s_q, s_kv, mask_words, out_dtype, n_kv_streams;
+  int n_streams, n_qtiles;   // work items of the persistent ring kernel: n_qtiles * heads * n_streams
   float scale_log2;   // scale * log2(e)
 };
 
@@ -1050,9 +1057,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   }
 }
 
-#ifdef FF_ONE_CTA
-#include "attn_onecta.cuh"      // experimental one-CTA-per-SM variant (not in the product build)
-#endif
+#include "attn_ring.cuh"        // ring-buffered kernel: the product kernel for fp16-P, 8 < head_dim <= 80
 
 // ---------------------------------------------------------------------------------------------------------------
 // host side
@@ -1094,38 +1099,73 @@ int make_map(CUtensorMap* map, const void* base, int streams, int S, int heads, 
   return FF_OK;
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE attribute: configure once per (kernel, device).
+template <typename K>
+int ensure_smem(K kernel, int bytes, std::atomic<uint64_t>& done) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return FF_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return ff::fail(FF_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", bytes, cudaGetErrorString(e));
+  done.fetch_or(bit, std::memory_order_release);
+  return FF_OK;
+}
+
 template <int DPAD, bool HILO>
 int launch(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const KParams& kp, int n_streams,
            cudaStream_t st) {
   using C = Cfg<DPAD, HILO>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_masked_kv_kernel<DPAD, HILO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C::SMEM_BYTES);
-    if (e != cudaSuccess) return ff::fail(FF_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", C::SMEM_BYTES,
-                                          cudaGetErrorString(e));
-    configured = true;
-  }
+  static std::atomic<uint64_t> configured{0};
+  int rc = ensure_smem(attn_masked_kv_kernel<DPAD, HILO>, C::SMEM_BYTES, configured);
+  if (rc != FF_OK) return rc;
   dim3 grid((kp.s_q + BM - 1) / BM, kp.heads, n_streams);
   attn_masked_kv_kernel<DPAD, HILO><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(mq, mk, mv, kp);
   return ff::check_launch("ff_attn_masked_kv");
 }
 
-#ifdef FF_ONE_CTA
-int launch_onecta(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const KParams& kp, int n_streams,
-                  cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_onecta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OC::SMEM_BYTES);
-    if (e != cudaSuccess) return ff::fail(FF_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", OC::SMEM_BYTES,
-                                          cudaGetErrorString(e));
-    configured = true;
+int sm_count() {                    // SMs of the current device (cached per device)
+  static std::atomic<int> cached[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int n = cached[dev & 63].load(std::memory_order_relaxed);
+  if (n == 0) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+    cached[dev & 63].store(n, std::memory_order_relaxed);
   }
-  dim3 grid((kp.s_q + BM - 1) / BM, kp.heads, n_streams);
-  attn_onecta_kernel<<<grid, NUM_THREADS, OC::SMEM_BYTES, st>>>(mq, mk, mv, kp);
-  return ff::check_launch("ff_attn_masked_kv (one-CTA variant)");
+  return n;
 }
-#endif
+
+template <int DPAD, int NWG, int NBUF, bool TOKEN>
+int launch_ring(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const KParams& kp, int n_streams,
+                cudaStream_t st) {
+  using C = RCfg<DPAD, NWG, NBUF>;
+  static std::atomic<uint64_t> configured{0};
+  int rc = ensure_smem(attn_ring_kernel<DPAD, NWG, NBUF, TOKEN>, C::SMEM_BYTES, configured);
+  if (rc != FF_OK) return rc;
+  // persistent grid: one CTA per SM (two for the layouts that fit twice), never more CTAs than work items
+  const int n_items = kp.n_qtiles * kp.heads * n_streams;
+  int ctas = sm_count() * C::MIN_CTAS;
+  if (ctas > n_items) ctas = n_items;
+  attn_ring_kernel<DPAD, NWG, NBUF, TOKEN><<<ctas, C::NUM_THREADS, C::SMEM_BYTES, st>>>(mq, mk, mv, kp);
+  return ff::check_launch("ff_attn_masked_kv (ring kernel)");
+}
+
+// Kernel selection for the fp16-P path, 8 < head_dim <= 80 (FF_ATTN_RING in the environment, read once; experiments only):
+//   0 = legacy kernel; ring <DPAD, warpgroups, S/P buffers, exp token> for d<=40 / d<=80:
+//   1 = <48,1,3,0> (two CTAs per SM) / <80,2,3,0>    2 = <48,2,4,0> / <80,2,3,0>    3 = <48,3,5,0> / <80,2,3,0>
+//   4 = <48,3,5,1> / <80,2,3,1>                      5 = <48,2,4,1> / <80,2,3,1>
+//   6 = legacy kernel for d<=40 / <80,2,3,0> for d<=80 -- the default: what measured fastest per head dim in round 2.
+int ring_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("FF_ATTN_RING");
+    mode = e ? atoi(e) : FF_RING_DEFAULT;
+    if (mode < 0 || mode > 6) mode = FF_RING_DEFAULT;
+  }
+  return mode;
+}
 
 }  // namespace
 
@@ -1207,15 +1247,22 @@ extern "C" int ff_attn_masked_kv(const FFAttnArgs* a, void* stream) {
   kp.mask_words = a->mask_words;
   kp.out_dtype = a->out_dtype;
   kp.n_kv_streams = a->n_kv_streams;
+  kp.n_streams = a->n_streams;
+  kp.n_qtiles = (a->s_q + BM - 1) / BM;
   kp.scale_log2 = a->scale * 1.4426950408889634f;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int d = a->head_dim;
   // thresholds leave room for the ones column at channel d inside DPV (see ff_attn_v_head_stride)
   if (v_f16) {
     if (d <= 8) return launch<16, false>(mq, mk, mv, kp, a->n_streams, st);
-#ifdef FF_ONE_CTA
-    if (d <= 40) return launch_onecta(mq, mk, mv, kp, a->n_streams, st);
-#endif
+    const int rm = ring_mode();
+    if (rm == 1 && d <= 40) return launch_ring<48, 1, 3, false>(mq, mk, mv, kp, a->n_streams, st);
+    if (rm == 2 && d <= 40) return launch_ring<48, 2, 4, false>(mq, mk, mv, kp, a->n_streams, st);
+    if (rm == 3 && d <= 40) return launch_ring<48, 3, 5, false>(mq, mk, mv, kp, a->n_streams, st);
+    if (rm == 4 && d <= 40) return launch_ring<48, 3, 5, true>(mq, mk, mv, kp, a->n_streams, st);
+    if (rm == 5 && d <= 40) return launch_ring<48, 2, 4, true>(mq, mk, mv, kp, a->n_streams, st);
+    if (d > 40 && d <= 80 && (rm == 4 || rm == 5)) return launch_ring<80, 2, 3, true>(mq, mk, mv, kp, a->n_streams, st);
+    if (d > 40 && d <= 80 && rm != 0) return launch_ring<80, 2, 3, false>(mq, mk, mv, kp, a->n_streams, st);
     if (d <= 40) return launch<48, false>(mq, mk, mv, kp, a->n_streams, st);
     if (d <= 80) return launch<80, false>(mq, mk, mv, kp, a->n_streams, st);
     return launch<160, false>(mq, mk, mv, kp, a->n_streams, st);

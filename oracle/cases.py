@@ -136,7 +136,22 @@ PIPE_CASES = {
                          use_auto_draw=True, reduce_inp_artifacts=True, end_scale=0.0, prompt=""),
     "mmsa":         dict(seed=3, res=128, num_step=8, start_step=2, end_step=8, eta=0.0, gs=5.0, method="mmsa",
                          use_auto_draw=False, reduce_inp_artifacts=False, end_scale=0.5, prompt="a photo of a thing"),
+    # the full 50-step schedule (BASELINE.json north_star: "final latents after a full 50-step edit"), driver-like inputs
+    # (cons_area = target mask, draw_mask = ones: evaluation/FreeFine/freefine_batch_infer_2d.py:196,212-230):
+    # the GeoBench-2D default (15 + 15 UNet calls), the whole schedule (50 + 50, what bench.py times by default) with the
+    # quirk-faithful settings, and the whole schedule quirk-free
+    "sched50_ss35": dict(seed=8, res=128, num_step=50, start_step=35, end_step=50, eta=1.0, gs=7.5, method="tca",
+                         use_auto_draw=True, reduce_inp_artifacts=True, end_scale=0.0, prompt="", driver_like=True),
+    "sched50_full": dict(seed=9, res=128, num_step=50, start_step=0, end_step=50, eta=1.0, gs=7.5, method="tca",
+                         use_auto_draw=True, reduce_inp_artifacts=True, end_scale=0.0, prompt="", driver_like=True),
+    "sched50_quirkfree": dict(seed=10, res=128, num_step=50, start_step=0, end_step=25, eta=1.0, gs=7.5, method="tca",
+                              use_auto_draw=False, reduce_inp_artifacts=False, end_scale=0.5, prompt="a photo of a thing"),
 }
+
+# BASELINE.json configs[0]: object repositioning on one 512x512 Examples/Editing image, 10-step inversion + sampling
+# (SURVEY.md 8d "Config 1"): Examples/Editing/2D/bear, dx = +60 px, GeoBench-2D settings otherwise.
+CONFIG1 = dict(example="bear", edit_param=(60, 0, 0, 1.0, 1.0), num_step=10, start_step=0, end_step=10, eta=1.0, gs=7.5,
+               method="tca", use_auto_draw=True, reduce_inp_artifacts=True, end_scale=0.0, prompt="", seed=11)
 
 
 BG_CASES = {

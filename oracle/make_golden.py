@@ -6,6 +6,7 @@ The GPU box has no /root/reference; there the committed fixtures are the pin.
 """
 from __future__ import annotations
 
+import json
 import os
 import sys
 
@@ -164,6 +165,8 @@ def gen_pipeline(ref):
         pipe, controller = ref_import.make_reference_pipeline(ref, parts)
         img, ori_mask3, edit_param, draw, cons = cases.edit_case_inputs(c["seed"], c["res"])
         coarse, tgt_mask, _ = ref.vis_utils.re_edit_2d(img, ori_mask3, edit_param, img)
+        if c.get("driver_like"):          # freefine_batch_infer_2d.py:196,229
+            draw, cons = np.ones_like(ori_mask3[:, :, 0]), tgt_mask
         counter = {"k": 0}
 
         def fake_randn(shape, generator=None, device=None, dtype=None, _c=c, _n=counter):
@@ -188,6 +191,7 @@ def gen_pipeline(ref):
         out[name + "/latents"] = torch.stack(inter).numpy()
         out[name + "/edit_img"], out[name + "/ref_img"] = edit_img, ref_img
         out[name + "/n_noise"] = np.array(counter["k"])
+        out[name + "/params_json"] = np.array(json.dumps(c))      # read by freefine_b200/selfcheck.py (no oracle import there)
     # background generation / object removal (register_attention_control_4bggen, model.py:1088-1118 without the GIF)
     for name, c in cases.BG_CASES.items():
         parts = build_standin("tiny")
@@ -242,6 +246,47 @@ def gen_pipeline(ref):
     np.savez_compressed(os.path.join(OUT, "pipeline.npz"), **out)
 
 
+def gen_config1(ref):
+    """BASELINE.json configs[0] / SURVEY.md 8d config 1: the reference's own example image (Examples/Editing/2D/bear,
+    read like vis_utils.py:349-360), moved by dx = +60 px, 10-step inversion + 10-step TCA sampling, tiny stand-in UNet
+    on the CPU.  The two PNGs are copied beside the fixture so that the GPU test reads the same files."""
+    import shutil
+    from freefine_b200.standin import build_standin
+    c = cases.CONFIG1
+    src_dir = os.path.join(ref_import.REF_ROOT, "Examples", "Editing", "2D", c["example"])
+    for f in ("source.png", "source_mask.png"):
+        shutil.copyfile(os.path.join(src_dir, f), os.path.join(OUT, f"config1_{c['example']}_{f}"))
+    img = ref.vis_utils.read_and_resize_img(os.path.join(src_dir, "source.png"))
+    ori_mask3 = ref.vis_utils.read_and_resize_mask(os.path.join(src_dir, "source_mask.png"))
+    coarse, tgt_mask, _ = ref.vis_utils.re_edit_2d(img, ori_mask3, c["edit_param"], img)
+    parts = build_standin("tiny")
+    pipe, controller = ref_import.make_reference_pipeline(ref, parts)
+    counter = {"k": 0}
+
+    def fake_randn(shape, generator=None, device=None, dtype=None):
+        t = cases.step_noise(c["seed"], counter["k"], shape)
+        counter["k"] += 1
+        return t
+
+    ref.model.randn_tensor = fake_randn
+    torch.manual_seed(c["seed"])
+    ori_mask = pipe.mask_reduce_dim(ori_mask3)
+    _, inv = pipe.DDIM_inversion_func(img=coarse, mask=tgt_mask, prompt="", num_step=c["num_step"],
+                                      start_step=c["start_step"], ref_img=img, verbose=True)
+    edit_img, ref_img, inter = pipe.Details_Preserving_regeneration(
+        coarse, inv, c["prompt"], tgt_mask, ori_mask, np.ones_like(ori_mask), num_steps=c["num_step"],
+        start_step=c["start_step"], end_step=c["end_step"], guidance_scale=c["gs"], eta=c["eta"], share_attn=True,
+        method_type=c["method"], verbose=True, local_text_edit=True, local_perturbation=True, return_intermediates=True,
+        cons_area=tgt_mask, use_auto_draw=c["use_auto_draw"], end_scale=c["end_scale"],
+        reduce_inp_artifacts=c["reduce_inp_artifacts"])
+    out = {"img_checksum": np.array([int(img.astype(np.int64).sum()), int(ori_mask.astype(np.int64).sum())]),
+           "tgt_mask_bits": np.packbits(tgt_mask != 0), "coarse_checksum": np.array(int(coarse.astype(np.int64).sum())),
+           "inverted_last": inv[-1].numpy(), "latents_last": inter[-1].numpy(),
+           "latents_mid": inter[len(inter) // 2].numpy(), "edit_img_small": edit_img[::4, ::4].copy(),
+           "n_noise": np.array(counter["k"]), "n_latents": np.array(len(inter)), "params_json": np.array(json.dumps(c))}
+    np.savez_compressed(os.path.join(OUT, "config1.npz"), **out)
+
+
 def gen_coarse3d(ref):
     """re_edit_3d of the UNMODIFIED reference (cv2.warpAffine) on seeded inputs."""
     out = {}
@@ -258,12 +303,19 @@ def main():
     from freefine_b200.standin import build_standin
     parts = build_standin("tiny")
     torch.set_grad_enabled(False)
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]
+    if only:                                    # e.g. `python -m oracle.make_golden config1 pipeline`
+        for name in only:
+            fn = globals()["gen_" + name]
+            fn(ref, parts) if name in ("steps", "masks") else fn(ref)
+        return
     gen_attention(ref)
     gen_steps(ref, parts)
     gen_warp(ref)
     gen_masks(ref, parts)
     gen_pipeline(ref)
     gen_coarse3d(ref)
+    gen_config1(ref)
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -31,33 +31,37 @@ def shard_indices(n: int, rank: int, world: int):
 
 def gather_results(local: torch.Tensor, indices, n_total: int) -> torch.Tensor:
     """local [n_local, ...] results of the edits `indices` (as from shard_indices) -> [n_total, ...] on every rank,
-    row i = result of edit i (first occurrence wins for the padded duplicates)."""
+    row i = result of edit i (first occurrence wins for the padded duplicates).  Every rank holds ceil(n/world) edits
+    (shard_indices pads the tail), so ONE all_gather_into_tensor moves the results and one moves the indices; the
+    de-duplication is host-side index arithmetic on a single small D2H copy (no per-edit synchronisation)."""
+    idx_local = torch.as_tensor(list(indices), dtype=torch.int64)
+    if local.shape[0] != idx_local.numel():
+        raise ValueError(f"{local.shape[0]} results for {idx_local.numel()} indices")
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        out = torch.empty((n_total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-        seen = set()
-        for row, i in zip(local, indices):
-            if i not in seen:
-                out[i] = row
-                seen.add(i)
-        return out
-    world = dist.get_world_size()
-    idx_t = torch.tensor(list(indices), dtype=torch.int64, device=local.device)
-    counts = [torch.zeros(1, dtype=torch.int64, device=local.device) for _ in range(world)]
-    dist.all_gather(counts, torch.tensor([len(indices)], dtype=torch.int64, device=local.device))
-    n_max = int(max(int(c) for c in counts))
-    pad = lambda t: torch.cat([t, t.new_zeros((n_max - t.shape[0],) + tuple(t.shape[1:]))]) if t.shape[0] < n_max else t
-    all_idx = [torch.empty(n_max, dtype=torch.int64, device=local.device) for _ in range(world)]
-    all_res = [torch.empty((n_max,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device) for _ in range(world)]
-    dist.all_gather(all_idx, pad(idx_t))
-    dist.all_gather(all_res, pad(local.contiguous()))
-    out = torch.empty((n_total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    seen = set()
-    for r in range(world):
-        for k in range(int(counts[r])):
-            i = int(all_idx[r][k])
-            if i not in seen:
-                out[i] = all_res[r][k]
-                seen.add(i)
-    if len(seen) != n_total:
-        raise RuntimeError(f"gathered {len(seen)} distinct edits, expected {n_total}")
-    return out
+        all_idx, all_res = idx_local, local
+    else:
+        world = dist.get_world_size()
+        n_loc = torch.tensor([idx_local.numel()], dtype=torch.int64, device=local.device)
+        n_all = torch.empty(world, dtype=torch.int64, device=local.device)
+        dist.all_gather_into_tensor(n_all, n_loc)
+        n_all = n_all.cpu()
+        n_max = int(n_all.max())
+        if int(n_all.min()) != n_max:       # not the sampler's layout: pad to the longest shard with index -1
+            pad = n_max - idx_local.numel()
+            idx_local = torch.cat([idx_local, torch.full((pad,), -1, dtype=torch.int64)])
+            local = torch.cat([local, local.new_zeros((pad,) + tuple(local.shape[1:]))])
+        all_idx_d = torch.empty(world * n_max, dtype=torch.int64, device=local.device)
+        all_res = torch.empty((world * n_max,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(all_idx_d, idx_local.to(local.device))
+        dist.all_gather_into_tensor(all_res, local.contiguous())
+        all_idx = all_idx_d.cpu()
+    # first occurrence of every edit index, in rank-major order (what the reference's rank-0 merge keeps last is the same
+    # value: a padded duplicate is the same edit computed twice)
+    import numpy as np
+    ai = all_idx.numpy()
+    valid = np.nonzero(ai >= 0)[0]
+    uniq, first = np.unique(ai[valid], return_index=True)
+    if len(uniq) != n_total or (n_total and (uniq[0] != 0 or uniq[-1] != n_total - 1)):
+        raise RuntimeError(f"gathered {len(uniq)} distinct edits, expected {n_total}")
+    rows = torch.from_numpy(valid[first]).to(all_res.device)
+    return all_res.index_select(0, rows)

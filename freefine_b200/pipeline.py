@@ -136,7 +136,15 @@ class FreeFinePipeline:
         h, w = x.shape[-2:]
         noise = None
         if eta > 0:
-            noise = randn_tensor(x.shape, generator=generator, device=x.device, dtype=torch.float32).contiguous()
+            if isinstance(generator, (list, tuple)):
+                # one generator per edit: every edit sees the reference's own stream (seed_everything(seed), then one
+                # randn_tensor([2,C,h,w]) draw per step, model.py:1018,186-188) whatever the batch / shard layout
+                if len(generator) != E:
+                    raise ValueError(f"{len(generator)} generators for {E} edits")
+                noise = torch.stack([randn_tensor((2,) + tuple(x.shape[1:]), generator=g, device=x.device, dtype=torch.float32)
+                                     for g in generator]).reshape(x.shape).contiguous()
+            else:
+                noise = randn_tensor(x.shape, generator=generator, device=x.device, dtype=torch.float32).contiguous()
         cm = None if cfg_mask is None else self._var_mask(cfg_mask, E, h, w)
         return ops.ddim_cfg_step(noise_pred4.float().contiguous(), x.float().contiguous(), noise, cm,
                                  self._var_mask(var_mask, E, h, w), float(guidance_scale),
@@ -236,7 +244,9 @@ class FreeFinePipeline:
                          guidance_scale=7.5, latents=None, unconditioning=None, neg_prompt=None,
                          return_intermediates=False, eta=0.0, end_scale=0.5, local_var_reg=None,
                          completion_mask_cfg=None, local_edit_text=True, share_attn=True, method_type=None,
-                         verbose=False, local_perturbation=True, **kwds):
+                         verbose=False, local_perturbation=True, generator=None, **kwds):
+        """`generator`: None (global generator, as the reference), one torch.Generator, or a list with one generator per
+        edit (batched edits: each edit draws its own [2,C,h,w] noise per step, independent of batch composition)."""
         self.method_type = method_type
         assert guidance_scale > 1.0, 'USING THIS MODULE CFG Must > 1.0'
         c = self.controller
@@ -299,7 +309,7 @@ class FreeFinePipeline:
             c.log_mask = False
             noise_pred = self._unet(model_inputs, t, te)
             latents = self.cfg_ctrl_step(noise_pred, t, latents, completion_mask_cfg if local_edit_text else None,
-                                         var_mask, guidance_scale, eta=eta)
+                                         var_mask, guidance_scale, eta=eta, generator=generator)
             latents_list.append(latents)
         image = self.latent2image(latents, return_type="pt")
         if return_intermediates:
@@ -822,7 +832,11 @@ class FreeFinePipeline:
         c.reset()
         c.fg_retain_mask, c.fg_retain_mask_st2, c.fg_ref_mask, c.local_edit_region = fg, sh, orim, fg
         prompts = [p for t in guidance_texts for p in (t, "")]
-        image, inter = self.forward_sampling(prompt=prompts, refer_latents=inverted[::-1], end_step=end_step,
+        # the reference seeds every edit alike (seed_everything(seed), model.py:1018) and draws [2,C,h,w] per step: one
+        # generator per edit reproduces that stream for each edit, independent of E, of its position in the batch and of
+        # how a sweep is sharded over ranks
+        gens = [torch.Generator(device=self.device).manual_seed(int(seed)) for _ in range(E)] if eta > 0 else None
+        image, inter = self.forward_sampling(prompt=prompts, refer_latents=inverted[::-1], end_step=end_step, generator=gens,
                                              latents=inverted[-1].clone(), guidance_scale=guidance_scale,
                                              num_inference_steps=num_step, num_actual_inference_steps=num_step - start_step,
                                              eta=eta, completion_mask_cfg=comp, local_var_reg=lvar, method_type=method_type,

@@ -193,3 +193,11 @@ def coarse3d_case_inputs(seed: int, res: int = 128):
     ori, om3, _, _, _ = edit_case_inputs(seed + 50, res)
     bg, _, _, _, _ = edit_case_inputs(seed + 70, res)
     return src, m3, bg, ori, om3[:, :, :1].astype(bool)
+
+
+# re_edit_2d (vis_utils.py:210-274) with rotation + anisotropic scale: (seed, edit_param (dx, dy, rz, sx, sy))
+COARSE2D_CASES = {
+    "move": (41, (11, -7, 0, 1.0, 1.0)),
+    "rot_scale": (42, (-6, 9, 23.0, 1.15, 0.85)),
+    "rot_only": (43, (0, 0, -31.0, 1.0, 1.0)),
+}

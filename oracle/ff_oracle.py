@@ -340,6 +340,29 @@ def warp_blend(src, theta, mask_src, bg):
 # per-edit mask preparation (uint8 algebra incl. wrap-around quirk Q1)
 # ----------------------------------------------------------------------------------------------------------------
 
+def re_edit_2d(src_img: np.ndarray, src_mask: np.ndarray, edit_param, inp_cur: np.ndarray):
+    """Coarse 2-D edit on the CPU exactly as the reference does it with OpenCV (src/utils/vis_utils.py:210-274): rotation by
+    -rz about the centre of the mask's bounding box (cv2.getRotationMatrix2D, scale 1), translation (dx, dy) plus the
+    re-centring term (1 - s) * centre, the diagonal scaled by (sx, sy); bilinear warp of the image, nearest warp of the
+    mask, np.where blends.  Returns (final image, warped mask * 255, image with the hole)."""
+    import cv2
+    m = src_mask[:, :, 0] if src_mask.ndim == 3 else src_mask
+    dx, dy, rz, sx, sy = edit_param
+    h, w = m.shape[:2]
+    ys, xs = np.where(m)
+    cx, cy = (xs.max() + xs.min()) / 2, (ys.max() + ys.min()) / 2
+    M = cv2.getRotationMatrix2D((cx, cy), -rz, 1)
+    M[0, 2] += dx + (1 - sx) * cx
+    M[1, 2] += dy + (1 - sy) * cy
+    M[0, 0] *= sx
+    M[1, 1] *= sy
+    warped = cv2.warpAffine(src_img, M, (w, h))
+    wmask = cv2.warpAffine(m.astype(np.uint8), M, (w, h), flags=cv2.INTER_NEAREST).astype(bool)
+    hole = np.where(m[:, :, None].astype(bool), 0, src_img)
+    return (np.where(wmask[:, :, None], warped, inp_cur), wmask.astype(np.uint8) * 255,
+            np.where(wmask[:, :, None], warped, hole))
+
+
 def dilate_mask(mask: np.ndarray, k: int) -> np.ndarray:
     """model.py:927-934 / vis_utils.py:340-347: cv2.dilate with a k x k ones kernel (anchor at k//2), restated as a
     sliding max with OpenCV's border handling for dilation (out-of-image = minimum)."""

@@ -287,6 +287,17 @@ def gen_config1(ref):
     np.savez_compressed(os.path.join(OUT, "config1.npz"), **out)
 
 
+def gen_coarse2d(ref):
+    """re_edit_2d of the UNMODIFIED reference (cv2.warpAffine) incl. rotation + anisotropic scale."""
+    out = {}
+    for name, (seed, ep) in cases.COARSE2D_CASES.items():
+        img, m3, _, _, _ = cases.edit_case_inputs(seed, 128)
+        bg, _, _, _, _ = cases.edit_case_inputs(seed + 70, 128)
+        final, tmask, hole = ref.vis_utils.re_edit_2d(img, m3, ep, bg)
+        out[name + "/final"], out[name + "/tmask"], out[name + "/hole"] = final, tmask, hole
+    np.savez_compressed(os.path.join(OUT, "coarse2d.npz"), **out)
+
+
 def gen_coarse3d(ref):
     """re_edit_3d of the UNMODIFIED reference (cv2.warpAffine) on seeded inputs."""
     out = {}
@@ -315,6 +326,7 @@ def main():
     gen_masks(ref, parts)
     gen_pipeline(ref)
     gen_coarse3d(ref)
+    gen_coarse2d(ref)
     gen_config1(ref)
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):

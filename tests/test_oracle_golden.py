@@ -102,3 +102,15 @@ def test_mask_prep_bit_exact(golden):
     assert 2 in np.unique(g["auto1_red1/comp"])
     for k in (15, 30):
         assert np.array_equal(O.dilate_mask(g["ori"][:, :, 0], k), g[f"dilate{k}"])
+
+
+def test_re_edit_2d_matches_reference(golden):
+    """oracle.re_edit_2d (the CPU arm's coarse edit) vs the UNMODIFIED reference's cv2 outputs: bit-exact."""
+    from oracle import cases
+    g = golden["coarse2d"]
+    for name, (seed, ep) in cases.COARSE2D_CASES.items():
+        img, m3, _, _, _ = cases.edit_case_inputs(seed, 128)
+        bg, _, _, _, _ = cases.edit_case_inputs(seed + 70, 128)
+        final, tmask, hole = O.re_edit_2d(img, m3, ep, bg)
+        assert np.array_equal(tmask, g[name + "/tmask"]) and np.array_equal(final, g[name + "/final"]), name
+        assert np.array_equal(hole, g[name + "/hole"]), name

@@ -14,6 +14,7 @@
 // All accesses are 128-bit; sums are combined in a fixed order (bit-reproducible run to run).
 #include <cuda_bf16.h>
 
+#include <atomic>
 #include <cstdlib>
 
 #include "ff_common.cuh"
@@ -42,7 +43,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 constexpr int GN_THREADS = 256;
-constexpr int GN_MAX_CHUNKS = 64;     // pixel chunks per image (partial statistics per chunk)
+constexpr int GN_MAX_CHUNKS = 64;     // pixel chunks per image (partial statistics per chunk), two-kernel form
+constexpr int GN_MAX_CHUNKS_FUSED = 128;   // ... single-read form (the workspace is sized for this one)
 constexpr int GN_CHUNK_PX = 128;      // pixels per CTA, images of more than 1024 pixels
 constexpr int GN_CHUNK_PX_SMALL = 64;  // ... of at most 1024 pixels
 
@@ -183,6 +185,192 @@ gn_apply_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_
       for (int j = 0; j < 8; ++j) {
         float t = fmaf(f[j], sc[j], sh[j]);
         if (SILU) t = __fdividef(t, 1.f + __expf(-t));     // 2 MUFU ops; the IEEE division made this kernel ALU-bound
+        f[j] = t;
+      }
+      *py = pack8(f);
+    }
+  }
+}
+
+// ---- single-read GroupNorm (round 2) -----------------------------------------------------------------------------------
+// The two-kernel form above moves three passes of real traffic (statistics read, apply read, write): 0.33 of the HBM peak
+// on ALGORITHMIC bytes (x once + y once).  Here ONE kernel keeps its chunk of the image in shared memory between the
+// statistics and the apply phase: x is read from HBM exactly once.  The CTAs of an image meet at a per-image barrier in
+// global memory (partial sums published, counter incremented, everybody spins until the counter reaches n_chunks).
+// Forward progress: a CTA takes its LOGICAL index from an atomic ticket when it starts, images are contiguous ticket
+// ranges, so every CTA of an earlier image is already running (or done) and can finish without waiting for anybody else;
+// of the image that is only partly started at most n_chunks - 1 <= 63 CTAs wait, fewer than the 148 that are resident even
+// at one CTA per SM, so a slot for the next ticket always frees up.  The counters live in the caller's workspace, which
+// must be ZERO before the first call and is left zeroed by every call (self-cleaning), see include/freefine_b200.h.
+struct GnCtrl {                       // head of the workspace
+  unsigned int ticket, pad[3];
+};
+
+template <bool SILU>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_fused_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_nc, const __nv_bfloat16* __restrict__ gamma,
+                     const __nv_bfloat16* __restrict__ beta, uint4* __restrict__ y, unsigned int* __restrict__ ctrl,
+                     float2* __restrict__ partial, int N, int HW, int C, int G, int chunk_px, int n_chunks, float eps) {
+  extern __shared__ __align__(16) unsigned char gsm[];
+  const GnLayout L(C);
+  uint4* tile = reinterpret_cast<uint4*>(gsm);                                    // [chunk_px][CV]
+  float* red = reinterpret_cast<float*>(gsm + (size_t)chunk_px * L.CV * sizeof(uint4));   // [R][2][C]
+  float* mean = red + (size_t)L.R * 2 * C;                                        // [G]
+  float* rstd = mean + G;                                                         // [G]
+  __shared__ unsigned int s_id;
+  __shared__ __align__(8) unsigned long long s_bar;
+  unsigned int* done = ctrl + 4;        // [N] CTAs of image n that have published their partial sums
+  unsigned int* left = done + N;        // [N] CTAs of image n that have read the partial sums
+  if (threadIdx.x == 0) {
+    s_id = atomicAdd(&ctrl[0], 1u);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const unsigned int id = s_id;
+  const int n = (int)(id / (unsigned)n_chunks), chunk = (int)(id % (unsigned)n_chunks);
+  const int p0 = chunk * chunk_px, p1 = min(HW, p0 + chunk_px);
+  const int cpg = C / G;
+  // ---- phase 1: HBM -> shared memory.  A chunk of an NHWC image is one contiguous run of bytes: a single thread issues it
+  // as bulk asynchronous copies (cp.async.bulk, completion on an mbarrier), so the whole 80-120 KB chunk is in flight at
+  // once -- with per-thread 16-byte loads a CTA keeps ~16 KB in flight and the phase is latency-bound (measured: the
+  // single-read kernel was SLOWER than the two-kernel form, 96 vs 76 us at 32x320x64x64).
+  {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+    if (threadIdx.x == 0) {
+      const uint32_t bytes = (uint32_t)(p1 - p0) * (uint32_t)C * 2u;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      const char* src = reinterpret_cast<const char*>(x + ((size_t)n * HW + p0) * L.CV);
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tile);
+      for (uint32_t off = 0; off < bytes; off += 32768u) {
+        const uint32_t sz = bytes - off < 32768u ? bytes - off : 32768u;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst + off), "l"(src + off), "r"(sz), "r"(bar) : "memory");
+      }
+    }
+    uint32_t ok = 0;
+    while (!ok) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(bar) : "memory");
+    }
+  }
+  // per-thread channel-column sums over the chunk, from shared memory
+  if (L.r < L.R) {
+    for (int v = L.col; v < L.CV; v += L.cols) {
+      float a[8], sacc[8], ssacc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a[j] = add_nc ? __ldg(add_nc + (size_t)n * C + 8 * v + j) : 0.f;
+        sacc[j] = ssacc[j] = 0.f;
+      }
+      const uint4* pt = tile + (size_t)L.r * L.CV + v;
+      const size_t step = (size_t)L.R * L.CV;
+#pragma unroll 4
+      for (int p = p0 + L.r; p < p1; p += L.R, pt += step) {
+        float f[8];
+        unpack8(*pt, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float t = f[j] + a[j];
+          sacc[j] += t;
+          ssacc[j] = fmaf(t, t, ssacc[j]);
+        }
+      }
+      float* dst = red + (size_t)L.r * 2 * C + 8 * v;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        dst[j] = sacc[j];
+        dst[C + j] = ssacc[j];
+      }
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    const int cnt = L.R * cpg;
+    for (int g = warp; g < G; g += GN_THREADS / 32) {
+      float S = 0.f, SS = 0.f;
+      for (int i = lane; i < cnt; i += 32) {
+        const int rr = i / cpg, c = i - rr * cpg;
+        const float* src = red + (size_t)rr * 2 * C + g * cpg + c;
+        S += src[0];
+        SS += src[C];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        S += __shfl_xor_sync(0xffffffffu, S, o);
+        SS += __shfl_xor_sync(0xffffffffu, SS, o);
+      }
+      if (lane == 0) partial[((size_t)n * n_chunks + chunk) * G + g] = make_float2(S, SS);
+    }
+  }
+  // ---- per-image barrier: publish, then wait for the other chunks of this image
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(&done[n], 1u);
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(done + n) : "memory");
+      if (seen < (unsigned)n_chunks) __nanosleep(64);
+    } while (seen < (unsigned)n_chunks);
+  }
+  __syncthreads();
+  // ---- phase 2: statistics of the whole image (every CTA of image n derives bit-identical values)
+  {
+    const float inv_cnt = 1.f / ((float)cpg * (float)HW);
+    for (int g = warp; g < G; g += GN_THREADS / 32) {
+      float S = 0.f, SS = 0.f;
+      for (int ch = lane; ch < n_chunks; ch += 32) {
+        const float2 t = __ldcg(partial + ((size_t)n * n_chunks + ch) * G + g);      // written by other SMs: bypass L1
+        S += t.x;
+        SS += t.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        S += __shfl_xor_sync(0xffffffffu, S, o);
+        SS += __shfl_xor_sync(0xffffffffu, SS, o);
+      }
+      if (lane == 0) {
+        const float m = S * inv_cnt;
+        const float var = fmaxf(SS * inv_cnt - m * m, 0.f);
+        mean[g] = m;
+        rstd[g] = 1.f / sqrtf(var + eps);
+      }
+    }
+  }
+  __syncthreads();
+  // the partial sums of this image have been read by this CTA: the last reader re-arms the image's counters, the CTA
+  // with the last ticket re-arms the ticket (every ticket has been handed out by then)
+  if (threadIdx.x == 0) {
+    if (atomicAdd(&left[n], 1u) == (unsigned)n_chunks - 1u) {
+      done[n] = 0u;
+      left[n] = 0u;
+    }
+    if (id == (unsigned)N * (unsigned)n_chunks - 1u) ctrl[0] = 0u;
+  }
+  // ---- phase 3: apply from shared memory
+  if (L.r >= L.R) return;
+  for (int v = L.col; v < L.CV; v += L.cols) {
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = 8 * v + j, g = c / cpg;
+      const float a = add_nc ? __ldg(add_nc + (size_t)n * C + c) : 0.f;
+      sc[j] = rstd[g] * __bfloat162float(gamma[c]);
+      sh[j] = fmaf(a - mean[g], sc[j], __bfloat162float(beta[c]));     // y = (x + a - mean) * rstd * gamma + beta
+    }
+    const uint4* pt = tile + (size_t)L.r * L.CV + v;
+    uint4* py = y + ((size_t)n * HW + p0 + L.r) * L.CV + v;
+    const size_t step = (size_t)L.R * L.CV;
+#pragma unroll 4
+    for (int p = p0 + L.r; p < p1; p += L.R, pt += step, py += step) {
+      float f[8];
+      unpack8(*pt, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = fmaf(f[j], sc[j], sh[j]);
+        if (SILU) t = __fdividef(t, 1.f + __expf(-t));
         f[j] = t;
       }
       *py = pack8(f);
@@ -346,9 +534,34 @@ int grid_for(long long total) {
 
 }  // namespace
 
+// workspace = [GnCtrl | done[N] | left[N]] rounded up to 256 bytes, then the partial sums
+int64_t gn_ctrl_bytes(int N) { return ((int64_t)sizeof(GnCtrl) + 8LL * N + 255) / 256 * 256; }
+
+// Chunking of the single-read kernel: the chunk (chunk_px pixels x C channels, bf16) must fit in shared memory next to the
+// reduction scratch; ~100 KB tiles keep two CTAs per SM where the image allows it.  Returns 0 when no chunking fits (then
+// the two-kernel form runs).
+int gn_fused_chunks(int HW, int C, int* chunk_px, size_t* smem) {
+  const int CV = C / 8, cols = CV < GN_THREADS ? CV : GN_THREADS, R = GN_THREADS / cols;
+  const size_t scratch = (size_t)R * 2 * C * sizeof(float) + 2 * 64 * sizeof(float) + 64;   // red + mean/rstd (G <= 64 here)
+  static const int tile_kb = [] { const char* e = getenv("FF_GN_TILE_KB"); const int v = e ? atoi(e) : 0; return v >= 8 && v <= 180 ? v : 48; }();
+  int px = (int)(((size_t)tile_kb * 1024) / ((size_t)C * 2));
+  const int cap = HW <= 1024 ? GN_CHUNK_PX_SMALL : GN_CHUNK_PX;
+  if (px > cap) px = cap;
+  if (px < 1) px = 1;
+  int n_chunks = (HW + px - 1) / px;
+  if (n_chunks > GN_MAX_CHUNKS_FUSED) n_chunks = GN_MAX_CHUNKS_FUSED;
+  px = (HW + n_chunks - 1) / n_chunks;
+  n_chunks = (HW + px - 1) / px;
+  const size_t need = (size_t)px * C * 2 + scratch;
+  if (need > 200 * 1024) return 0;
+  *chunk_px = px;
+  *smem = need;
+  return n_chunks;
+}
+
 extern "C" int64_t ff_group_norm_ws_bytes(int32_t N, int32_t G) {
   if (N <= 0 || G <= 0) return 0;
-  return (int64_t)N * GN_MAX_CHUNKS * G * (int64_t)sizeof(float2);
+  return gn_ctrl_bytes(N) + (int64_t)N * GN_MAX_CHUNKS_FUSED * G * (int64_t)sizeof(float2);
 }
 
 extern "C" int ff_group_norm_nhwc(const void* x, const float* add_nc, const void* gamma, const void* beta, void* y,
@@ -360,15 +573,50 @@ extern "C" int ff_group_norm_nhwc(const void* x, const float* add_nc, const void
   FF_REQUIRE(C % 8 == 0 && C % G == 0, "ff_group_norm_nhwc: C must be a multiple of 8 and of G (C=%d G=%d)", C, G);
   FF_REQUIRE(ff::aligned16(x) && ff::aligned16(y) && ff::aligned16(workspace),
              "ff_group_norm_nhwc: x / y / workspace must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned int* ctrl = static_cast<unsigned int*>(workspace);
+  float2* partial = reinterpret_cast<float2*>(static_cast<char*>(workspace) + gn_ctrl_bytes(N));
+  // The single-read kernel is an EXPERIMENT switch (FF_GN_SINGLE_READ=1): measured on B200 in round 2 it only wins on
+  // small images (32x1280x16x16: 23.6 vs 39.0 us); at the sizes that matter it is slower than the two-kernel form (83 vs 77
+  // us at 32x320x64x64, 333 vs 206 us at 32x960x64x64) -- a CTA parked at the per-image barrier holds its shared memory, and
+  // load, reduce and store phases of the CTAs on an SM do not overlap enough (profiles/r2_gn_single_read.txt).
+  static const bool two_kernel = [] { const char* e = getenv("FF_GN_SINGLE_READ"); return !(e && atoi(e) != 0); }();
+  {
+    int px = 0;
+    size_t smem = 0;
+    const int nc = (two_kernel || G > 64) ? 0 : gn_fused_chunks(HW, C, &px, &smem);
+    if (nc > 0) {
+      // single-read form: x is read from HBM once (see gn_fused_nhwc_kernel)
+      static std::atomic<uint64_t> configured{0};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      const uint64_t bit = 1ull << (dev & 63);
+      if (!(configured.load(std::memory_order_acquire) & bit)) {
+        cudaError_t e1 = cudaFuncSetAttribute(gn_fused_nhwc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 1024);
+        cudaError_t e2 = cudaFuncSetAttribute(gn_fused_nhwc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 1024);
+        if (e1 != cudaSuccess || e2 != cudaSuccess)
+          return ff::fail(FF_E_CUDA, "ff_group_norm_nhwc: cudaFuncSetAttribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+        configured.fetch_or(bit, std::memory_order_release);
+      }
+      const unsigned int grid1 = (unsigned)N * (unsigned)nc;
+      if (silu)
+        gn_fused_nhwc_kernel<true><<<grid1, GN_THREADS, smem, st>>>(
+            static_cast<const uint4*>(x), add_nc, static_cast<const __nv_bfloat16*>(gamma),
+            static_cast<const __nv_bfloat16*>(beta), static_cast<uint4*>(y), ctrl, partial, N, HW, C, G, px, nc, eps);
+      else
+        gn_fused_nhwc_kernel<false><<<grid1, GN_THREADS, smem, st>>>(
+            static_cast<const uint4*>(x), add_nc, static_cast<const __nv_bfloat16*>(gamma),
+            static_cast<const __nv_bfloat16*>(beta), static_cast<uint4*>(y), ctrl, partial, N, HW, C, G, px, nc, eps);
+      return ff::check_launch("ff_group_norm_nhwc (single-read)");
+    }
+  }
   int chunk_px = 0;
   const int n_chunks = gn_chunks(HW, N, &chunk_px);
   const int CV = C / 8, cols = CV < GN_THREADS ? CV : GN_THREADS, R = GN_THREADS / cols;
   const size_t smem_stats = (size_t)R * 2 * C * sizeof(float);
   FF_REQUIRE(smem_stats <= 48 * 1024, "ff_group_norm_nhwc: C=%d too large", C);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const dim3 grid(n_chunks, N);
-  gn_stats_nhwc_kernel<<<grid, GN_THREADS, smem_stats, st>>>(static_cast<const uint4*>(x), add_nc,
-                                                             static_cast<float2*>(workspace), HW, C, G, chunk_px,
+  gn_stats_nhwc_kernel<<<grid, GN_THREADS, smem_stats, st>>>(static_cast<const uint4*>(x), add_nc, partial, HW, C, G, chunk_px,
                                                              n_chunks);
   int rc = ff::check_launch("ff_group_norm_nhwc (statistics)");
   if (rc != FF_OK) return rc;
@@ -376,12 +624,12 @@ extern "C" int ff_group_norm_nhwc(const void* x, const float* add_nc, const void
   if (silu)
     gn_apply_nhwc_kernel<true><<<grid, GN_THREADS, smem_apply, st>>>(
         static_cast<const uint4*>(x), add_nc, static_cast<const __nv_bfloat16*>(gamma),
-        static_cast<const __nv_bfloat16*>(beta), static_cast<const float2*>(workspace), static_cast<uint4*>(y), HW, C, G,
+        static_cast<const __nv_bfloat16*>(beta), partial, static_cast<uint4*>(y), HW, C, G,
         chunk_px, n_chunks, eps);
   else
     gn_apply_nhwc_kernel<false><<<grid, GN_THREADS, smem_apply, st>>>(
         static_cast<const uint4*>(x), add_nc, static_cast<const __nv_bfloat16*>(gamma),
-        static_cast<const __nv_bfloat16*>(beta), static_cast<const float2*>(workspace), static_cast<uint4*>(y), HW, C, G,
+        static_cast<const __nv_bfloat16*>(beta), partial, static_cast<uint4*>(y), HW, C, G,
         chunk_px, n_chunks, eps);
   return ff::check_launch("ff_group_norm_nhwc (apply)");
 }

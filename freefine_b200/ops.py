@@ -350,13 +350,14 @@ _GN_WS: dict = {}
 
 
 def _gn_workspace(N: int, G: int, device) -> torch.Tensor:
-    """Statistics workspace of ff_group_norm_nhwc, one per (device, stream): consecutive calls on a stream are ordered,
-    so the buffer is safely reused."""
+    """Workspace of ff_group_norm_nhwc, one per (device, stream): consecutive calls on a stream are ordered, so the
+    buffer is safely reused.  It carries the barrier counters of the single-read kernel: zero-initialised here, left
+    zeroed by every call (include/freefine_b200.h)."""
     key = (device, torch.cuda.current_stream().cuda_stream)
     need = int(_lib.load().ff_group_norm_ws_bytes(N, G))
     ws = _GN_WS.get(key)
     if ws is None or ws.numel() < need:
-        ws = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=device)
+        ws = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=device)
         _GN_WS[key] = ws
     return ws
 

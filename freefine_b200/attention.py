@@ -294,7 +294,7 @@ class Attention_Modulator(AttentionControl):
         self._advance()
         return out
 
-    def _style_align(self, query, key, value, mask):
+    def _style_align(self, query, key, value, mask, bg=False):
         B, S, _ = query.shape
         if B % 4:
             raise ValueError("style-align expects 4 streams per edit")
@@ -306,8 +306,8 @@ class Attention_Modulator(AttentionControl):
             bits, pop = self._table("sdsa", S, [mask])
             src_id = lambda e: e
         pf = self.sort_keys and src_id is not None
-        plan = self._plan(("style", E, self.heads, self.method, pf),
-                          lambda: plans.style_align_plan(E, self.heads, src_id, prefix=pf))
+        plan = self._plan(("style", E, self.heads, self.method, pf, bg),
+                          lambda: plans.style_align_plan(E, self.heads, src_id, prefix=pf, bg=bg))
         kv_index = self._kv_index("sdsa", S, bits, [s // 4 if s % 2 else -1 for s in range(B)]) if pf else None
         out = self._attend(query, key, value, plan, bits, pop, kv_index)
         self._advance()
@@ -318,8 +318,11 @@ class Attention_Modulator(AttentionControl):
         return self._style_align(query, key, value, self.fg_ref_mask)
 
     def style_align_share_attention_bg(self, query, key, value, is_cross, place_in_unet):
-        """reference :1193-1238; SDSA masks the ref half by the object mask (prepare_sdsa_mask_for_bggen :926-939)."""
-        return self._style_align(query, key, value, self.fg_retain_mask)
+        """reference :1193-1238; with method 'sdsa' the mask of prepare_sdsa_mask_for_bggen (:926-939) = 1 - [ones ; obj]:
+        on the Q0-masked (stream, head) pairs the self half is masked out entirely and the ref half admits the keys OUTSIDE
+        the object mask (fg_retain_mask); see plans.style_align_plan(bg=True).  (Never dispatched by the reference's own
+        register functions, :273-291; pinned by a golden of the method itself.)"""
+        return self._style_align(query, key, value, self.fg_retain_mask, bg=True)
 
     # ---- cross-attention variants -----------------------------------------------------------------------------------
     def modulate_local_cross_attn(self, query, key, value, is_cross, place_in_unet):

@@ -4,7 +4,9 @@ torch.cuda.current_stream().  No function has a PyTorch / CPU fallback.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -20,6 +22,24 @@ _DT = {torch.float32: FF_DT_F32, torch.bfloat16: FF_DT_BF16}
 COUNTS: dict = {}
 PROFILE = None
 PLAN_REGISTRY: dict = {}     # device plan pointer -> host (numpy) plan, filled by the controller; read only when PROFILE is on
+
+
+# NVTX ranges around the phases of an edit (inversion / sampling steps, UNet calls, attention launches, step kernels) so
+# that an nsys timeline of the hot path is one command: FREEFINE_NVTX=1 nsys profile python bench.py ...  (SURVEY.md 5).
+# Off by default: a push/pop pair per attention launch is ~1 us of host time on a path that issues 3000 launches per step.
+NVTX = os.environ.get("FREEFINE_NVTX", "0") == "1"
+
+
+@contextlib.contextmanager
+def nvtx_range(name: str):
+    if NVTX and torch.cuda.is_available():
+        torch.cuda.nvtx.range_push(name)
+        try:
+            yield
+        finally:
+            torch.cuda.nvtx.range_pop()
+    else:
+        yield
 
 
 def _count(name: str):
@@ -301,7 +321,8 @@ def attn_masked_kv(q, k, v, plan, heads, scale, bitmasks=None, popcount=None, ou
     if prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    rc = _lib.load().ff_attn_masked_kv(C.byref(a), _stream())
+    with nvtx_range(f"ff_attn_masked_kv S_q={Sq} S_kv={Skv} d={Cc // heads} streams={B}"):
+        rc = _lib.load().ff_attn_masked_kv(C.byref(a), _stream())
     _lib.check(rc, "ff_attn_masked_kv")
     COUNTS["ff_attn_masked_kv"] = COUNTS.get("ff_attn_masked_kv", 0) + 1
     if prof is not None:

@@ -198,7 +198,8 @@ class FreeFinePipeline:
 
     def _unet(self, latents, t, text_embeddings):
         dt = self.unet.dtype if hasattr(self.unet, "dtype") else next(self.unet.parameters()).dtype
-        out = self.unet(latents.to(dt), t, encoder_hidden_states=text_embeddings.to(dt))
+        with ops.nvtx_range(f"ff.unet streams={latents.shape[0]}"):
+            out = self.unet(latents.to(dt), t, encoder_hidden_states=text_embeddings.to(dt))
         return out.float()
 
     # ------------------------------------------------------------------------------------------------------------
@@ -224,12 +225,13 @@ class FreeFinePipeline:
         for i, t in enumerate(reversed(self.scheduler.timesteps)):
             if num_actual_inference_steps is not None and i >= num_actual_inference_steps:
                 continue
-            model_inputs = torch.cat([latents] * 2) if guidance_scale > 1. else latents
-            noise_pred = self._unet(model_inputs, t, text_embeddings)
-            if guidance_scale > 1.:
-                eu, ec = noise_pred.chunk(2, dim=0)
-                noise_pred = eu + guidance_scale * (ec - eu)
-            latents, _ = self.inv_step(noise_pred, t, latents)
+            with ops.nvtx_range(f"ff.invert step {i} t={int(t)}"):
+                model_inputs = torch.cat([latents] * 2) if guidance_scale > 1. else latents
+                noise_pred = self._unet(model_inputs, t, text_embeddings)
+                if guidance_scale > 1.:
+                    eu, ec = noise_pred.chunk(2, dim=0)
+                    noise_pred = eu + guidance_scale * (ec - eu)
+                latents, _ = self.inv_step(noise_pred, t, latents)
             latents_list.append(latents)
         if return_intermediates:
             return latents, latents_list
@@ -307,9 +309,10 @@ class FreeFinePipeline:
                 te[:, :2] = unconditioning[i].to(te.dtype)
                 te = te.reshape(4 * E, *cond.shape[1:])
             c.log_mask = False
-            noise_pred = self._unet(model_inputs, t, te)
-            latents = self.cfg_ctrl_step(noise_pred, t, latents, completion_mask_cfg if local_edit_text else None,
-                                         var_mask, guidance_scale, eta=eta, generator=generator)
+            with ops.nvtx_range(f"ff.sample step {i} t={int(t)}"):
+                noise_pred = self._unet(model_inputs, t, te)
+                latents = self.cfg_ctrl_step(noise_pred, t, latents, completion_mask_cfg if local_edit_text else None,
+                                             var_mask, guidance_scale, eta=eta, generator=generator)
             latents_list.append(latents)
         image = self.latent2image(latents, return_type="pt")
         if return_intermediates:
@@ -819,7 +822,8 @@ class FreeFinePipeline:
                                             for e in range(E)]), dtype=torch.float32)
         imgs = imgs_u8.permute(0, 3, 1, 2).float().contiguous()
         bgs = imgs if inp_bgs is None else to_dev(inp_bgs).permute(0, 3, 1, 2).float().contiguous()
-        coarse, tgt = coarse_edit.re_edit_2d_device(imgs, masks.contiguous(), to_dev(thetas), bgs)
+        with ops.nvtx_range("ff.coarse_edit (warp + blend)"):
+            coarse, tgt = coarse_edit.re_edit_2d_device(imgs, masks.contiguous(), to_dev(thetas), bgs)
         coarse = coarse.round().clamp(0, 255)                                   # the reference hands a uint8 image on
         draw = torch.zeros_like(masks) if draw_masks is None else to_dev(draw_masks)
         lat_hw = (H // 8, W // 8)

@@ -125,16 +125,26 @@ def compose_plan(n_src: int, heads: int, method: str, cg, src_ids, tgt_ids, pref
     return p
 
 
-def style_align_plan(n_edits: int, heads: int, src_id=None, prefix: bool = False) -> np.ndarray:
+def style_align_plan(n_edits: int, heads: int, src_id=None, prefix: bool = False, bg: bool = False) -> np.ndarray:
     """style_align_share_attention (attention.py:1142-1192): keys/values [self ; ref] under ONE softmax; with
-    src_id (SDSA) the ref half is masked by fg_ref_mask on the Q0-masked (stream, head) pairs (:940-951)."""
+    src_id (SDSA) the ref half is masked by fg_ref_mask on the Q0-masked (stream, head) pairs (:940-951).
+
+    bg=True: style_align_share_attention_bg (:1193-1238) with prepare_sdsa_mask_for_bggen (:926-939), whose mask is
+    1 - [ones ; obj]: on the Q0-masked pairs the WHOLE self half is masked out and the ref half admits only the keys
+    OUTSIDE the object mask src_id(e) -- a single-segment pass over the ref stream with KEY_INVERT.  (Degenerate case: an
+    object mask covering every token leaves no key; the reference then attends uniformly over [self ; ref] (quirk Q4),
+    this plan uniformly over the ref keys.)"""
     p = _empty(4 * n_edits, heads)
     for e in range(n_edits):
         for sl in range(4):
             s = 4 * e + sl
             r = 4 * e + (1 if sl < 2 else 3)
             for h in range(heads):
-                km2 = src_id(e) if (src_id is not None and q0_masked(heads, sl, h)) else -1
+                masked = src_id is not None and q0_masked(heads, sl, h)
+                if bg and masked:
+                    _add(p, s, h, r, 1.0, key_mask=src_id(e), flags=FF_PASS_KEY_INVERT | (FF_PASS_KEY_PREFIX if prefix else 0))
+                    continue
+                km2 = src_id(e) if masked else -1
                 _add(p, s, h, s, 1.0, kv2=r, key_mask2=km2, flags=FF_PASS_KEY2_PREFIX if (prefix and km2 >= 0) else 0)
     return p
 

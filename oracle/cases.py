@@ -144,6 +144,12 @@ PIPE_CASES = {
                          use_auto_draw=True, reduce_inp_artifacts=True, end_scale=0.0, prompt="", driver_like=True),
     "sched50_full": dict(seed=9, res=128, num_step=50, start_step=0, end_step=50, eta=1.0, gs=7.5, method="tca",
                          use_auto_draw=True, reduce_inp_artifacts=True, end_scale=0.0, prompt="", driver_like=True),
+    # the style-align ablation methods through forward_sampling (model.py:514-520: every self-attention layer attends to
+    # [self ; ref] keys, SDSA with the source-object mask on the ref half)
+    "ssa":  dict(seed=12, res=128, num_step=6, start_step=1, end_step=4, eta=1.0, gs=7.5, method="ssa",
+                 use_auto_draw=False, reduce_inp_artifacts=False, end_scale=0.5, prompt="a photo of a thing"),
+    "sdsa": dict(seed=13, res=128, num_step=6, start_step=1, end_step=4, eta=0.0, gs=7.5, method="sdsa",
+                 use_auto_draw=False, reduce_inp_artifacts=False, end_scale=0.5, prompt="a photo of a thing"),
     "sched50_quirkfree": dict(seed=10, res=128, num_step=50, start_step=0, end_step=25, eta=1.0, gs=7.5, method="tca",
                               use_auto_draw=False, reduce_inp_artifacts=False, end_scale=0.5, prompt="a photo of a thing"),
 }

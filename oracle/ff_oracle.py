@@ -168,9 +168,11 @@ def tca_compose(q, k, v, heads, scale, src_list, tgt_list, method, cg):
     return _merge_heads(out)
 
 
-def style_align(q, k, v, heads, scale, src=None):
+def style_align(q, k, v, heads, scale, src=None, bg=False):
     """style_align_share_attention (attention.py:1142-1192): keys/values [self ; ref] under ONE softmax;
-    'sdsa' (src given) masks the ref half by fg_ref_mask with the Q0 tiling (prepare_sdsa_mask :940-951)."""
+    'sdsa' (src given) masks the ref half by fg_ref_mask with the Q0 tiling (prepare_sdsa_mask :940-951).
+    bg=True: style_align_share_attention_bg (:1193-1238) with prepare_sdsa_mask_for_bggen (:926-939): additive mask of
+    1 - [ones ; obj], i.e. on the Q0-masked pairs the self half is masked out and the ref half admits keys outside obj."""
     B, S, C = q.shape
     qh, kh, vh = _split_heads(q, heads), _split_heads(k, heads), _split_heads(v, heads)
     out = torch.empty_like(qh)
@@ -182,7 +184,10 @@ def style_align(q, k, v, heads, scale, src=None):
             allowed = None
             if src is not None and q0_masked(heads, s, h):
                 srcb = torch.as_tensor(src).flatten().bool()
-                allowed = torch.cat([torch.ones(S, dtype=torch.bool), srcb])[None, :].expand(S, 2 * S)
+                if bg:
+                    allowed = torch.cat([torch.zeros(S, dtype=torch.bool), ~srcb])[None, :].expand(S, 2 * S)
+                else:
+                    allowed = torch.cat([torch.ones(S, dtype=torch.bool), srcb])[None, :].expand(S, 2 * S)
             out[s, h] = _softmax_av(qh[s, h], kk, vv, scale, allowed)
     return _merge_heads(out)
 

@@ -26,6 +26,7 @@ class _State:
     def reset(self):
         self.cur_att_layer = 0
         self.use_tca = False
+        self.use_style_align = False
         self.local_edit = False
         self.method = None
         self.cg = None
@@ -66,7 +67,10 @@ class OraclePipeline:
             ctx = encoder_hidden_states if is_cross else hidden_states
             q, k, v = mod.to_q(hidden_states), mod.to_k(ctx), mod.to_v(ctx)
             S = q.shape[1]
-            if not is_cross and st.use_tca and place == "up":
+            if not is_cross and st.use_style_align:                  # every place is in style_align_scope (:388-389)
+                src = O.process_mask_before_attention(st.fg_ref, S) if st.method == "sdsa" else None
+                hs = O.style_align(q, k, v, mod.heads, mod.scale, src)
+            elif not is_cross and st.use_tca and place == "up":
                 if st.cur_att_layer // 2 not in st.layer_idx:
                     hs = O.plain_attention(q, k, v, mod.heads, mod.scale)
                 else:
@@ -122,8 +126,11 @@ class OraclePipeline:
                                                          use_auto_draw, cons_area, reduce_inp_artifacts)
         st.reset()
         st.fg_retain, st.fg_ref, st.region = fg, ori, fg
-        st.use_tca, st.layer_idx = True, list(range(10, 16))
-        st.method = "tca" if method == "tca" else "mmsa"
+        if method in ("ssa", "sdsa"):                                # model.py:514-520
+            st.use_style_align, st.method = True, method
+        else:
+            st.use_tca, st.layer_idx = True, list(range(10, 16))
+            st.method = "tca" if method == "tca" else "mmsa"
         st.local_edit = True
         refer = inverted[::-1]
         x = refer[0].clone()

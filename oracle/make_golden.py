@@ -89,6 +89,20 @@ def gen_attention(ref):
     np.savez_compressed(os.path.join(OUT, "attention.npz"), **out)
 
 
+def gen_style_bg(ref):
+    """style_align_share_attention_bg of the UNMODIFIED reference (attention.py:1193-1238; 'sdsa' uses
+    prepare_sdsa_mask_for_bggen :926-939) -- dead code in the reference's dispatch, pinned here as a method."""
+    out = {}
+    q, k, v = cases.qkv(4, 64, 64, 41)
+    obj = torch.from_numpy(cases.blob_mask(64, 42))
+    for method in ("ssa", "sdsa"):
+        c = _ctrl(ref, 8, 8 ** -0.5, method, None)
+        c.fg_retain_mask = obj.clone()
+        out[f"style_bg_{method}/out"] = c.style_align_share_attention_bg(q.clone(), k.clone(), v.clone(), False, "up").numpy()
+    out["style_bg/q"], out["style_bg/k"], out["style_bg/v"], out["style_bg/obj"] = q.numpy(), k.numpy(), v.numpy(), obj.numpy()
+    np.savez_compressed(os.path.join(OUT, "attention_bg.npz"), **out)
+
+
 def gen_steps(ref, parts):
     pipe, _ = ref_import.make_reference_pipeline(ref, parts)
     out = {}
@@ -321,6 +335,7 @@ def main():
             fn(ref, parts) if name in ("steps", "masks") else fn(ref)
         return
     gen_attention(ref)
+    gen_style_bg(ref)
     gen_steps(ref, parts)
     gen_warp(ref)
     gen_masks(ref, parts)

@@ -19,24 +19,25 @@ def launches():
         v = float(r[vi].replace(",", "")) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "nsecond": 1e-6, "usecond": 1e-3, "msecond": 1.0}[r[ui]]
         name = re.sub(r"\(.*", "", r[ki]).replace("void ", "").replace("<unnamed>::", "")
         name = re.sub(r"(attn_masked_kv_kernel<[^>]*>).*", r"\1", name)
-        name = name if "attn_masked" in name or "warp_affine" in name else re.sub(r"<.*", "", name)
+        name = re.sub(r"(attn_ring_kernel<[^>]*>).*", r"\1", name)
+        name = name if "attn_masked" in name or "attn_ring" in name or "warp_affine" in name else re.sub(r"<.*", "", name)
         name = "at::layer_norm (eager)" if name.startswith("at::") and "layer_norm" in name else name
         tot[name][0] += v
         tot[name][1] += 1
     total = sum(v[0] for v in tot.values())
     n = sum(v[1] for v in tot.values())
     lines = ["# %s -- ncu launch list (gpu__time_duration.sum, --clock-control none) of:" % TAG,
-             "#   python bench.py --steps 1 --warmup 0 --start-step 49 --no-cpu-baseline --no-e2e",
+             "#   python bench.py --steps 1 --warmup 0 --start-step 49 --no-cpu-baseline --no-e2e" + (" --no-extras" if TAG != "r1" else ""),
              "#   = one batch of 8 512x512 edits with 1 inversion UNet call (16 streams) + 1 TCA sampling call (32 streams)",
              "# per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.  Raw list: %s_launches_bench.csv" % TAG,
              "# total %.1f ms over %d launches" % (total, n)]
     for name, (ms, c) in sorted(tot.items(), key=lambda kv: -kv[1][0])[:24]:
         lines.append("%9.3f ms %5.1f%%  x%4d  %s" % (ms, 100 * ms / total, c, name[:90]))
-    ours = {k: (round(v[0], 3), v[1]) for k, v in tot.items() if any(s in k for s in ("attn_masked", "warp_affine", "ddim_", "mask_downsample", "cross_region", "kv_gather", "gn_stats", "gn_apply",
+    ours = {k: (round(v[0], 3), v[1]) for k, v in tot.items() if any(s in k for s in ("attn_masked", "attn_ring", "gn_fused", "warp_affine", "ddim_", "mask_downsample", "cross_region", "kv_gather", "gn_stats", "gn_apply",
                                                                                       "geglu_kernel", "layer_norm_kernel", "bias_residual"))}
     lines.append("# our kernels (ms, launches): %s" % ours)
     lines.append("# share of our kernels: %.1f%%   share of all ff_attn_masked_kv launches: %.1f%%" % (
-        100 * sum(v[0] for v in ours.values()) / total, 100 * sum(v[0] for k, v in ours.items() if "attn_masked" in k) / total))
+        100 * sum(v[0] for v in ours.values()) / total, 100 * sum(v[0] for k, v in ours.items() if "attn_masked" in k or "attn_ring" in k) / total))
     open(os.path.join(OUT, TAG + "_launches_summary.txt"), "w").write("\n".join(lines) + "\n")
     os.replace(PRE + "launches_bench.csv", os.path.join(OUT, TAG + "_launches_bench.csv")) if False else None
     print("\n".join(lines[:14]))
@@ -93,6 +94,17 @@ if __name__ == "__main__":
         open(cp, "w").writelines(l for l in open(PRE + "launches_bench.csv") if not l.startswith("=="))
         sys.exit(0)
     timing = open(PRE + "attn_case_timing.txt").read().strip()
+    if os.path.exists(PRE + "attn_d40_full.ncu-rep"):          # round 2: one capture per product attention kernel
+        full(PRE + "attn_d40_full.ncu-rep", os.path.join(OUT, TAG + "_attn_ncu_summary.txt"),
+             ["# %s -- ncu --set full --clock-control none, kernel attn_masked_kv_kernel<48,false> of profiles/attn_case.py" % TAG,
+              "# (ff_attn_masked_kv, 8 batched edits = 32 streams x 8 heads, S=4096, d=40, 'tca' plans, synthetic masks, fp16 P.V path;",
+              "#  the product kernel for d <= 40 in round 2: every ring-kernel layout measured slower at this shape)",
+              "# CUDA-event timing of the same launches OUTSIDE ncu (profiles/attn_case.py 5):"] + ["#   " + l for l in timing.splitlines()])
+        full(PRE + "attn_d80_full.ncu-rep", os.path.join(OUT, TAG + "_attn_d80_ncu_summary.txt"),
+             ["# %s -- ncu --set full --clock-control none, kernel attn_ring_kernel<80,2,3,false> of profiles/attn_case.py" % TAG,
+              "# (ff_attn_masked_kv, 32 streams x 8 heads, S=1024, d=80: the ring-buffered persistent kernel, csrc/attn_ring.cuh)",
+              "# CUDA-event timing of the same launches OUTSIDE ncu (profiles/attn_case.py 5):"] + ["#   " + l for l in timing.splitlines()])
+        sys.exit(0)
     full(PRE + "attn_full.ncu-rep", os.path.join(OUT, TAG + "_attn_ncu_summary.txt"),
          ["# %s -- ncu --set full --clock-control none, kernel attn_masked_kv_kernel<48,false> of profiles/attn_case.py" % TAG,
           "# (ff_attn_masked_kv, 8 batched edits = 32 streams x 8 heads, S=4096, d=40, 'tca' plans, synthetic masks, fp16 P.V path)",

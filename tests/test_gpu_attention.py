@@ -279,3 +279,43 @@ def test_error_paths(dev):
         ops.attn_masked_kv(q, q, q, ops.to_device_bytes(plans.plain_plan(4, 16), dev), 16, 1.0)
     with pytest.raises(RuntimeError):
         ops.attn_masked_kv(q.cpu(), q, q, pl, 8, 1.0)
+
+
+def test_style_align_bg_golden(dev, golden):
+    """style_align_share_attention_bg (attention.py:1193-1238): 'ssa' = [self ; ref] under one softmax; 'sdsa' with
+    prepare_sdsa_mask_for_bggen (:926-939): self half masked out, ref keys outside the object mask, on the Q0 pairs."""
+    g = golden["attention_bg"]
+    T = lambda k: torch.from_numpy(g[k])
+    sc = 8 ** -0.5
+    obj = O.process_mask_before_attention(T("style_bg/obj"), 64).numpy()
+    q, k, v = T("style_bg/q"), T("style_bg/k"), T("style_bg/v")
+    out = _run(dev, q, k, v, plans.style_align_plan(1, 8, None, bg=True), 8, sc, [obj])
+    assert float((out - T("style_bg_ssa/out")).abs().max()) < TOL
+    out = _run(dev, q, k, v, plans.style_align_plan(1, 8, lambda e: 0, bg=True), 8, sc, [obj])
+    assert float((out - T("style_bg_sdsa/out")).abs().max()) < TOL
+    out = _run(dev, q, k, v, plans.style_align_plan(1, 8, lambda e: 0, prefix=True, bg=True), 8, sc, [obj], sort_streams=[-1, 0, -1, 0])
+    assert float((out - T("style_bg_sdsa/out")).abs().max()) < TOL
+
+
+def test_s9216_head_slices_vs_oracle(dev):
+    """BASELINE.json configs[4]: 768^2 -> 96x96 latents, S = 9216, d = 40 (the ragged-free 144-tile case).  One edit
+    (4 streams x 8 heads) on the GPU; a masked head of the cond-edit stream, an unmasked head of the uncond-edit stream and a
+    masked head of a ref stream against the CPU oracle (one head slice each: seconds on the CPU)."""
+    heads, d, S = 8, 40, 9216
+    q, k, v = cases.qkv(4, S, heads * d, 1301)
+    src = O.process_mask_before_attention(torch.from_numpy(cases.blob_mask(768, 1302, (0.08, 0.2))), S).numpy()
+    tgt = O.process_mask_before_attention(torch.from_numpy(cases.blob_mask(768, 1303, (0.08, 0.2))), S).numpy()
+    cg = 0.35
+    plan = plans.tca_plan(1, heads, "tca", cg, lambda e: 0, lambda e: 1, prefix=True)
+    out = _run(dev, q, k, v, plan, heads, d ** -0.5, [src, tgt], sort_streams=[-1, 0, -1, 0])
+    srcb, tgtb = torch.from_numpy(src != 0), torch.from_numpy(tgt != 0)
+    allowed = torch.where(tgtb[:, None], srcb[None, :], ~srcb[None, :])
+    sl = lambda t, s, h: t[s, :, h * d:(h + 1) * d]
+    for s, h in ((2, 0), (0, 1), (3, 2)):
+        r = 1 if s < 2 else 3
+        masked = plans.q0_masked(heads, s, h)
+        ref_pass = O._softmax_av(sl(q, s, h), sl(k, r, h), sl(v, r, h), d ** -0.5, allowed if masked else None)
+        self_pass = O._softmax_av(sl(q, s, h), sl(k, s, h), sl(v, s, h), d ** -0.5)
+        ref = cg * ref_pass + (1 - cg) * self_pass
+        err = float((sl(out, s, h) - ref).abs().max())
+        assert err < TOL, (s, h, err)

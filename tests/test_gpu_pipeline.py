@@ -240,6 +240,22 @@ def test_re_edit_2d_matches_cv2_reference(dev, golden):
         assert np.abs(final.astype(np.int32) - g[name + "/coarse"].astype(np.int32)).max() <= 1, name
 
 
+def test_re_edit_2d_rotation_scale_matches_cv2_reference(dev, golden):
+    """re_edit_2d with rotation + anisotropic scale (tests/golden/coarse2d.npz, the unmodified reference's cv2 outputs): the
+    nearest-warped mask bit-exact (quirk Q11: the pixel-centre-exact theta), images within cv2's 1/32-pixel fixed-point
+    coordinate quantisation + uint8 rounding."""
+    from freefine_b200.coarse_edit import re_edit_2d
+    g = golden["coarse2d"]
+    for name, (seed, ep) in cases.COARSE2D_CASES.items():
+        img, m3, _, _, _ = cases.edit_case_inputs(seed, 128)
+        bg, _, _, _, _ = cases.edit_case_inputs(seed + 70, 128)
+        final, tmask, hole = re_edit_2d(img, m3, ep, bg)
+        assert np.array_equal(tmask, g[name + "/tmask"]), name
+        tol = 1 if name == "move" else 3
+        assert np.abs(final.astype(np.int32) - g[name + "/final"].astype(np.int32)).max() <= tol, name
+        assert np.abs(hole.astype(np.int32) - g[name + "/hole"].astype(np.int32)).max() <= tol, name
+
+
 def test_re_edit_3d_matches_cv2_reference(dev, golden):
     """re_edit_3d (vis_utils.py:275-339) on the warp kernel vs the outputs of the unmodified reference (cv2.warpAffine):
     the nearest-warped mask bit-exact, images within cv2's 1/32-pixel fixed-point coordinate quantisation (+ uint8

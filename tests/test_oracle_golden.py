@@ -114,3 +114,14 @@ def test_re_edit_2d_matches_reference(golden):
         final, tmask, hole = O.re_edit_2d(img, m3, ep, bg)
         assert np.array_equal(tmask, g[name + "/tmask"]) and np.array_equal(final, g[name + "/final"]), name
         assert np.array_equal(hole, g[name + "/hole"]), name
+
+
+def test_style_align_bg_matches_reference(golden):
+    """style_align_share_attention_bg: 'ssa' = plain [self ; ref] attention, 'sdsa' = mask 1 - [ones ; obj] on the Q0 pairs."""
+    g = golden["attention_bg"]
+    T = lambda k: torch.from_numpy(g[k])
+    obj = O.process_mask_before_attention(T("style_bg/obj"), 64).numpy()
+    out = O.style_align(T("style_bg/q"), T("style_bg/k"), T("style_bg/v"), 8, 8 ** -0.5, None, bg=True)
+    assert float((out - T("style_bg_ssa/out")).abs().max()) < 5e-5
+    out = O.style_align(T("style_bg/q"), T("style_bg/k"), T("style_bg/v"), 8, 8 ** -0.5, obj, bg=True)
+    assert float((out - T("style_bg_sdsa/out")).abs().max()) < 5e-5

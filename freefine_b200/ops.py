@@ -227,6 +227,40 @@ def mask_downsample_pack(masks, h, w, bits=None, popcount=None):
     return bits, popcount
 
 
+def mask_prep(shifted, ori, draw, cons, lat_hw, use_auto_draw, reduce_inp_artifacts):
+    """prepare_various_mask (model.py:1432-1512) for E edits in one launch: uint8 [E,H,W] masks (any non-zero = set; draw /
+    cons may be None where the reference does not read them) -> (fg, shifted, ori) uint8 [E,H,W] in {0,1} and
+    (completion, local_var) uint8 [E,h,w] in {0,1,2} (quirk Q1).  See ff_mask_prep."""
+    _chk(shifted, torch.uint8, "shifted", 3)
+    _chk(ori, torch.uint8, "ori", 3)
+    E, H, W = shifted.shape
+    for name, t in (("ori", ori), ("draw", draw), ("cons", cons)):
+        if t is not None:
+            _chk(t, torch.uint8, name, 3)
+            if tuple(t.shape) != (E, H, W):
+                raise ValueError(f"{name} must be [{E},{H},{W}], got {tuple(t.shape)}")
+    h, w = lat_hw
+    dev = shifted.device
+    fg, sh, orib = (torch.empty((E, H, W), dtype=torch.uint8, device=dev) for _ in range(3))
+    comp, lvar = (torch.empty((E, h, w), dtype=torch.uint8, device=dev) for _ in range(2))
+    rc = _lib.load().ff_mask_prep(_ptr(shifted), _ptr(ori), _ptr(draw), _ptr(cons), E, H, W, h, w, int(bool(use_auto_draw)),
+                                  int(bool(reduce_inp_artifacts)), _ptr(fg), _ptr(sh), _ptr(orib), _ptr(comp), _ptr(lvar), _stream())
+    _lib.check(rc, "ff_mask_prep")
+    _count("ff_mask_prep")
+    return fg, sh, orib, comp, lvar
+
+
+def dilate_mask(mask, k):
+    """cv2.dilate(mask != 0, ones(k, k)) on uint8 [N,H,W] (or [H,W]) CUDA masks -> {0,1}.  See ff_dilate_mask."""
+    m = mask if mask.dim() == 3 else mask[None]
+    _chk(m, torch.uint8, "mask", 3)
+    out = torch.empty_like(m)
+    rc = _lib.load().ff_dilate_mask(_ptr(m), _ptr(out), m.shape[0], m.shape[1], m.shape[2], int(k), _stream())
+    _lib.check(rc, "ff_dilate_mask")
+    _count("ff_dilate_mask")
+    return out if mask.dim() == 3 else out[0]
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # (a) attention
 # ---------------------------------------------------------------------------------------------------------------

@@ -327,11 +327,15 @@ class FreeFinePipeline:
 
     def dilate_mask(self, mask, dilate_factor=15):
         """cv2.dilate(mask.astype(uint8), ones(k,k)) (reference model.py:927-934): sliding max with the anchor at k//2,
-        outside = 0.  Returns a numpy uint8 array like the reference."""
+        outside = 0.  Returns a numpy uint8 array like the reference.  On a CUDA device binary masks go through
+        ff_dilate_mask; the CPU form (sliding max, also for non-binary masks) is the restatement the CPU tests pin."""
         k = int(dilate_factor)
         a = k // 2
         m = torch.from_numpy(np.ascontiguousarray(mask.astype(np.uint8))).to(self.device)
         squeeze = m.dim() == 2
+        if m.is_cuda and m.shape[1] % 4 == 0 and int(m.max()) <= 1:
+            y = ops.dilate_mask(m if squeeze else m.permute(2, 0, 1).contiguous(), k)
+            return (y if squeeze else y.permute(1, 2, 0)).cpu().numpy()
         x = (m[None, None] if squeeze else m.permute(2, 0, 1)[None]).float()
         x = F.pad(x, (a, k - 1 - a, a, k - 1 - a), value=0.0)
         y = F.max_pool2d(x, kernel_size=k, stride=1)
@@ -352,10 +356,38 @@ class FreeFinePipeline:
             t /= norm_
         return t
 
+    def _masks_for_kernel(self, masks, sup_res_w, sup_res_h, init_code):
+        """uint8 [1,H,W] device copies of the numpy masks when ff_mask_prep applies (CUDA, integer masks already at the
+        working resolution, latent grid dividing it); None sends the caller down the general per-op path."""
+        if self.device.type != 'cuda':
+            return None
+        lh, lw = init_code.shape[2], init_code.shape[3]
+        if sup_res_h % lh or sup_res_w % lw or sup_res_w % 4:
+            return None
+        out = []
+        for m in masks:
+            if m is None:
+                out.append(None)
+                continue
+            m = np.asarray(m)
+            m = m[:, :, 0] if m.ndim == 3 else m
+            if m.shape != (sup_res_h, sup_res_w) or m.dtype.kind not in 'ub':
+                return None
+            out.append(torch.from_numpy(np.ascontiguousarray(m.astype(np.uint8)))[None].to(self.device))
+        return out
+
     def prepare_various_mask(self, shifted_mask, ori_mask, draw_mask, sup_res_w, sup_res_h, init_code, verbose=False,
                              use_auto_draw=False, cons_area=None, reduce_inp_artifacts=False):
         """reference model.py:1432-1512 -> (fg_mask, shifted, ori, completion [lat], local_var [lat]).  The tensors are
         uint8 and the algebra wraps exactly like the reference (cons - ori, 1 - x: quirk Q1)."""
+        if use_auto_draw or reduce_inp_artifacts:
+            assert cons_area is not None, 'for auto draw / auto artifact expansion use cons area '
+        dev_masks = self._masks_for_kernel((shifted_mask, ori_mask, None if use_auto_draw else draw_mask,
+                                            cons_area if (use_auto_draw or reduce_inp_artifacts) else None),
+                                           sup_res_w, sup_res_h, init_code)
+        if dev_masks is not None:               # CUDA: dilations + algebra + down-sampling in one launch (ff_mask_prep)
+            r = ops.mask_prep(*dev_masks, (init_code.shape[2], init_code.shape[3]), use_auto_draw, reduce_inp_artifacts)
+            return tuple(t[0] for t in r)
         P = lambda m: self.prepare_tensor_mask(m, sup_res_w, sup_res_h)
         if not use_auto_draw:
             if not reduce_inp_artifacts:
@@ -768,6 +800,10 @@ class FreeFinePipeline:
     def prepare_various_mask_batch(self, shifted, ori, draw, cons, lat_hw, use_auto_draw, reduce_inp_artifacts):
         """prepare_various_mask (model.py:1432-1512) for E edits at once on device tensors [E,H,W] uint8 (any nonzero =
         set).  Same uint8 algebra (wrap-around included, quirk Q1) as the per-edit method."""
+        if shifted.is_cuda:                     # one launch (ff_mask_prep); the algebra below is its CPU restatement
+            need_cons = use_auto_draw or reduce_inp_artifacts
+            return ops.mask_prep(shifted.contiguous(), ori.contiguous(), None if use_auto_draw else draw.contiguous(),
+                                 cons.contiguous() if need_cons else None, lat_hw, use_auto_draw, reduce_inp_artifacts)
         b = lambda t: (t > 0).to(torch.uint8)
 
         def dil(t, k):

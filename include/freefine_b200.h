@@ -134,6 +134,22 @@ int ff_kv_gather_cast(const void* k, const void* v, const int64_t* row_index, vo
 int ff_mask_downsample_pack(const uint8_t* masks, int32_t n, int32_t H, int32_t W, int32_t h, int32_t w,
                             uint32_t* bits, int32_t words, int32_t* popcount, void* stream);
 
+/* Mask preparation of E edits in one launch.  Replaces FreeFinePipeline.prepare_various_mask (src/demo/model.py:1432-1512)
+ * incl. its dilate_mask calls (:927-934: cv2.dilate with a 15 x 15 / 30 x 30 ones kernel, anchor k/2), prepare_tensor_mask
+ * (:1622-1639, `> 0` binarisation) and the nearest down-sampling of the completion / local-variance masks to the latent
+ * grid (:1505-1511).  All inputs uint8 [E,H,W], any non-zero = set: shifted (target mask), ori (source-object mask), draw
+ * (user completion region; may be NULL with use_auto_draw), cons (constraint area; may be NULL when neither flag is set).
+ * Outputs uint8: fg / shifted_out / ori_out [E,H,W] in {0,1} (the controller's fg_retain / fg_retain_st2 / fg_ref masks),
+ * comp_lat / lvar_lat [E,h,w] in {0,1,2} -- the uint8 wrap-around of the reference's `cons - ori` and `1 - x` (quirk Q1)
+ * is reproduced bit for bit.  H % h == 0, W % w == 0, W % 4 == 0.                                                    */
+int ff_mask_prep(const uint8_t* shifted, const uint8_t* ori, const uint8_t* draw, const uint8_t* cons, int32_t E,
+                 int32_t H, int32_t W, int32_t h, int32_t w, int32_t use_auto_draw, int32_t reduce_inp_artifacts,
+                 uint8_t* fg, uint8_t* shifted_out, uint8_t* ori_out, uint8_t* comp_lat, uint8_t* lvar_lat, void* stream);
+
+/* out[n] = cv2.dilate(mask[n] != 0, ones(k, k)) (anchor k/2, outside = 0), uint8 [N,H,W] -> {0,1}: dilate_mask
+ * (model.py:927-934, src/utils/vis_utils.py:340-347).  W % 4 == 0.                                                    */
+int ff_dilate_mask(const uint8_t* mask, uint8_t* out, int32_t N, int32_t H, int32_t W, int32_t k, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * (b) fused affine warp + resample + mask-guided blend
  *

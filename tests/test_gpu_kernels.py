@@ -197,3 +197,53 @@ def test_kv_gather_cast_bit_exact(dev):
         k3, v3 = ops.kv_gather_cast(k, v, heads, idx, p_operand="bf16x2")          # bf16 staging: plain copy + ones column
         assert v3.data.dtype == torch.bfloat16 and torch.equal(v3.values().view(600, C), v.view(600, C)[idx])
         assert bool((v3.data[..., d] == 1).all()) and bool((v3.data[..., d + 1:] == 0).all())
+
+
+def _blob_masks(rng, E, H, W, val):
+    """Random rectangles + speckle, some touching the border (the dilation windows clip there)."""
+    m = np.zeros((E, H, W), np.uint8)
+    for e in range(E):
+        for _ in range(int(rng.integers(1, 4))):
+            y0, x0 = int(rng.integers(0, H - 8)), int(rng.integers(0, W - 8))
+            m[e, y0:y0 + int(rng.integers(4, H // 2)), x0:x0 + int(rng.integers(4, W // 2))] = val
+        m[e][rng.random((H, W)) < 0.001] = val
+    m[0, :3, :] = val
+    m[-1, :, -2:] = val
+    return m
+
+
+@pytest.mark.parametrize("H,W,h,w", [(128, 128, 16, 16), (512, 512, 64, 64), (768, 512, 96, 64), (64, 100, 8, 25)])
+def test_mask_prep_bit_exact(dev, H, W, h, w):
+    """ff_mask_prep (dilations + uint8 algebra incl. the {0,1,2} wrap of quirk Q1 + latent down-sampling, one launch)
+    vs the oracle's prepare_various_mask (model.py:1432-1512) per edit; ff_dilate_mask vs the oracle's dilate_mask."""
+    from freefine_b200 import ops
+    rng = np.random.default_rng(H + W)
+    E = 3
+    shifted, ori = _blob_masks(rng, E, H, W, 255), _blob_masks(rng, E, H, W, 1)
+    draw, cons = _blob_masks(rng, E, H, W, 1), _blob_masks(rng, E, H, W, 255)
+    cons[1] = 0                                             # cons - ori wraps wherever ori is set
+    up = lambda a: torch.from_numpy(a).to(dev)
+    for auto in (False, True):
+        for red in (False, True):
+            got = ops.mask_prep(up(shifted), up(ori), None if auto else up(draw), up(cons) if (auto or red) else None,
+                                (h, w), auto, red)
+            for e in range(E):
+                ref = O.prepare_various_mask(shifted[e], ori[e], draw[e], W, H, h, w, use_auto_draw=auto, cons_area=cons[e],
+                                             reduce_inp_artifacts=red)
+                for nm, t, r in zip(("fg", "sh", "ori", "comp", "lvar"), got, ref):
+                    assert t.dtype == torch.uint8
+                    assert np.array_equal(t[e].cpu().numpy(), r.numpy()), (auto, red, e, nm)
+    if W % 4 == 0:
+        for k in (1, 2, 15, 30):
+            got = ops.dilate_mask(up(ori), k).cpu().numpy()
+            for e in range(E):
+                assert np.array_equal(got[e], O.dilate_mask(ori[e], k)), (k, e)
+
+
+def test_mask_prep_rejects_bad_input(dev):
+    from freefine_b200 import ops
+    z = torch.zeros(1, 64, 64, dtype=torch.uint8, device=dev)
+    with pytest.raises(RuntimeError):
+        ops.mask_prep(z, z, None, None, (8, 8), True, True)       # cons_area missing (the reference asserts)
+    with pytest.raises(RuntimeError):
+        ops.mask_prep(z, z, z, z, (7, 8), False, False)           # latent grid does not divide the image

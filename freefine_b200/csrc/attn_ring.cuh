@@ -49,6 +49,11 @@ template <int DPAD_, int NWG_, int NBUF_> struct RCfg {
   static constexpr int MIN_CTAS = TMEM_COLS == 256 ? 2 : 1;
   static constexpr int NUM_WARPS = 4 * NWG + 4;                        // softmax warps, K producer, QK issuer, PV issuer, V producer
   static constexpr int NUM_THREADS = 32 * NUM_WARPS;
+  // Register rebalancing (setmaxnreg) for the 20-warp layout: ptxas caps the kernel at 65536 / 640 -> 96 registers; the four
+  // auxiliary warps (one warpgroup) release down to 32, which lets the 16 softmax warps grow to 112 -- the whole 64-column
+  // row stays in registers.  (512 * 112 + 128 * 32 = 61440 = 640 * 96.)
+  static constexpr bool REBALANCE = false;
+  static constexpr int REG_AUX = 32, REG_SOFTMAX = 112;
   static constexpr int SMEM_Q = NKT * TILE_BYTES;
   static constexpr int SMEM_K = NKT * KV_BYTES;                        // one K stage == one V stage
   static constexpr int ACC_LD = DPAD + 4;
@@ -351,6 +356,10 @@ attn_ring_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     return plan;
   };
 
+  if constexpr (C::REBALANCE) {
+    if (warp >= SW) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REG_AUX));
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::REG_SOFTMAX));
+  }
   if (warp == SW || warp == SW + 3) {
     // ===================================== TMA producers ====================================
     // Two single-thread producers (every mbarrier operation of a thread costs ~100-250 cycles of latency, and one thread

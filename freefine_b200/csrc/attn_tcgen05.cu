@@ -28,6 +28,7 @@
 
 #include <atomic>
 #include <cstdlib>
+#include <type_traits>
 
 #include "ff_common.cuh"
 
@@ -131,7 +132,16 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
+// Slow path of every wait.  A waiting warp is woken many times before its phase completes (ncu source counters, round 2:
+// ~7 wake-ups per wait -- NANOSLEEP.SYNCS returns on every event of the barrier), and with a clock64 time-out check in
+// the loop each wake-up cost 12 issue slots: 22 % of ALL instructions the d = 40 launch executed were this loop, taken
+// from the softmax warps that share the schedulers.  The loop is now try_wait + a counter; the loud time-out (a protocol
+// bug must fail, not hang the GPU) is counted in wake-ups instead of cycles.
+#ifndef FF_WAIT_FORM
+#define FF_WAIT_FORM 1   // 0: clock64 time-out (round 1), 1: counted, try_wait with suspend hint, 2: counted, plain try_wait
+#endif
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+#if FF_WAIT_FORM == 0
   const long long t0 = clock64();
   while (!mbar_try(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {   // ~2 s: a protocol bug must fail loudly, not hang the GPU
@@ -140,6 +150,27 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
       __trap();
     }
   }
+#else
+#pragma unroll 1
+  for (uint32_t n = 0; n < (1u << 26); ++n) {
+#if FF_WAIT_FORM == 1
+    if (mbar_try(bar, parity)) return;
+#else
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+#endif
+  }
+  printf("ff_attn: mbarrier wait timed out (block %d,%d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y,
+         blockIdx.z, threadIdx.x, bar, parity);
+  __trap();
+#endif
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
@@ -515,6 +546,88 @@ __device__ __forceinline__ void softmax_chunk_f16(const float* s, uint32_t* pk, 
   }
 }
 
+
+// ---- lean issue blocks of the d <= 40 fp16-P issuer warp (FF_LEAN_ISSUER): ONE asm statement per tile, executed by the
+// whole warp (the election happens inside); the per-K-step descriptor / TMEM-address arithmetic is done inside on PTX
+// registers.  (With `if (leader) { mma; ...; commit; }` in C++ ptxas keeps every precomputed operand in vector registers
+// and moves it to a uniform register with R2UR per tile: ~120 mostly serial instructions = ~500 cycles per tile, all of
+// them inside the p_full -> s_full(t+2) window during which the owning softmax warpgroup idles.)
+#ifndef FF_LEAN_ISSUER
+#define FF_LEAN_ISSUER 1
+#endif
+__device__ __forceinline__ void lean_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+#ifdef FF_LEAN_SPIN   // experiment: poll instead of the hardware-sleep wait (wake-up latency vs issue slots)
+  for (int n = 0; !done && n < FF_LEAN_SPIN; ++n) done = mbar_test(bar, parity);
+#endif
+  if (!done) mbar_wait_slow(bar, parity);
+}
+// S = Q K^T for DPAD = 48: three K-steps of 16 channels (32 B inside the 128-B row = 2 descriptor units), then the commit
+__device__ __forceinline__ void lean_qk48(uint32_t sbuf, uint64_t qdesc, uint64_t kdesc, uint32_t idesc, uint32_t bar_s_) {
+  asm volatile(
+      "{\n\t.reg .pred e, pf, pt;\n\t.reg .b64 q1, q2, k1, k2;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 pf, 0, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+      "add.u64 q1, %1, 2;\n\tadd.u64 q2, %1, 4;\n\tadd.u64 k1, %2, 2;\n\tadd.u64 k2, %2, 4;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pf;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], q1, k1, %3, pt;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], q2, k2, %3, pt;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%4];\n\t}"
+      ::"r"(sbuf), "l"(qdesc), "l"(kdesc), "r"(idesc), "r"(bar_s_)
+      : "memory");
+}
+// O (+)= P V: four K-steps of 16 keys (A = packed fp16 P in TMEM at columns +0, +8, +32, +40 of the S/P buffer, B = V tile
+// MN-major, 2048 B = 128 descriptor units per K-step), commit kv_empty; then -- WITH_QK -- S = Q K^T of the same buffer's
+// next tile right behind it in the pipe and its s_full commit, or -- last tiles of a parity -- a virtual s_full commit.
+template <bool WITH_QK>
+__device__ __forceinline__ void lean_pv_qk48(uint32_t obuf, uint32_t sp, uint64_t vdesc, uint32_t idesc_pv, uint32_t acc0,
+                                             uint32_t bar_kve, uint64_t qdesc, uint64_t kdesc, uint32_t idesc_qk,
+                                             uint32_t bar_s_) {
+  if constexpr (WITH_QK) {
+    asm volatile(
+        "{\n\t.reg .pred e, p0, pf, pt;\n\t.reg .b64 v1, v2, v3, q1, q2, k1, k2;\n\t.reg .b32 a1, a2, a3;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p0, %4, 0;\n\tsetp.ne.b32 pf, 0, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+        "add.u64 v1, %2, 128;\n\tadd.u64 v2, %2, 256;\n\tadd.u64 v3, %2, 384;\n\t"
+        "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 32;\n\tadd.u32 a3, %1, 40;\n\t"
+        "add.u64 q1, %6, 2;\n\tadd.u64 q2, %6, 4;\n\tadd.u64 k1, %7, 2;\n\tadd.u64 k2, %7, 4;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], v1, %3, pt;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], v2, %3, pt;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], v3, %3, pt;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], %6, %7, %8, pf;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], q1, k1, %8, pt;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], q2, k2, %8, pt;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t}"
+        ::"r"(obuf), "r"(sp), "l"(vdesc), "r"(idesc_pv), "r"(acc0), "r"(bar_kve), "l"(qdesc), "l"(kdesc), "r"(idesc_qk),
+          "r"(bar_s_)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred e, p0, pt;\n\t.reg .b64 v1, v2, v3;\n\t.reg .b32 a1, a2, a3;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p0, %4, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+        "add.u64 v1, %2, 128;\n\tadd.u64 v2, %2, 256;\n\tadd.u64 v3, %2, 384;\n\t"
+        "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 32;\n\tadd.u32 a3, %1, 40;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], v1, %3, pt;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], v2, %3, pt;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], v3, %3, pt;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t}"
+        ::"r"(obuf), "r"(sp), "l"(vdesc), "r"(idesc_pv), "r"(acc0), "r"(bar_kve), "r"(bar_s_)
+        : "memory");
+  }
+}
+
 template <int DPAD, bool P_HILO>
 __global__ void __launch_bounds__(NUM_THREADS, Cfg<DPAD, P_HILO>::MIN_CTAS)
 attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -678,6 +791,44 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       }
       FF_TRACE(0, 20);
       mbar_wait(bar_q, 0);
+      if constexpr (FF_LEAN_ISSUER && DPAD == 48 && !P_HILO && C::NSTAGE == 4) {
+        // Lean flat loop, unrolled over one turn of the four-stage K/V ring: tile t = 4g + u sits in stage u, its S/P
+        // buffer and accumulator have parity u & 1, p_full(t) has phase (u >> 1) & 1, and the K/V stage of tile t + 2 is
+        // (u + 2) & 3 with phase g (u < 2) or g + 1 -- everything but g is a compile-time constant.  kv_full(t + 2) is
+        // waited for BEFORE p_full(t) (no deadlock with four stages: its refill only needed PV(t - 2)).
+        tc_fence_after();
+        if (n_total > 0) { lean_wait(bar_kv_full, 0); tc_fence_after(); lean_qk48(tmem + C::TMEM_S, qdesc0, kdesc0, idesc_qk, bar_s); }
+        if (n_total > 1) {
+          lean_wait(bar_kv_full + 8, 0);
+          tc_fence_after();
+          lean_qk48(tmem + C::TMEM_S + BN, qdesc0, kdesc0 + (uint64_t)(C::SMEM_STAGE >> 4), idesc_qk, bar_s + 8);
+        }
+        uint32_t gph = 0;
+        int t = 0;
+#pragma unroll 1
+        while (t < n_total) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (t < n_total) {
+              const bool more = t + 2 < n_total;
+              const int pstart = t >= pe2 ? pe2 : (t >= pe1 ? pe1 : (t >= pe0 ? pe0 : 0));
+              const uint32_t acc0 = (t - pstart < 2) ? 0u : 1u;      // the first tile of each parity in a pass starts O
+              const uint32_t sp = tmem + C::TMEM_S + BN * (u & 1);
+              const uint32_t obuf = tmem + C::TMEM_O + C::DPV * (u & 1);
+              const uint64_t vd = vdesc0 + (uint64_t)((u * C::SMEM_STAGE) >> 4);
+              const uint64_t kd = kdesc0 + (uint64_t)((((u + 2) & 3) * C::SMEM_STAGE) >> 4);
+              if (more) lean_wait(bar_kv_full + 8 * ((u + 2) & 3), u < 2 ? gph : gph ^ 1u);
+              lean_wait(bar_p + 8 * (u & 1), (uint32_t)((u >> 1) & 1));
+              tc_fence_after();
+              if (more) lean_pv_qk48<true>(obuf, sp, vd, idesc_pv, acc0, bar_kv_empty + 8 * u, qdesc0, kd, idesc_qk, bar_s + 8 * (u & 1));
+              else lean_pv_qk48<false>(obuf, sp, vd, idesc_pv, acc0, bar_kv_empty + 8 * u, 0, 0, 0, bar_s + 8 * (u & 1));
+              ++t;
+            }
+          }
+          gph ^= 1u;
+        }
+        __syncwarp();
+      } else {
       int qk_t = 0;                                   // next tile whose S = Q K^T is to be issued
       uint32_t q_stage = 0, q_phase = 0, p_stage = 0;
       auto wait_kv = [&]() { mbar_wait_hot<1>(bar_kv_full + 8 * q_stage, q_phase); };
@@ -757,6 +908,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         if (++p_stage == (uint32_t)C::NSTAGE) p_stage = 0;
       }
       __syncwarp();
+      }
     }
   } else {
     // ===================================== softmax + epilogue ===============================
@@ -1162,7 +1314,7 @@ int ring_mode() {
   if (mode < 0) {
     const char* e = getenv("FF_ATTN_RING");
     mode = e ? atoi(e) : FF_RING_DEFAULT;
-    if (mode < 0 || mode > 6) mode = FF_RING_DEFAULT;
+    if (mode < 0 || mode > 7) mode = FF_RING_DEFAULT;
   }
   return mode;
 }
@@ -1259,6 +1411,7 @@ extern "C" int ff_attn_masked_kv(const FFAttnArgs* a, void* stream) {
     if (rm == 1 && d <= 40) return launch_ring<48, 1, 3, false>(mq, mk, mv, kp, a->n_streams, st);
     if (rm == 2 && d <= 40) return launch_ring<48, 2, 4, false>(mq, mk, mv, kp, a->n_streams, st);
     if (rm == 3 && d <= 40) return launch_ring<48, 3, 5, false>(mq, mk, mv, kp, a->n_streams, st);
+    if (rm == 7 && d <= 40) return launch_ring<48, 4, 5, false>(mq, mk, mv, kp, a->n_streams, st);
     if (rm == 4 && d <= 40) return launch_ring<48, 3, 5, true>(mq, mk, mv, kp, a->n_streams, st);
     if (rm == 5 && d <= 40) return launch_ring<48, 2, 4, true>(mq, mk, mv, kp, a->n_streams, st);
     if (d > 40 && d <= 80 && (rm == 4 || rm == 5)) return launch_ring<80, 2, 3, true>(mq, mk, mv, kp, a->n_streams, st);

@@ -37,7 +37,16 @@ for cta in range(2):
         a = [int(x - t0) if x else -1 for x in sm[i, :7]]
         b = [int(x - t0) if x else -1 for x in mm[i, :5]]
         print(f"tile {i:2d} S " + " ".join(f"{x:7d}" for x in a) + "  | M " + " ".join(f"{x:7d}" for x in b))
-    dt = np.diff(sm[4:40, 0].astype(np.int64))
-    print("softmax tile period: mean %.0f  min %d  max %d" % (dt.mean(), dt.min(), dt.max()))
-    seg = (sm[4:40, 1:7] - sm[4:40, 0:6]).astype(np.int64)
-    print("mean phase durations: wait_s %.0f  load %.0f  max %.0f  exp %.0f  st_wait %.0f  arrive %.0f" % tuple(seg.mean(0)))
+    rows = [i for i in range(4, 60) if sm[i, 0] and sm[i, 6]]              # this warp's tiles (one parity)
+    dt = np.diff(sm[rows, 0].astype(np.int64))
+    print("softmax tile period (own tiles): mean %.0f  min %d  max %d" % (dt.mean(), dt.min(), dt.max()))
+    seg = (sm[rows, 1:7] - sm[rows, 0:6]).astype(np.int64)
+    print("mean phase durations: wait_s %.0f  load+max(h0) %.0f  load+max(h1) %.0f  exp %.0f  st_wait %.0f  arrive %.0f" % tuple(seg.mean(0)))
+    mrows = [i for i in range(4, 60) if mm[i, 0] and mm[i, 4]]
+    if mrows:
+        md = np.diff(mm[mrows, 0].astype(np.int64))
+        print("issuer tile period: mean %.0f; p_full wait %.0f, issue %.0f" % (md.mean(), (mm[mrows, 3] - mm[mrows, 0]).mean(), (mm[mrows, 4] - mm[mrows, 3]).mean()))
+        # hand-shake: softmax arrive(t) -> issuer saw p_full(t); issuer issued -> softmax saw s_full(t+2)
+        hs1 = [int(mm[i, 3] - sm[i, 6]) for i in rows if mm[i, 3]]
+        hs2 = [int(sm[i + 2, 1] - mm[i, 4]) for i in rows if i + 2 < 64 and sm[i + 2, 1] and mm[i, 4]]
+        print("arrive(t) -> issuer resumed: mean %.0f | PV(t),QK(t+2) issued -> softmax resumed on s_full(t+2): mean %.0f" % (np.mean(hs1), np.mean(hs2)))

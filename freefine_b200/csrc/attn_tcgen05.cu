@@ -58,6 +58,9 @@ template <bool HILO> constexpr float rescale_threshold() { return HILO ? 24.f : 
 #ifndef FF_POLY_PATTERN
 #define FF_POLY_PATTERN 0x92
 #endif
+#ifndef FF_SELF_ISSUE
+#define FF_SELF_ISSUE 0   // experiment switch (measured slower: 2.84 vs 2.35 ms, profiles/r2b_attn_experiments.txt)
+#endif
 
 // DPAD: head_dim padded to the K-step of Q K^T (a multiple of 16).  DPV: channels per head of the staged V = columns
 // of the V tile / of O: head_dim real channels, a column of ONES at channel head_dim (its P.V column is the softmax
@@ -82,6 +85,12 @@ template <int DPAD, bool HILO> struct Cfg {
   static constexpr int SMEM_BYTES = SMEM_Q + NSTAGE * SMEM_STAGE + SMEM_ACC + SMEM_MX + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static constexpr int MIN_CTAS = (SMEM_BYTES <= 113 * 1024 && TMEM_COLS == 256) ? 2 : 1;
+  // SELF (d <= 40, fp16 P): there is no MMA-issuer warp.  When a softmax warpgroup has stored its P tile it meets on a
+  // named barrier and its first warp issues PV(t) and QK(t+2) itself -- the p_full mbarrier round trip (arrive -> the
+  // sleeping issuer warp resumes: ~330 cycles in the round-2 timelines, on the critical chain of every tile) is replaced
+  // by a bar.sync among four warps, and nine warps instead of ten leave 112 instead of 96 registers per thread.
+  static constexpr bool SELF = FF_SELF_ISSUE && DPAD == 48 && !HILO && NSTAGE == 4;
+  static constexpr int THREADS = SELF ? 32 * (NUM_SOFTMAX_WARPS + 1) : NUM_THREADS;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -537,6 +546,10 @@ __device__ __forceinline__ void softmax_chunk_f16(const float* s, uint32_t* pk, 
       x.x = (bits >> (2 * i)) & 1u ? x.x : -INFINITY;
       x.y = (bits >> (2 * i + 1)) & 1u ? x.y : -INFINITY;
       e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+#ifdef FF_KO_EXP     // timing experiment only (wrong results): no exp2 at all, neither MUFU nor polynomial
+    } else if (true) {
+      e = x;
+#endif
     } else if ((FF_POLY_PATTERN >> i) & 1) {
       e = poly_exp2_x2(x);
     } else {
@@ -586,6 +599,17 @@ __device__ __forceinline__ void lean_qk48(uint32_t sbuf, uint64_t qdesc, uint64_
 // O (+)= P V: four K-steps of 16 keys (A = packed fp16 P in TMEM at columns +0, +8, +32, +40 of the S/P buffer, B = V tile
 // MN-major, 2048 B = 128 descriptor units per K-step), commit kv_empty; then -- WITH_QK -- S = Q K^T of the same buffer's
 // next tile right behind it in the pipe and its s_full commit, or -- last tiles of a parity -- a virtual s_full commit.
+// timing experiments only (wrong results): -DFF_KO_PV1 / -DFF_KO_QK1 issue only the first K-step of P.V / Q.K^T
+#ifdef FF_KO_PV1
+#define FF_KO_PVSTEPS(x)
+#else
+#define FF_KO_PVSTEPS(x) x
+#endif
+#ifdef FF_KO_QK1
+#define FF_KO_QKSTEPS(x)
+#else
+#define FF_KO_QKSTEPS(x) x
+#endif
 template <bool WITH_QK>
 __device__ __forceinline__ void lean_pv_qk48(uint32_t obuf, uint32_t sp, uint64_t vdesc, uint32_t idesc_pv, uint32_t acc0,
                                              uint32_t bar_kve, uint64_t qdesc, uint64_t kdesc, uint32_t idesc_qk,
@@ -599,13 +623,13 @@ __device__ __forceinline__ void lean_pv_qk48(uint32_t obuf, uint32_t sp, uint64_
         "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 32;\n\tadd.u32 a3, %1, 40;\n\t"
         "add.u64 q1, %6, 2;\n\tadd.u64 q2, %6, 4;\n\tadd.u64 k1, %7, 2;\n\tadd.u64 k2, %7, 4;\n\t"
         "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p0;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], v1, %3, pt;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], v2, %3, pt;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], v3, %3, pt;\n\t"
+        FF_KO_PVSTEPS("@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], v1, %3, pt;\n\t")
+        FF_KO_PVSTEPS("@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], v2, %3, pt;\n\t")
+        FF_KO_PVSTEPS("@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], v3, %3, pt;\n\t")
         "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t"
         "@e tcgen05.mma.cta_group::1.kind::f16 [%1], %6, %7, %8, pf;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], q1, k1, %8, pt;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], q2, k2, %8, pt;\n\t"
+        FF_KO_QKSTEPS("@e tcgen05.mma.cta_group::1.kind::f16 [%1], q1, k1, %8, pt;\n\t")
+        FF_KO_QKSTEPS("@e tcgen05.mma.cta_group::1.kind::f16 [%1], q2, k2, %8, pt;\n\t")
         "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t}"
         ::"r"(obuf), "r"(sp), "l"(vdesc), "r"(idesc_pv), "r"(acc0), "r"(bar_kve), "l"(qdesc), "l"(kdesc), "r"(idesc_qk),
           "r"(bar_s_)
@@ -629,7 +653,7 @@ __device__ __forceinline__ void lean_pv_qk48(uint32_t obuf, uint32_t sp, uint64_
 }
 
 template <int DPAD, bool P_HILO>
-__global__ void __launch_bounds__(NUM_THREADS, Cfg<DPAD, P_HILO>::MIN_CTAS)
+__global__ void __launch_bounds__(Cfg<DPAD, P_HILO>::THREADS, Cfg<DPAD, P_HILO>::MIN_CTAS)
 attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                       const __grid_constant__ CUtensorMap tm_v, const KParams p) {
   using C = Cfg<DPAD, P_HILO>;
@@ -743,7 +767,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         }
       }
     }
-  } else if (warp == NUM_SOFTMAX_WARPS + 1) {
+  } else if (!C::SELF && warp == NUM_SOFTMAX_WARPS + 1) {
     // ===================================== MMA issuer =======================================
     // The WHOLE warp runs this warp-uniform loop, so that descriptors, barrier addresses and counters live in uniform
     // registers; only the elected lane executes tcgen05.mma / tcgen05.commit.  (Running the loop inside `if (lane == 0)`
@@ -925,6 +949,43 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     float* const acc_row = acc_smem + (size_t)rloc * C::ACC_LD;
     bool acc_started = false;       // has any pass been added to the accumulator yet (uniform across the CTA)
     int it = 0;                     // global tile counter (all roles count alike)
+    // ---- SELF: the first warp of each warpgroup is the MMA issuer of the warpgroup's tiles (tile t sits in K/V stage
+    // t % 4, its S/P buffer and accumulator have the warpgroup's parity)
+    int n_total = 0;
+    [[maybe_unused]] constexpr uint32_t s_idesc_qk = make_idesc(BN, 0);
+    [[maybe_unused]] constexpr uint32_t s_idesc_pv = make_idesc(C::DPV, 1, !P_HILO);
+    [[maybe_unused]] const uint64_t s_qdesc0 = smem_desc_sw128(sQ, 16);
+    [[maybe_unused]] const uint64_t s_kdesc0 = smem_desc_sw128(sKV, 16);
+    [[maybe_unused]] const uint64_t s_vdesc0 = smem_desc_sw128(sKV + C::NKT * KV_BYTES, KV_BYTES);
+    if constexpr (C::SELF) {
+      if (wq == 0) {
+#pragma unroll 1
+        for (int ip = 0; ip < n_pass; ++ip) {             // tiles of the whole CTA (same decisions as every role)
+          const FFAttnPass ps = plan->pass[ip];
+          const PassCtx cx = make_ctx(ps, p, q0);
+          if (!cx.active) continue;
+#pragma unroll 1
+          for (int seg = 0; seg < 2; ++seg) {
+            const SegCtx sg = seg ? cx.s1 : cx.s0;
+            if (sg.kv < 0) continue;
+#pragma unroll 1
+            for (int j0 = 0; j0 < n_kv_tiles;) {
+              const int cls = tile_class(sg, j0, p), j1 = run_end(sg, j0, cls, p), jb = j0;
+              j0 = j1;
+              if (!tile_skip(cx, sg, cls, p.s_kv)) n_total += j1 - jb;
+            }
+          }
+        }
+        n_total = __shfl_sync(0xffffffffu, n_total, 0);
+        if (wg < n_total) {                                 // S of my first tile (tile wg, stage wg)
+          mbar_wait(bar_q, 0);
+          lean_wait(bar_kv_full + 8 * wg, 0);
+          tc_fence_after();
+          lean_qk48(tmem + C::TMEM_S + BN * wg, s_qdesc0, s_kdesc0 + (uint64_t)((wg * C::SMEM_STAGE) >> 4), s_idesc_qk,
+                    bar_s + 8 * wg);
+        }
+      }
+    }
 #pragma unroll 1
     for (int ip = 0; ip < n_pass; ++ip) {
       const FFAttnPass ps = plan->pass[ip];
@@ -1012,8 +1073,13 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
               mt = fmaxf(m0, m1);
             }
             {
+#ifdef FF_KO_LD2      // timing experiment only (wrong results): columns [32,64) are never read
+#pragma unroll
+              for (int i = 0; i < 32; ++i) sb[i] = mt + (float)i;
+#else
               tmem_ld32(tS + 32, sb);
               tmem_wait_ld32(sb);
+#endif
               float m0, m1;
               if (cls != TILE_MIX) {
                 m0 = fmaxf(sb[0], sb[1]);
@@ -1070,11 +1136,15 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 #pragma unroll
             for (int hb = 1; hb >= 0; --hb) {
               float sa[32];
+#ifdef FF_KO_REREAD   // timing experiment only (wrong results): columns [0,32) are not read a second time
+              const float* sv = sb;
+#else
               if (hb == 0) {
                 tmem_ld32(tS, sa);
                 tmem_wait_ld32(sa);
               }
               const float* sv = hb ? sb : sa;
+#endif
               const uint32_t kbits = hb ? kb_hi : kb_lo;
               if (cls != TILE_MIX) {
 #pragma unroll
@@ -1101,8 +1171,25 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             tmem_wait_st();
             FF_TL(0, itj, 5);
             tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_p + 8 * wg);
+            if constexpr (C::SELF) {
+              named_bar_sync(3 + wg, 128);                 // every row of P(itj) has been stored
+              if (wq == 0) {
+                const int stg = itj & 3, nxt = (itj + 2) & 3;
+                const bool more = itj + 2 < n_total;
+                if (more) lean_wait(bar_kv_full + 8 * nxt, (uint32_t)(((itj + 2) >> 2) & 1));
+                tc_fence_after();
+                const uint32_t sp = tmem + C::TMEM_S + BN * wg;
+                const uint32_t obuf = tmem + C::TMEM_O + C::DPV * wg;
+                const uint64_t vd = s_vdesc0 + (uint64_t)((stg * C::SMEM_STAGE) >> 4);
+                const uint64_t kd = s_kdesc0 + (uint64_t)((nxt * C::SMEM_STAGE) >> 4);
+                const uint32_t acc0 = n_mine == 0 ? 0u : 1u;   // my first tile of the pass starts the accumulator
+                if (more) lean_pv_qk48<true>(obuf, sp, vd, s_idesc_pv, acc0, bar_kv_empty + 8 * stg, s_qdesc0, kd, s_idesc_qk, bar_s + 8 * wg);
+                else lean_pv_qk48<false>(obuf, sp, vd, s_idesc_pv, acc0, bar_kv_empty + 8 * stg, 0, 0, 0, bar_s + 8 * wg);
+              }
+            } else {
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_p + 8 * wg);
+            }
             FF_TL(0, itj, 6);
             FF_TRACE(itj, 34);
             ++n_mine;
@@ -1272,7 +1359,7 @@ int launch(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, 
   int rc = ensure_smem(attn_masked_kv_kernel<DPAD, HILO>, C::SMEM_BYTES, configured);
   if (rc != FF_OK) return rc;
   dim3 grid((kp.s_q + BM - 1) / BM, kp.heads, n_streams);
-  attn_masked_kv_kernel<DPAD, HILO><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(mq, mk, mv, kp);
+  attn_masked_kv_kernel<DPAD, HILO><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(mq, mk, mv, kp);
   return ff::check_launch("ff_attn_masked_kv");
 }
 

@@ -839,11 +839,14 @@ class FreeFinePipeline:
     def FreeFine_generation_batch(self, ori_imgs, ori_masks, edit_params, guidance_texts, guidance_scale=7.5, eta=1.0,
                                   end_step=50, num_step=50, start_step=35, method_type='tca', seed=42, draw_masks=None,
                                   use_auto_draw=True, reduce_inp_artifacts=True, end_scale=0.0, inp_bgs=None,
-                                  thetas=None, return_latents=False):
+                                  thetas=None, return_latents=False, coarse_inputs=None, target_masks=None):
         """E whole 2-D edits (coarse warp+blend -> DDIM inversion -> TCA sampling -> decode) in one stream batch.
         ori_imgs: uint8 [E,H,W,3] (numpy / pinned host tensor / CUDA tensor), ori_masks: uint8 [E,H,W] 0/1,
         edit_params: list of (dx,dy,rz,sx,sy) (or precomputed `thetas` f32 [E,2,3] when the masks live on the device).
         Defaults are the reference's GeoBench-2D settings (freefine_batch_infer_2d.py:212-230).
+        coarse_inputs u8 [E,H,W,3] + target_masks u8 [E,H,W] (any non-zero = set): the coarse edit was made elsewhere
+        (GeoBench-3D: the depth / novel-view pre-step, freefine_batch_infer_3d_depth.py:117-122) -- the warp is skipped,
+        edit_params / thetas are ignored and cons_area = target mask as in that driver (:160).
         Returns uint8 images [E,H,W,3] on the side the inputs came from (host inputs -> host numpy)."""
         from . import coarse_edit
         assert method_type in ['tca', 'mmsa', 'mmsa_es'], method_type
@@ -852,15 +855,21 @@ class FreeFinePipeline:
         to_dev = lambda a: (a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))).to(self.device, non_blocking=True)
         imgs_u8, masks = to_dev(ori_imgs), to_dev(ori_masks)
         E, H, W = masks.shape
-        if thetas is None:
+        if (coarse_inputs is None) != (target_masks is None):
+            raise ValueError("coarse_inputs and target_masks go together")
+        if coarse_inputs is None and thetas is None:
             mh = ori_masks.cpu().numpy() if torch.is_tensor(ori_masks) else np.asarray(ori_masks)
             thetas = torch.tensor(np.stack([coarse_edit.cv2_theta(coarse_edit.edit_matrix(mh[e], edit_params[e]), W, H)
                                             for e in range(E)]), dtype=torch.float32)
         imgs = imgs_u8.permute(0, 3, 1, 2).float().contiguous()
         bgs = imgs if inp_bgs is None else to_dev(inp_bgs).permute(0, 3, 1, 2).float().contiguous()
-        with ops.nvtx_range("ff.coarse_edit (warp + blend)"):
-            coarse, tgt = coarse_edit.re_edit_2d_device(imgs, masks.contiguous(), to_dev(thetas), bgs)
-        coarse = coarse.round().clamp(0, 255)                                   # the reference hands a uint8 image on
+        if coarse_inputs is not None:
+            coarse = to_dev(coarse_inputs).permute(0, 3, 1, 2).float().contiguous()
+            tgt = to_dev(target_masks).contiguous()
+        else:
+            with ops.nvtx_range("ff.coarse_edit (warp + blend)"):
+                coarse, tgt = coarse_edit.re_edit_2d_device(imgs, masks.contiguous(), to_dev(thetas), bgs)
+            coarse = coarse.round().clamp(0, 255)                               # the reference hands a uint8 image on
         draw = torch.zeros_like(masks) if draw_masks is None else to_dev(draw_masks)
         lat_hw = (H // 8, W // 8)
         fg, sh, orim, comp, lvar = self.prepare_various_mask_batch(tgt, masks, draw, tgt, lat_hw, use_auto_draw,

@@ -121,6 +121,31 @@ def test_batch_noise_is_per_edit(dev):
         assert _rel_l2(both[2 * i:2 * i + 2].cpu(), one.cpu()) < 1e-3, i
 
 
+def test_batch_with_precomputed_coarse_input_matches_per_edit_call(dev):
+    """GeoBench-3D calling convention (freefine_batch_infer_3d_depth.py:144-165): coarse input, target mask and draw mask
+    come from outside, use_auto_draw=False, cons_area = target mask.  The batched entry point (warp skipped) must give
+    what the per-edit FreeFine_generation of the reference surface gives for every edit."""
+    from freefine_b200 import selfcheck, synth
+    pipe, _ = selfcheck.build_pipeline(dev, torch.float32)
+    b = synth.make_batch(3, 2, 128)
+    rng = np.random.default_rng(4)
+    E, H, W = b["masks"].shape
+    coarse = rng.integers(0, 256, (E, H, W, 3)).astype(np.uint8)
+    tgt = np.stack([np.roll(m, (9, -7), (0, 1)) for m in b["masks"]]).astype(np.uint8) * 255
+    draw = np.stack([np.roll(m, (9, 6), (0, 1)) for m in b["masks"]]).astype(np.uint8)
+    kw = dict(guidance_scale=7.5, eta=1.0, end_step=6, num_step=6, start_step=2, method_type="tca", end_scale=0.0,
+              use_auto_draw=False, reduce_inp_artifacts=True)
+    out, lat = pipe.FreeFine_generation_batch(b["images"], b["masks"], None, b["prompts"], coarse_inputs=coarse,
+                                              target_masks=tgt, draw_masks=draw, return_latents=True, **kw)
+    assert out.shape == (E, H, W, 3) and out.dtype == np.uint8
+    for i in range(E):
+        one = pipe.FreeFine_generation(b["images"][i], b["masks"][i], coarse[i], tgt[i], b["prompts"][i], draw_mask=draw[i],
+                                       cons_area=tgt[i], return_intermediates=True, **kw)
+        ref_lat = pipe.last_intermediates[-1]
+        assert _rel_l2(lat[2 * i:2 * i + 2].cpu(), ref_lat.cpu()) < 1e-3, i
+        assert np.abs(out[i].astype(int) - one.astype(int)).max() <= 2, i
+
+
 def test_mask_prep_bit_exact_on_device(dev, golden):
     g = golden["masks"]
     pipe, _ = _make(dev)

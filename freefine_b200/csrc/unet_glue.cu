@@ -45,6 +45,10 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 constexpr int GN_THREADS = 256;
 constexpr int GN_MAX_CHUNKS = 64;     // pixel chunks per image (partial statistics per chunk), two-kernel form
 constexpr int GN_MAX_CHUNKS_FUSED = 128;   // ... single-read form (the workspace is sized for this one)
+#ifndef FF_GN_MLP
+#define FF_GN_MLP 4
+#endif
+constexpr int GN_MLP = FF_GN_MLP;     // independent 16-byte loads in flight per thread (statistics and apply loops)
 constexpr int GN_CHUNK_PX = 128;      // pixels per CTA, images of more than 1024 pixels
 constexpr int GN_CHUNK_PX_SMALL = 64;  // ... of at most 1024 pixels
 
@@ -83,15 +87,26 @@ gn_stats_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_
       }
       const uint4* px = x + ((size_t)n * HW + p0 + L.r) * L.CV + v;
       const size_t step = (size_t)L.R * L.CV;
-#pragma unroll 4
-      for (int p = p0 + L.r; p < p1; p += L.R, px += step) {
-        float f[8];
-        unpack8(__ldg(px), f);
+      // batches of GN_MLP independent loads, THEN the arithmetic: with a plain `#pragma unroll 4` ptxas kept two loads in
+      // flight per thread (each load sat next to its 32 dependent operations) and the pass ran at 2.5 TB/s
+#pragma unroll 1
+      for (int p = p0 + L.r; p < p1; p += GN_MLP * L.R, px += GN_MLP * step) {
+        uint4 raw[GN_MLP];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float t = f[j] + a[j];
-          s[j] += t;
-          ss[j] = fmaf(t, t, ss[j]);
+        for (int u = 0; u < GN_MLP; ++u)
+          raw[u] = (p + u * L.R < p1) ? __ldg(px + u * step) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int u = 0; u < GN_MLP; ++u) {
+          if (p + u * L.R < p1) {
+            float f[8];
+            unpack8(raw[u], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float t = f[j] + a[j];
+              s[j] += t;
+              ss[j] = fmaf(t, t, ss[j]);
+            }
+          }
         }
       }
       float* dst = sm + (size_t)L.r * 2 * C + 8 * v;
@@ -177,19 +192,161 @@ gn_apply_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_
     const uint4* px = x + off;
     uint4* py = y + off;
     const size_t step = (size_t)L.R * L.CV;
-#pragma unroll 4
-    for (int p = p0 + L.r; p < p1; p += L.R, px += step, py += step) {
+#pragma unroll 1
+    for (int p = p0 + L.r; p < p1; p += GN_MLP * L.R, px += GN_MLP * step, py += GN_MLP * step) {
+      uint4 raw[GN_MLP];                                   // (independent loads first: see the statistics kernel)
+#pragma unroll
+      for (int u = 0; u < GN_MLP; ++u)
+        raw[u] = (p + u * L.R < p1) ? __ldg(px + u * step) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int u = 0; u < GN_MLP; ++u) {
+        if (p + u * L.R < p1) {
+          float f[8];
+          unpack8(raw[u], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float t = fmaf(f[j], sc[j], sh[j]);
+            if (SILU) t = __fdividef(t, 1.f + __expf(-t));     // 2 MUFU ops; the IEEE division made this kernel ALU-bound
+            f[j] = t;
+          }
+          py[u * step] = pack8(f);
+        }
+      }
+    }
+  }
+}
+
+// ---- register-resident GroupNorm for small images (round 2) ------------------------------------------------------------
+// The 8 x 8 / 16 x 16 / 32 x 32 levels of the UNet are HALF of the GroupNorm launches of a call, and the two-kernel form
+// is latency-bound there: its CTAs split an image by pixels only, so a 32 x 1280 x 8 x 8 tensor (5 MB) is walked by 32 CTAs
+// whose threads each chase 64 dependent loads (ncu launch list of round 2: 35-50 us per kernel for tensors that take
+// 2-5 us at the HBM peak; 60 % of all GroupNorm time of a UNet call).  Groups are independent, so this kernel splits by
+// CHANNELS instead: one CTA per (image, bundle of B groups whose channels fill whole 16-byte vectors), all HW pixels of
+// those channels in registers (VPT vectors per thread, all loads in flight at once), statistics and apply in one pass --
+// x is read exactly once, there is no workspace traffic, and a 32 x 1280 x 16 x 16 launch has 1024 CTAs instead of 128.
+template <bool SILU, int VPT>
+__global__ void __launch_bounds__(GN_THREADS, VPT >= 24 ? 2 : 1)
+gn_small_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_nc, const __nv_bfloat16* __restrict__ gamma,
+                     const __nv_bfloat16* __restrict__ beta, uint4* __restrict__ y, int HW, int C, int G, int B, float eps) {
+  __shared__ float sm[GN_THREADS / 32 * 8 * 2 + 16];   // [warp][group][S, SS] partials, then [B] mean, [B] rstd
+  const int cpg = C / G, bch = B * cpg, BV = bch >> 3, CV = C >> 3;
+  const int R = GN_THREADS / BV, col = threadIdx.x % BV, r = threadIdx.x / BV;
+  const bool live = r < R;
+  const int n = blockIdx.y, bundle = blockIdx.x;
+  const int c0 = bundle * bch + 8 * col;        // my eight channels
+  float* stat = sm + GN_THREADS / 32 * 8 * 2;
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = add_nc ? __ldg(add_nc + (size_t)n * C + c0 + j) : 0.f;
+  uint4 raw[VPT];
+  const uint4* px = x + ((size_t)n * HW) * CV + bundle * BV + col;
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    const int p = r + k * R;
+    raw[k] = (live && p < HW) ? __ldg(px + (size_t)p * CV) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  float s[8], ss[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    if (live && r + k * R < HW) {
       float f[8];
-      unpack8(__ldg(px), f);
+      unpack8(raw[k], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = f[j] + a[j];
+        s[j] += t;
+        ss[j] = fmaf(t, t, ss[j]);
+      }
+    }
+  }
+  // ---- per-group sums of the bundle: each thread folds its eight channels into (at most B <= 8) group partials, a warp
+  // butterfly and one shared-memory hop combine them -- fixed order, bit-reproducible, ~100 instructions per thread
+  // (a first version reduced [R][2][bch] channel sums from shared memory with one warp per group: with B = 1 that was ONE
+  // warp walking 2040 values while seven idled)
+  int gid[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) gid[j] = (8 * col + j) / cpg;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    if (g < B) {                                            // (CTA-uniform)
+      float S = 0.f, SS = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        S += gid[j] == g ? s[j] : 0.f;
+        SS += gid[j] == g ? ss[j] : 0.f;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        S += __shfl_xor_sync(0xffffffffu, S, o);
+        SS += __shfl_xor_sync(0xffffffffu, SS, o);
+      }
+      if (lane == 0) {
+        sm[(warp * 8 + g) * 2] = S;
+        sm[(warp * 8 + g) * 2 + 1] = SS;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < B) {
+    float S = 0.f, SS = 0.f;
+#pragma unroll
+    for (int w = 0; w < GN_THREADS / 32; ++w) {
+      S += sm[(w * 8 + threadIdx.x) * 2];
+      SS += sm[(w * 8 + threadIdx.x) * 2 + 1];
+    }
+    const float inv_cnt = 1.f / ((float)cpg * (float)HW);
+    const float m = S * inv_cnt;
+    const float var = fmaxf(SS * inv_cnt - m * m, 0.f);
+    stat[threadIdx.x] = m;
+    stat[B + threadIdx.x] = 1.f / sqrtf(var + eps);
+  }
+  __syncthreads();
+  if (!live) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = gid[j];
+    sc[j] = stat[B + g] * __bfloat162float(gamma[c0 + j]);
+    sh[j] = fmaf(a[j] - stat[g], sc[j], __bfloat162float(beta[c0 + j]));     // y = (x + a - mean) * rstd * gamma + beta
+  }
+  uint4* py = y + ((size_t)n * HW) * CV + bundle * BV + col;
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    const int p = r + k * R;
+    if (p < HW) {
+      float f[8];
+      unpack8(raw[k], f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float t = fmaf(f[j], sc[j], sh[j]);
-        if (SILU) t = __fdividef(t, 1.f + __expf(-t));     // 2 MUFU ops; the IEEE division made this kernel ALU-bound
+        if (SILU) t = __fdividef(t, 1.f + __expf(-t));
         f[j] = t;
       }
-      *py = pack8(f);
+      py[(size_t)p * CV] = pack8(f);
     }
   }
+}
+
+// groups per bundle B (the smallest B dividing G whose B * cpg channels are whole 16-byte vectors), vectors per thread;
+// 0 = the shape does not fit the register-resident form
+int gn_small_plan(int HW, int C, int G, int* B_out, size_t* smem) {
+  static const bool off = [] { const char* e = getenv("FF_GN_SMALL"); return e && atoi(e) == 0; }();
+  if (off) return 0;
+  const int cpg = C / G;
+  int B = 0;
+  for (int b = 1; b <= 8; b <<= 1)
+    if (G % b == 0 && (b * cpg) % 8 == 0) { B = b; break; }
+  if (!B) return 0;
+  const int BV = B * cpg / 8;
+  if (BV > GN_THREADS) return 0;
+  const int R = GN_THREADS / BV, need = (HW + R - 1) / R;
+  if (need > 24) return 0;
+  *B_out = B;
+  *smem = 0;                                                 // (static shared memory only)
+  return need <= 2 ? 2 : (need <= 4 ? 4 : (need <= 6 ? 6 : (need <= 12 ? 12 : 24)));
 }
 
 // ---- single-read GroupNorm (round 2) -----------------------------------------------------------------------------------
@@ -423,17 +580,30 @@ __device__ __forceinline__ float gelu_erf(float g) {
 
 __global__ void __launch_bounds__(256)
 geglu_kernel(const uint4* __restrict__ h, uint4* __restrict__ out, long long total, int FV) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long m = i / FV;
-    const int v = (int)(i - m * FV);
+  // two output vectors per trip: four independent 16-byte loads in flight per thread before the erf arithmetic
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 2 * stride) {
+    const long long i2 = i + stride;
+    const bool two = i2 < total;
+    const long long m = i / FV, m2 = two ? i2 / FV : m;
+    const int v = (int)(i - m * FV), v2 = two ? (int)(i2 - m2 * FV) : v;
     const uint4* row = h + m * 2 * FV;
+    const uint4* row2 = h + m2 * 2 * FV;
+    const uint4 qx = __ldg(row + v), qg = __ldg(row + FV + v);
+    const uint4 qx2 = __ldg(row2 + v2), qg2 = __ldg(row2 + FV + v2);
     float x[8], g[8];
-    unpack8(__ldg(row + v), x);
-    unpack8(__ldg(row + FV + v), g);
+    unpack8(qx, x);
+    unpack8(qg, g);
 #pragma unroll
     for (int j = 0; j < 8; ++j) x[j] *= bf16_round(gelu_erf(g[j]));
     out[i] = pack8(x);
+    if (two) {
+      unpack8(qx2, x);
+      unpack8(qg2, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] *= bf16_round(gelu_erf(g[j]));
+      out[i2] = pack8(x);
+    }
   }
 }
 
@@ -496,6 +666,68 @@ layer_norm_kernel(const uint4* __restrict__ x, const __nv_bfloat16* __restrict__
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = fmaf((f[k][j] - mean) * rstd, ga[j], be[j]);
         py[v] = pack8(o);
+      }
+    }
+  }
+}
+
+// LayerNorm for C = 40 * LPR channels (320 / 640 / 1280: every transformer width of SD1.5): LPR = 8 / 16 / 32 lanes share a
+// row, FIVE 16-byte vectors per lane -- no idle lanes (the generic kernel above gives a 320-channel row to a whole warp:
+// 40 vectors over 32 lanes = two rounds with 24 lanes idle in the second, and a five-step butterfly where three suffice).
+// gamma / beta stay packed in registers across the rows a warp walks.
+template <int LPR>
+__global__ void __launch_bounds__(256, 2)
+layer_norm5_kernel(const uint4* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
+                   const __nv_bfloat16* __restrict__ beta, uint4* __restrict__ y, long long M, float eps) {
+  constexpr int RPW = 32 / LPR, CV = 5 * LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR, rsel = lane / LPR;
+  uint4 gq[5], bq[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    gq[k] = __ldg(reinterpret_cast<const uint4*>(gamma) + sub + LPR * k);
+    bq[k] = __ldg(reinterpret_cast<const uint4*>(beta) + sub + LPR * k);
+  }
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const float inv_c = 1.f / (float)(8 * CV);
+  for (long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW; row0 < M; row0 += nwarps * RPW) {
+    const long long row = row0 + rsel;
+    const bool valid = row < M;
+    uint4 raw[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) raw[k] = valid ? __ldg(x + row * CV + sub + LPR * k) : make_uint4(0u, 0u, 0u, 0u);
+    float f[5][8];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      unpack8(raw[k], f[k]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += f[k][j];
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * inv_c;
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = f[k][j] - mean;
+        ss = fmaf(d, d, ss);
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = 1.f / sqrtf(ss * inv_c + eps);
+    if (valid) {
+      uint4* py = y + row * CV + sub;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        float ga[8], be[8], o[8];
+        unpack8(gq[k], ga);
+        unpack8(bq[k], be);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf((f[k][j] - mean) * rstd, ga[j], be[j]);
+        py[LPR * k] = pack8(o);
       }
     }
   }
@@ -581,6 +813,30 @@ extern "C" int ff_group_norm_nhwc(const void* x, const float* add_nc, const void
   // us at 32x320x64x64, 333 vs 206 us at 32x960x64x64) -- a CTA parked at the per-image barrier holds its shared memory, and
   // load, reduce and store phases of the CTAs on an SM do not overlap enough (profiles/r2_gn_single_read.txt).
   static const bool two_kernel = [] { const char* e = getenv("FF_GN_SINGLE_READ"); return !(e && atoi(e) != 0); }();
+  {
+    int B = 0;
+    size_t smem = 0;
+    const int vpt = gn_small_plan(HW, C, G, &B, &smem);
+    if (vpt > 0) {
+      const dim3 grid(G / B, N);
+      const uint4* xp = static_cast<const uint4*>(x);
+      const __nv_bfloat16* gp = static_cast<const __nv_bfloat16*>(gamma);
+      const __nv_bfloat16* bp = static_cast<const __nv_bfloat16*>(beta);
+      uint4* yp = static_cast<uint4*>(y);
+#define FF_GN_SMALL_LAUNCH(V)                                                                                            \
+  do {                                                                                                                   \
+    if (silu) gn_small_nhwc_kernel<true, V><<<grid, GN_THREADS, smem, st>>>(xp, add_nc, gp, bp, yp, HW, C, G, B, eps);    \
+    else gn_small_nhwc_kernel<false, V><<<grid, GN_THREADS, smem, st>>>(xp, add_nc, gp, bp, yp, HW, C, G, B, eps);        \
+  } while (0)
+      if (vpt == 2) FF_GN_SMALL_LAUNCH(2);
+      else if (vpt == 4) FF_GN_SMALL_LAUNCH(4);
+      else if (vpt == 6) FF_GN_SMALL_LAUNCH(6);
+      else if (vpt == 12) FF_GN_SMALL_LAUNCH(12);
+      else FF_GN_SMALL_LAUNCH(24);
+#undef FF_GN_SMALL_LAUNCH
+      return ff::check_launch("ff_group_norm_nhwc (register-resident)");
+    }
+  }
   {
     int px = 0;
     size_t smem = 0;
@@ -673,6 +929,15 @@ extern "C" int ff_layer_norm(const void* x, const void* gamma, const void* beta,
   const int rows_per_warp = vpl <= 1 ? 8 : (vpl <= 2 ? 4 : (vpl <= 3 ? 2 : 1));
   const long long blocks = (M + 8LL * rows_per_warp - 1) / (8LL * rows_per_warp);
   FF_REQUIRE(blocks <= 2147483647LL, "ff_layer_norm: too many rows");
+  if (CV == 40 || CV == 80 || CV == 160) {                    // C = 320 / 640 / 1280: sub-warp rows, five vectors per lane
+    const int lpr = CV / 5, rpw = 32 / lpr;
+    long long nb = (M + 8LL * rpw * 4 - 1) / (8LL * rpw * 4);   // about four row groups per warp
+    if (nb > 148 * 16) nb = 148 * 16;
+    if (lpr == 8) layer_norm5_kernel<8><<<(int)nb, 256, 0, st>>>(xp, gp, bp, yp, M, eps);
+    else if (lpr == 16) layer_norm5_kernel<16><<<(int)nb, 256, 0, st>>>(xp, gp, bp, yp, M, eps);
+    else layer_norm5_kernel<32><<<(int)nb, 256, 0, st>>>(xp, gp, bp, yp, M, eps);
+    return ff::check_launch("ff_layer_norm");
+  }
   if (vpl <= 1) layer_norm_kernel<1, 8><<<(int)blocks, 256, 0, st>>>(xp, gp, bp, yp, M, CV, eps);
   else if (vpl <= 2) layer_norm_kernel<2, 4><<<(int)blocks, 256, 0, st>>>(xp, gp, bp, yp, M, CV, eps);
   else if (vpl <= 3) layer_norm_kernel<3, 2><<<(int)blocks, 256, 0, st>>>(xp, gp, bp, yp, M, CV, eps);

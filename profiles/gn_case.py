@@ -6,7 +6,11 @@ import torch
 from freefine_b200 import ops
 
 dev = torch.device("cuda:0")
-for (n, c, h, w) in ((32, 320, 64, 64), (16, 320, 64, 64), (32, 960, 64, 64), (32, 640, 32, 32), (32, 1280, 16, 16), (16, 320, 96, 96)):
+SHAPES = ((32, 320, 64, 64), (16, 320, 64, 64), (32, 960, 64, 64), (32, 640, 32, 32), (32, 1280, 16, 16), (16, 320, 96, 96),
+          # the small levels of a 32- / 16-stream call (register-resident kernel unless FF_GN_SMALL=0)
+          (32, 1280, 8, 8), (32, 2560, 8, 8), (16, 1280, 8, 8), (32, 2560, 16, 16), (32, 1920, 16, 16), (16, 1280, 16, 16),
+          (32, 1280, 32, 32), (32, 320, 32, 32), (32, 1920, 32, 32), (32, 960, 32, 32))
+for (n, c, h, w) in SHAPES:
     x = torch.randn(n, c, h, w, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
     ga, be = torch.ones(c, device=dev).bfloat16(), torch.zeros(c, device=dev).bfloat16()
     add = torch.randn(n, c, device=dev)
@@ -24,4 +28,24 @@ for (n, c, h, w) in ((32, 320, 64, 64), (16, 320, 64, 64), (32, 960, 64, 64), (3
         e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) / 10)
     byt = 2 * x.numel() * 2
-    print(f"chunk_px={os.environ.get('FF_GN_CHUNK_PX', 'default')} {n}x{c}x{h}x{w}: {best * 1e3:7.1f} us  {byt / best / 1e6:6.0f} GB/s algorithmic")
+    print(f"chunk_px={os.environ.get('FF_GN_CHUNK_PX', 'default')} small={os.environ.get('FF_GN_SMALL', '1')} {n}x{c}x{h}x{w}: {best * 1e3:7.1f} us  {byt / best / 1e6:6.0f} GB/s algorithmic")
+
+# LayerNorm at the transformer widths of a 32-stream call (sub-warp-row kernel for C = 320 / 640 / 1280)
+for (m, c) in ((32 * 4096, 320), (32 * 1024, 640), (32 * 256, 1280), (16 * 4096, 320)):
+    x = torch.randn(1, m, c, device=dev).bfloat16()
+    ga, be = torch.ones(c, device=dev).bfloat16(), torch.zeros(c, device=dev).bfloat16()
+    fn = lambda: ops.layer_norm(x, ga, be, 1e-5)
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(10):
+            fn()
+    best = 1e9
+    for _ in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / 10)
+    byt = 2 * x.numel() * 2
+    print(f"layer_norm {m}x{c}: {best * 1e3:7.1f} us  {byt / best / 1e6:6.0f} GB/s algorithmic")

@@ -39,6 +39,10 @@ GN_SHAPES = [
     (2, 640, 24, 24, 32),     # ragged pixel chunks (768^2 mid resolution)
     (1, 320, 96, 96, 32),     # 768^2: chunk count capped
     (5, 1280, 1, 1, 32),      # single pixel
+    # register-resident small-image kernel at the SD1.5 sizes (bundles of 1 / 2 / 4 groups, 2..24 vectors per thread)
+    (2, 1280, 8, 8, 32), (2, 1280, 16, 16, 32), (2, 2560, 16, 16, 32), (2, 1920, 16, 16, 32), (2, 640, 32, 32, 32),
+    (1, 1280, 32, 32, 32), (2, 320, 32, 32, 32), (2, 1280, 24, 24, 32),
+    (2, 960, 32, 32, 32),     # 61 vectors per thread would be needed: stays on the two-kernel form
 ]
 
 

@@ -163,6 +163,9 @@ class Attention_Modulator(AttentionControl):
     def _table(self, kind: str, seq: int, masks, min_tokens: int = 0):
         """Bit-vector table of `masks` (list of [H,W]/[E,H,W] tensors, stacked edit-major) at `seq` tokens.
         Cached until any mask tensor is replaced or modified in place."""
+        # (address, version, shape) -- and the entry keeps strong references to the mask tensors (views pin their
+        # storage), so the caching allocator cannot hand a NEW mask the address of a cached one: no stale hits even for a
+        # caller that swaps masks without reset()
         sig = tuple((m.data_ptr(), m._version, tuple(m.shape)) for m in masks)
         hit = self._tables.get((kind, seq))
         if hit is not None and hit[0] == sig:
@@ -181,7 +184,7 @@ class Attention_Modulator(AttentionControl):
         words = ops.mask_words(max(seq, min_tokens))
         bits = torch.zeros((stacked.shape[0], words), dtype=torch.int32, device=stacked.device)
         bits, pop = ops.mask_downsample_pack(stacked, h, w, bits=bits)
-        self._tables[(kind, seq)] = (sig, bits, pop)
+        self._tables[(kind, seq)] = (sig, bits, pop, tuple(masks))
         return bits, pop
 
     def _plan(self, key, builder):

@@ -749,7 +749,14 @@ class FreeFinePipeline:
                                                 verbose=False, local_text_edit=True, local_perturbation=True,
                                                 return_intermediates=False, use_share_attention=False, dil_factor=15,
                                                 end_scale=0.5):
-        """reference model.py:1701-1750"""
+        """reference model.py:1701-1750.  The attention plans hold at most FF_MAX_PASS passes per (stream, head): N source
+        images need N + 1 of them ('tca' self-attention and the regional cross-attention), so N <= FF_MAX_PASS - 1 -- checked
+        here, before the first UNet call, instead of deep inside the first TCA layer (the reference loops over any N)."""
+        from ._lib import FF_MAX_PASS
+        n_src = len(ori_mask_lists)
+        if n_src + 1 > FF_MAX_PASS:
+            raise ValueError(f"cross-image composition with {n_src} source images needs {n_src + 1} attention passes per "
+                             f"head; this build supports FF_MAX_PASS = {FF_MAX_PASS} (at most {FF_MAX_PASS - 1} sources)")
         init_code_orig = deepcopy(inverted_latents[-1])
         full_h, full_w = source_image.shape[:2]
         tgt_masks, ori_masks, local_pert, comp_cfg = self.prepare_composition_masks(

@@ -100,7 +100,8 @@ def hbm_rooflines(dev, peak_gbs: float, with_eager: bool = False):
     byt = 2 * kk.numel() * 2 + kk.numel() * 2 + B * S * heads * 48 * 2 + idx.numel() * 8
     rows.append(_row("ff_kv_gather_cast", byt, ms, peak_gbs, size=f"{B} streams x {S} tokens, random row permutation"))
     del kk, vv, idx
-    for (n, c, hh, ww, G) in ((32, 320, 64, 64, 32), (32, 960, 64, 64, 32)):
+    # (the last two are the small levels of a call: register-resident single-read kernel; L2-resident tensors)
+    for (n, c, hh, ww, G) in ((32, 320, 64, 64, 32), (32, 960, 64, 64, 32), (32, 1280, 16, 16, 32), (32, 2560, 8, 8, 32)):
         xg = _nhwc(n, c, hh, ww, dev)
         ga, be = torch.ones(c, device=dev).bfloat16(), torch.zeros(c, device=dev).bfloat16()
         add = torch.randn(n, c, device=dev)

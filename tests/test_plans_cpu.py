@@ -118,3 +118,13 @@ def test_prefix_mode_sorted_keys_equals_bitmask_mode(golden):
     out = run_plan(T("compose/q"), ks, vs, plans.compose_plan(2, 8, "tca", 0.3, [0, 1], [2, 3], prefix=True), 8, 8 ** -0.5,
                    _bits(*srcs, *tgts))
     assert float((out - T("compose_tca/out")).abs().max()) < 2e-5
+
+
+def test_composition_source_count_is_checked_up_front():
+    """N sources need N + 1 passes per head (FF_MAX_PASS = 4): the entry point refuses N = 4 before any UNet call."""
+    from freefine_b200._lib import FF_MAX_PASS
+    from freefine_b200.pipeline import FreeFinePipeline
+    import pytest
+    with pytest.raises(ValueError, match="FF_MAX_PASS"):
+        FreeFinePipeline.Details_Preserving_regeneration_compose(object(), None, [None], ["a"] * FF_MAX_PASS,
+                                                                 [[0]] * FF_MAX_PASS, [[0]] * (FF_MAX_PASS + 1), None)

@@ -66,5 +66,16 @@ ops.group_norm_nhwc(xg, ga, be, 16, 1e-5, add_nc=torch.randn(2, 64, device=dev),
 ops.bias_residual_nhwc(xg.clone(), ga, xg)
 ops.geglu(torch.randn(2, 64, 256, device=dev).bfloat16())
 ops.layer_norm(torch.randn(2, 64, 320, device=dev).bfloat16(), torch.ones(320, device=dev).bfloat16(), torch.zeros(320, device=dev).bfloat16(), 1e-5)
+# round 2: the register-resident GroupNorm (bundles of 1 and 4 groups, ragged pixel count), the two-kernel form on a shape
+# that does not fit it, the generic LayerNorm next to the sub-warp-row one above, mask preparation and dilation
+for (n, c, h, w, G) in ((2, 1280, 8, 8, 32), (1, 320, 24, 24, 32), (1, 960, 32, 32, 32)):
+    xs_ = torch.randn(n, c, h, w, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    ops.group_norm_nhwc(xs_, torch.ones(c, device=dev).bfloat16(), torch.zeros(c, device=dev).bfloat16(), G, 1e-5, silu=True)
+ops.layer_norm(torch.randn(3, 17, 160, device=dev).bfloat16(), torch.ones(160, device=dev).bfloat16(), torch.zeros(160, device=dev).bfloat16(), 1e-5)
+ops.layer_norm(torch.randn(1, 5, 1280, device=dev).bfloat16(), torch.ones(1280, device=dev).bfloat16(), torch.zeros(1280, device=dev).bfloat16(), 1e-5)
+mm = lambda: ((torch.rand(2, 128, 128, device=dev) > 0.7).to(torch.uint8) * 255).contiguous()
+ops.mask_prep(mm(), mm(), None, mm(), (16, 16), True, True)
+ops.mask_prep(mm(), mm(), mm(), mm(), (16, 16), False, True)
+ops.dilate_mask(mm(), 15)
 torch.cuda.synchronize()
 print("kernel tour ok:", dict(ops.COUNTS))

@@ -458,6 +458,14 @@ def _register(model, controller, flavour: str):
                     hidden_states = c.plain_attention(query, key, value)
                     controller(None, is_cross, place_in_unet)
 
+            # (extension used by the channels-last UNet fast path: the caller's residual rides in `ff_block_residual` and is
+            # folded into the out-projection GEMM -- bias epilogue + beta * C -- instead of a separate add over [B,S,C])
+            block_res = getattr(self, "ff_block_residual", None)
+            if (block_res is not None and input_ndim == 3 and hidden_states.is_cuda and hidden_states.dtype == torch.bfloat16
+                    and isinstance(to_out, torch.nn.Linear) and not self.residual_connection
+                    and self.rescale_output_factor == 1.0):
+                self.ff_residual_fused = True
+                return ops.linear_bias_residual(hidden_states.contiguous(), to_out.weight, to_out.bias, block_res)
             hidden_states = to_out(hidden_states)
             if input_ndim == 4:
                 hidden_states = hidden_states.transpose(-1, -2).reshape(batch_size, channel, height, width)

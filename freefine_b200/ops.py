@@ -42,6 +42,9 @@ def nvtx_range(name: str):
         yield
 
 
+LIBRARY_ENTRIES = frozenset({"ff_linear_bias_residual"})     # C-ABI entries that launch library code (cuBLASLt), not our kernels
+
+
 def _count(name: str):
     COUNTS[name] = COUNTS.get(name, 0) + 1
 
@@ -452,6 +455,45 @@ def bias_residual_nhwc(h, bias=None, res=None):
     _lib.check(rc, "ff_bias_residual_nhwc")
     _count("ff_bias_residual_nhwc")
     return h
+
+
+_LT_WS: dict = {}
+
+
+def linear_bias_residual(x, weight, bias=None, res=None, out=None):
+    """x [..., K] . weight[N, K]^T (+ bias[N]) (+ res [..., N]) -> bf16 [..., N] in ONE cuBLASLt GEMM (bias epilogue +
+    beta * C): the `Linear(h) + hidden_states` tail of every transformer sub-block without its elementwise add.
+    See ff_linear_bias_residual."""
+    _chk(x, torch.bfloat16, "x")
+    _chk(weight, torch.bfloat16, "weight", 2)
+    N, K = weight.shape
+    if x.shape[-1] != K:
+        raise ValueError(f"x has {x.shape[-1]} features, weight expects {K}")
+    M = x.numel() // K
+    if bias is not None:
+        _chk(bias, torch.bfloat16, "bias", 1)
+        if bias.numel() != N:
+            raise ValueError("bias must have N elements")
+    oshape = tuple(x.shape[:-1]) + (N,)
+    if res is not None:
+        _chk(res, torch.bfloat16, "res")
+        if tuple(res.shape) != oshape:
+            raise ValueError(f"res must be {oshape}, got {tuple(res.shape)}")
+    if out is None:
+        out = torch.empty(oshape, dtype=torch.bfloat16, device=x.device)
+    else:
+        _chk(out, torch.bfloat16, "out")
+        if tuple(out.shape) != oshape:
+            raise ValueError(f"out must be {oshape}, got {tuple(out.shape)}")
+    key = (x.device, torch.cuda.current_stream().cuda_stream)
+    ws = _LT_WS.get(key)
+    if ws is None:
+        ws = _LT_WS[key] = torch.empty(32 << 20, dtype=torch.uint8, device=x.device)
+    rc = _lib.load().ff_linear_bias_residual(_ptr(x), _ptr(weight), _ptr(bias), _ptr(res), _ptr(out), M, N, K, _ptr(ws),
+                                             ws.numel(), _stream())
+    _lib.check(rc, "ff_linear_bias_residual")
+    _count("ff_linear_bias_residual")
+    return out
 
 
 def geglu(h):

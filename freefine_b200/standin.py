@@ -55,6 +55,22 @@ def _conv(x, conv: nn.Conv2d, bias=True, res=None):
     return h
 
 
+def _linear_res(h, lin: nn.Linear, res):
+    """lin(h) + res in one GEMM (bias epilogue + beta * C)."""
+    return ops.linear_bias_residual(h, lin.weight, lin.bias, res)
+
+
+def _attn_res(attn, h, res, **kw):
+    """attn(h) + res with the add folded into the out-projection GEMM when the registered attention forward supports it
+    (freefine_b200.attention: it reads `ff_block_residual`); any other forward adds eagerly."""
+    attn.ff_block_residual, attn.ff_residual_fused = res, False
+    try:
+        out = attn(h, **kw)
+    finally:
+        attn.ff_block_residual = None
+    return out if attn.ff_residual_fused else out + res
+
+
 def _tokens(x):
     """channels_last [N,C,H,W] -> [N, H*W, C] view."""
     n, c, h, w = x.shape
@@ -136,10 +152,12 @@ class FeedForward(nn.Module):
         super().__init__()
         self.net = nn.ModuleList([GEGLU(dim, dim * mult), nn.Dropout(0.0), nn.Linear(dim * mult, dim)])
 
-    def forward(self, x):
+    def forward(self, x, res=None):
+        if res is not None and _fast(x):        # out-projection + residual in one GEMM
+            return _linear_res(self.net[0](x), self.net[2], res)
         for m in self.net:
             x = m(x)
-        return x
+        return x if res is None else x + res
 
 
 class BasicTransformerBlock(nn.Module):
@@ -154,9 +172,9 @@ class BasicTransformerBlock(nn.Module):
 
     def forward(self, x, encoder_hidden_states=None):
         if _fast(x):
-            x = self.attn1(_ln(x, self.norm1)) + x
-            x = self.attn2(_ln(x, self.norm2), encoder_hidden_states=encoder_hidden_states) + x
-            return self.ff(_ln(x, self.norm3)) + x
+            x = _attn_res(self.attn1, _ln(x, self.norm1), x)
+            x = _attn_res(self.attn2, _ln(x, self.norm2), x, encoder_hidden_states=encoder_hidden_states)
+            return self.ff(_ln(x, self.norm3), res=x)
         x = self.attn1(self.norm1(x)) + x
         x = self.attn2(self.norm2(x), encoder_hidden_states=encoder_hidden_states) + x
         x = self.ff(self.norm3(x)) + x
@@ -179,8 +197,8 @@ class Transformer2DModel(nn.Module):
             t = F.linear(_tokens(_gn(x, self.norm)), self.proj_in.weight.reshape(c, c), self.proj_in.bias)
             for blk in self.transformer_blocks:
                 t = blk(t, encoder_hidden_states=encoder_hidden_states)
-            t = F.linear(t, self.proj_out.weight.reshape(c, c), self.proj_out.bias)
-            return _image(t, h, w) + x
+            t = ops.linear_bias_residual(t, self.proj_out.weight.reshape(c, c), self.proj_out.bias, _tokens(x))
+            return _image(t, h, w)
         res = x
         x = self.proj_in(self.norm(x))
         x = x.permute(0, 2, 3, 1).reshape(b, h * w, c)

@@ -150,6 +150,15 @@ int ff_mask_prep(const uint8_t* shifted, const uint8_t* ori, const uint8_t* draw
  * (model.py:927-934, src/utils/vis_utils.py:340-347).  W % 4 == 0.                                                    */
 int ff_dilate_mask(const uint8_t* mask, uint8_t* out, int32_t N, int32_t H, int32_t W, int32_t k, void* stream);
 
+/* out[M,N] = x[M,K] . w[N,K]^T (+ bias[N]) (+ res[M,N]), bf16 row-major, fp32 accumulation, ONE cuBLASLt GEMM (bias epilogue +
+ * beta * C): a plain library GEMM behind the C ABI.  Replaces `Linear(h) + hidden_states` at the end of every sub-block of
+ * diffusers' BasicTransformerBlock / Transformer2DModel as walked by override_forward (src/utils/attention.py:13-223), i.e. the
+ * GEMM + the separate elementwise add.  bias / res may be NULL; out may alias res (measured: cuBLASLt then rounds the GEMM
+ * result to bf16 before adding res, like the eager pair; out of place it rounds once).  N % 8 == 0, K % 8 == 0.  `workspace`
+ * (ws_bytes, 16-byte aligned, may be 0) is caller-owned cuBLASLt scratch.  Links libcublasLt.so.12.                          */
+int ff_linear_bias_residual(const void* x, const void* w, const void* bias, const void* res, void* out, int64_t M, int32_t N,
+                            int32_t K, void* workspace, int64_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * (b) fused affine warp + resample + mask-guided blend
  *

@@ -157,3 +157,53 @@ def test_unet_fast_path_matches_plain(dev, hw, monkeypatch):
     e_fast, e_eager = rel(fast), rel(eager)
     print(f"rel-L2 vs fp32: fast {e_fast:.3e}  eager bf16 {e_eager:.3e}")
     assert e_fast < 3e-2 and e_fast <= 1.25 * e_eager + 1e-3, (e_fast, e_eager)
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 320, 320), (1024, 640, 2560), (77, 1280, 1280), (131072, 320, 1280), (8, 64, 256)])
+@pytest.mark.parametrize("with_bias,with_res", [(True, True), (False, True), (True, False)])
+def test_linear_bias_residual(dev, M, N, K, with_bias, with_res):
+    """ff_linear_bias_residual (one cuBLASLt GEMM with bias epilogue + beta * C) vs x @ W^T + b + res in fp32."""
+    from freefine_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(M + N)
+    x = (torch.randn(M, K, generator=g) / K ** 0.5).to(dev).bfloat16()
+    w = torch.randn(N, K, generator=g).to(dev).bfloat16()
+    b = torch.randn(N, generator=g).to(dev).bfloat16() if with_bias else None
+    r = torch.randn(M, N, generator=g).to(dev).bfloat16() if with_res else None
+    r0 = r.clone() if with_res else None
+    got = ops.linear_bias_residual(x, w, b, r)
+    want = x.float() @ w.float().t()
+    if with_bias:
+        want = want + b.float()
+    if with_res:
+        want = want + r.float()
+        assert torch.equal(r, r0)                     # the residual is read, not written, unless out aliases it
+    assert got.shape == (M, N) and got.dtype == torch.bfloat16
+    torch.testing.assert_close(got.float(), want, rtol=RTOL, atol=2e-2)
+    assert torch.equal(got, ops.linear_bias_residual(x, w, b, r))          # repeatable
+    if with_res:                                      # in-place form: out aliases res (cuBLASLt then rounds twice, like eager)
+        got2 = ops.linear_bias_residual(x, w, b, r, out=r)
+        assert got2.data_ptr() == r.data_ptr()
+        torch.testing.assert_close(got2.float(), want, rtol=RTOL, atol=4e-2)
+
+
+def test_fast_path_folds_residuals_into_the_projection_gemms(dev):
+    """With the attention plugin registered (the bench's configuration) every `Linear(h) + hidden_states` of a transformer
+    block -- both attention out-projections, the feed-forward out-projection, proj_out -- is ONE GEMM: 4 x 16 calls, no
+    elementwise add; the result stays as close to the fp32 forward as the unfused fast path."""
+    from freefine_b200 import ops, selfcheck
+    pipe16, _ = selfcheck.build_pipeline(dev, torch.bfloat16)
+    pipe32, _ = selfcheck.build_pipeline(dev, torch.float32)
+    g = torch.Generator(device="cpu").manual_seed(9)
+    x = torch.randn(4, 4, 16, 16, generator=g).to(dev)
+    enc = torch.randn(4, 77, 64, generator=g).to(dev)
+    t = torch.tensor(321, device=dev)
+    with torch.no_grad():
+        want = pipe32.unet(x, t, encoder_hidden_states=enc)
+        pipe32.controller.reset()
+        before = ops.COUNTS.get("ff_linear_bias_residual", 0)
+        fast = pipe16.unet(x.bfloat16(), t, encoder_hidden_states=enc.bfloat16())
+        pipe16.controller.reset()
+    assert ops.COUNTS.get("ff_linear_bias_residual", 0) - before == 64
+    rel = float((fast.float() - want).norm() / want.norm())
+    print(f"rel-L2 vs fp32 with fused residual GEMMs: {rel:.3e}")
+    assert rel < 3e-2, rel

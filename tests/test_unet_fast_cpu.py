@@ -49,6 +49,17 @@ def ref_layer_norm(x, gamma, beta, eps):
     return F.layer_norm(x.float(), (x.shape[-1],), gamma.float(), beta.float(), eps).to(x.dtype)
 
 
+def ref_linear_bias_residual(x, weight, bias=None, res=None, out=None):
+    assert x.is_contiguous() and weight.is_contiguous() and (res is None or res.is_contiguous())
+    v = x.float() @ weight.float().t()
+    if bias is not None:
+        v = v + bias.float()
+    if res is not None:
+        assert res.shape == v.shape
+        v = v + res.float()
+    return v.to(x.dtype)
+
+
 @pytest.fixture
 def forced_fast(monkeypatch):
     monkeypatch.setattr(standin, "_fast", lambda x: True)
@@ -56,6 +67,7 @@ def forced_fast(monkeypatch):
     monkeypatch.setattr(ops, "bias_residual_nhwc", ref_bias_residual_nhwc)
     monkeypatch.setattr(ops, "geglu", ref_geglu)
     monkeypatch.setattr(ops, "layer_norm", ref_layer_norm)
+    monkeypatch.setattr(ops, "linear_bias_residual", ref_linear_bias_residual)
 
 
 def _inputs(parts, n=3, hw=16):

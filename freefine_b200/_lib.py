@@ -69,8 +69,8 @@ SIGNATURES = {
     "ff_cross_region_blend": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                         C.c_int32, C.c_int32, C.c_void_p]),
     "ff_group_norm_ws_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
-    "ff_group_norm_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
-                                     C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
+    "ff_group_norm_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
     "ff_bias_residual_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                         C.c_void_p]),
     "ff_geglu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),

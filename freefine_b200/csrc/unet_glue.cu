@@ -68,7 +68,7 @@ struct GnLayout {
 
 // partial[n][chunk][g] = (sum, sum of squares) of v = x + add over the pixels of the chunk and the channels of group g
 __global__ void __launch_bounds__(GN_THREADS)
-gn_stats_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_nc, float2* __restrict__ partial,
+gn_stats_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_nc, long long add_ld, float2* __restrict__ partial,
                      int HW, int C, int G, int chunk_px, int n_chunks) {
   extern __shared__ float sm[];                 // [R][2][C] per-row-slot channel sums, then reduced into slot 0
   const GnLayout L(C);
@@ -82,7 +82,7 @@ gn_stats_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_
       float a[8], s[8], ss[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        a[j] = add_nc ? __ldg(add_nc + (size_t)n * C + 8 * v + j) : 0.f;
+        a[j] = add_nc ? __ldg(add_nc + (size_t)n * add_ld + 8 * v + j) : 0.f;
         s[j] = ss[j] = 0.f;
       }
       const uint4* px = x + ((size_t)n * HW + p0 + L.r) * L.CV + v;
@@ -141,7 +141,7 @@ gn_stats_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_
 
 template <bool SILU>
 __global__ void __launch_bounds__(GN_THREADS)
-gn_apply_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_nc,
+gn_apply_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_nc, long long add_ld,
                      const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
                      const float2* __restrict__ partial, uint4* __restrict__ y, int HW, int C, int G, int chunk_px,
                      int n_chunks, float eps) {
@@ -184,7 +184,7 @@ gn_apply_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = 8 * v + j, g = c / cpg;
-      const float a = add_nc ? __ldg(add_nc + (size_t)n * C + c) : 0.f;
+      const float a = add_nc ? __ldg(add_nc + (size_t)n * add_ld + c) : 0.f;
       sc[j] = rstd[g] * __bfloat162float(gamma[c]);
       sh[j] = fmaf(a - mean[g], sc[j], __bfloat162float(beta[c]));     // y = (x + a - mean) * rstd * gamma + beta
     }
@@ -226,7 +226,8 @@ gn_apply_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_
 // x is read exactly once, there is no workspace traffic, and a 32 x 1280 x 16 x 16 launch has 1024 CTAs instead of 128.
 template <bool SILU, int VPT>
 __global__ void __launch_bounds__(GN_THREADS, VPT >= 24 ? 2 : 1)
-gn_small_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_nc, const __nv_bfloat16* __restrict__ gamma,
+gn_small_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_nc, long long add_ld,
+                     const __nv_bfloat16* __restrict__ gamma,
                      const __nv_bfloat16* __restrict__ beta, uint4* __restrict__ y, int HW, int C, int G, int B, float eps) {
   __shared__ float sm[GN_THREADS / 32 * 8 * 2 + 16];   // [warp][group][S, SS] partials, then [B] mean, [B] rstd
   const int cpg = C / G, bch = B * cpg, BV = bch >> 3, CV = C >> 3;
@@ -237,7 +238,7 @@ gn_small_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_
   float* stat = sm + GN_THREADS / 32 * 8 * 2;
   float a[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) a[j] = add_nc ? __ldg(add_nc + (size_t)n * C + c0 + j) : 0.f;
+  for (int j = 0; j < 8; ++j) a[j] = add_nc ? __ldg(add_nc + (size_t)n * add_ld + c0 + j) : 0.f;
   uint4 raw[VPT];
   const uint4* px = x + ((size_t)n * HW) * CV + bundle * BV + col;
 #pragma unroll
@@ -365,7 +366,8 @@ struct GnCtrl {                       // head of the workspace
 
 template <bool SILU>
 __global__ void __launch_bounds__(GN_THREADS)
-gn_fused_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_nc, const __nv_bfloat16* __restrict__ gamma,
+gn_fused_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_nc, long long add_ld,
+                     const __nv_bfloat16* __restrict__ gamma,
                      const __nv_bfloat16* __restrict__ beta, uint4* __restrict__ y, unsigned int* __restrict__ ctrl,
                      float2* __restrict__ partial, int N, int HW, int C, int G, int chunk_px, int n_chunks, float eps) {
   extern __shared__ __align__(16) unsigned char gsm[];
@@ -417,7 +419,7 @@ gn_fused_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_
       float a[8], sacc[8], ssacc[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        a[j] = add_nc ? __ldg(add_nc + (size_t)n * C + 8 * v + j) : 0.f;
+        a[j] = add_nc ? __ldg(add_nc + (size_t)n * add_ld + 8 * v + j) : 0.f;
         sacc[j] = ssacc[j] = 0.f;
       }
       const uint4* pt = tile + (size_t)L.r * L.CV + v;
@@ -513,7 +515,7 @@ gn_fused_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = 8 * v + j, g = c / cpg;
-      const float a = add_nc ? __ldg(add_nc + (size_t)n * C + c) : 0.f;
+      const float a = add_nc ? __ldg(add_nc + (size_t)n * add_ld + c) : 0.f;
       sc[j] = rstd[g] * __bfloat162float(gamma[c]);
       sh[j] = fmaf(a - mean[g], sc[j], __bfloat162float(beta[c]));     // y = (x + a - mean) * rstd * gamma + beta
     }
@@ -796,11 +798,12 @@ extern "C" int64_t ff_group_norm_ws_bytes(int32_t N, int32_t G) {
   return gn_ctrl_bytes(N) + (int64_t)N * GN_MAX_CHUNKS_FUSED * G * (int64_t)sizeof(float2);
 }
 
-extern "C" int ff_group_norm_nhwc(const void* x, const float* add_nc, const void* gamma, const void* beta, void* y,
-                                  void* workspace, int32_t N, int32_t HW, int32_t C, int32_t G, float eps, int32_t silu,
-                                  void* stream) {
+extern "C" int ff_group_norm_nhwc(const void* x, const float* add_nc, int64_t add_ld, const void* gamma, const void* beta,
+                                  void* y, void* workspace, int32_t N, int32_t HW, int32_t C, int32_t G, float eps,
+                                  int32_t silu, void* stream) {
   FF_REQUIRE(x && gamma && beta && y && workspace, "ff_group_norm_nhwc: null pointer");
   FF_REQUIRE(N > 0 && HW > 0 && C > 0 && G > 0, "ff_group_norm_nhwc: bad shape");
+  FF_REQUIRE(!add_nc || add_ld >= C, "ff_group_norm_nhwc: add_ld=%lld must be >= C=%d", (long long)add_ld, C);
   FF_REQUIRE(N <= 65535, "ff_group_norm_nhwc: N must be <= 65535");
   FF_REQUIRE(C % 8 == 0 && C % G == 0, "ff_group_norm_nhwc: C must be a multiple of 8 and of G (C=%d G=%d)", C, G);
   FF_REQUIRE(ff::aligned16(x) && ff::aligned16(y) && ff::aligned16(workspace),
@@ -825,8 +828,8 @@ extern "C" int ff_group_norm_nhwc(const void* x, const float* add_nc, const void
       uint4* yp = static_cast<uint4*>(y);
 #define FF_GN_SMALL_LAUNCH(V)                                                                                            \
   do {                                                                                                                   \
-    if (silu) gn_small_nhwc_kernel<true, V><<<grid, GN_THREADS, smem, st>>>(xp, add_nc, gp, bp, yp, HW, C, G, B, eps);    \
-    else gn_small_nhwc_kernel<false, V><<<grid, GN_THREADS, smem, st>>>(xp, add_nc, gp, bp, yp, HW, C, G, B, eps);        \
+    if (silu) gn_small_nhwc_kernel<true, V><<<grid, GN_THREADS, smem, st>>>(xp, add_nc, add_ld, gp, bp, yp, HW, C, G, B, eps);    \
+    else gn_small_nhwc_kernel<false, V><<<grid, GN_THREADS, smem, st>>>(xp, add_nc, add_ld, gp, bp, yp, HW, C, G, B, eps);        \
   } while (0)
       if (vpt == 2) FF_GN_SMALL_LAUNCH(2);
       else if (vpt == 4) FF_GN_SMALL_LAUNCH(4);
@@ -857,11 +860,11 @@ extern "C" int ff_group_norm_nhwc(const void* x, const float* add_nc, const void
       const unsigned int grid1 = (unsigned)N * (unsigned)nc;
       if (silu)
         gn_fused_nhwc_kernel<true><<<grid1, GN_THREADS, smem, st>>>(
-            static_cast<const uint4*>(x), add_nc, static_cast<const __nv_bfloat16*>(gamma),
+            static_cast<const uint4*>(x), add_nc, add_ld, static_cast<const __nv_bfloat16*>(gamma),
             static_cast<const __nv_bfloat16*>(beta), static_cast<uint4*>(y), ctrl, partial, N, HW, C, G, px, nc, eps);
       else
         gn_fused_nhwc_kernel<false><<<grid1, GN_THREADS, smem, st>>>(
-            static_cast<const uint4*>(x), add_nc, static_cast<const __nv_bfloat16*>(gamma),
+            static_cast<const uint4*>(x), add_nc, add_ld, static_cast<const __nv_bfloat16*>(gamma),
             static_cast<const __nv_bfloat16*>(beta), static_cast<uint4*>(y), ctrl, partial, N, HW, C, G, px, nc, eps);
       return ff::check_launch("ff_group_norm_nhwc (single-read)");
     }
@@ -872,19 +875,19 @@ extern "C" int ff_group_norm_nhwc(const void* x, const float* add_nc, const void
   const size_t smem_stats = (size_t)R * 2 * C * sizeof(float);
   FF_REQUIRE(smem_stats <= 48 * 1024, "ff_group_norm_nhwc: C=%d too large", C);
   const dim3 grid(n_chunks, N);
-  gn_stats_nhwc_kernel<<<grid, GN_THREADS, smem_stats, st>>>(static_cast<const uint4*>(x), add_nc, partial, HW, C, G, chunk_px,
+  gn_stats_nhwc_kernel<<<grid, GN_THREADS, smem_stats, st>>>(static_cast<const uint4*>(x), add_nc, add_ld, partial, HW, C, G, chunk_px,
                                                              n_chunks);
   int rc = ff::check_launch("ff_group_norm_nhwc (statistics)");
   if (rc != FF_OK) return rc;
   const size_t smem_apply = (size_t)2 * G * sizeof(float);
   if (silu)
     gn_apply_nhwc_kernel<true><<<grid, GN_THREADS, smem_apply, st>>>(
-        static_cast<const uint4*>(x), add_nc, static_cast<const __nv_bfloat16*>(gamma),
+        static_cast<const uint4*>(x), add_nc, add_ld, static_cast<const __nv_bfloat16*>(gamma),
         static_cast<const __nv_bfloat16*>(beta), partial, static_cast<uint4*>(y), HW, C, G,
         chunk_px, n_chunks, eps);
   else
     gn_apply_nhwc_kernel<false><<<grid, GN_THREADS, smem_apply, st>>>(
-        static_cast<const uint4*>(x), add_nc, static_cast<const __nv_bfloat16*>(gamma),
+        static_cast<const uint4*>(x), add_nc, add_ld, static_cast<const __nv_bfloat16*>(gamma),
         static_cast<const __nv_bfloat16*>(beta), partial, static_cast<uint4*>(y), HW, C, G,
         chunk_px, n_chunks, eps);
   return ff::check_launch("ff_group_norm_nhwc (apply)");

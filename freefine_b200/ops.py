@@ -428,13 +428,16 @@ def group_norm_nhwc(x, gamma, beta, groups, eps, add_nc=None, silu=False):
     _chk(beta, torch.bfloat16, "beta", 1)
     if gamma.numel() != Cc or beta.numel() != Cc:
         raise ValueError("gamma / beta must have C elements")
-    if add_nc is not None:
-        _chk(add_nc, torch.float32, "add_nc", 2)
-        if tuple(add_nc.shape) != (N, Cc):
-            raise ValueError(f"add_nc must be [{N},{Cc}], got {tuple(add_nc.shape)}")
+    add_ld = Cc
+    if add_nc is not None:      # fp32 [N,C]; rows may be a column block of a wider matrix (unit column stride)
+        if not add_nc.is_cuda or add_nc.dtype != torch.float32 or add_nc.dim() != 2:
+            raise TypeError("add_nc must be a 2-D float32 CUDA tensor")
+        if tuple(add_nc.shape) != (N, Cc) or add_nc.stride(1) != 1 or (N > 1 and add_nc.stride(0) < Cc):
+            raise ValueError(f"add_nc must be [{N},{Cc}] with unit column stride, got {tuple(add_nc.shape)} {add_nc.stride()}")
+        add_ld = add_nc.stride(0) if N > 1 else Cc
     y = torch.empty_like(x)             # preserves the channels_last strides
     ws = _gn_workspace(N, groups, x.device)
-    rc = _lib.load().ff_group_norm_nhwc(_ptr(x), _ptr(add_nc), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(ws), N, HW, Cc,
+    rc = _lib.load().ff_group_norm_nhwc(_ptr(x), _ptr(add_nc), add_ld, _ptr(gamma), _ptr(beta), _ptr(y), _ptr(ws), N, HW, Cc,
                                         groups, float(eps), int(bool(silu)), _stream())
     _lib.check(rc, "ff_group_norm_nhwc")
     _count("ff_group_norm_nhwc")

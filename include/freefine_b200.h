@@ -224,17 +224,17 @@ int ff_cross_region_blend(void* hs, const uint32_t* bitmasks, int32_t mask_words
  * channel index contiguous (torch channels_last == the [B, S, C] token layout of the attention layers).
  * ------------------------------------------------------------------------------------------------------------ */
 
-/* y = act(GroupNorm_G(x + add_nc[n, c])) : x, y bf16 [N, HW, C]; add_nc fp32 [N, C] or NULL (conv bias + projected
- * time embedding of ResnetBlock2D); gamma, beta bf16 [C]; fp32 statistics over (HW, C/G) per (n, group), biased
+/* y = act(GroupNorm_G(x + add_nc[n, c])) : x, y bf16 [N, HW, C]; add_nc fp32 [N, C] with row stride add_ld >= C elements
+ * (a column block of a wider matrix: all time-embedding projections of a UNet call come out of one GEMM), or NULL (conv
+ * bias + projected time embedding of ResnetBlock2D); gamma, beta bf16 [C]; fp32 statistics over (HW, C/G) per (n, group), biased
  * variance, eps inside the square root (torch.nn.GroupNorm); silu != 0 fuses x*sigmoid(x).  `workspace`: at least
  * ff_group_norm_ws_bytes(N, G) bytes, 16-byte aligned, ZERO-FILLED before its first use (cudaMemset once); every call
  * leaves it zero-filled where that matters (it holds the inter-CTA barrier counters of the single-read kernel, which
  * reads x from HBM exactly once), so one buffer serves all calls of a stream.  Not to be shared by calls that may run
  * concurrently (different streams: one workspace each).  C % 8 == 0, C % G == 0.                                  */
 int64_t ff_group_norm_ws_bytes(int32_t N, int32_t G);
-int ff_group_norm_nhwc(const void* x, const float* add_nc, const void* gamma, const void* beta, void* y,
-                       void* workspace, int32_t N, int32_t HW, int32_t C, int32_t G, float eps, int32_t silu,
-                       void* stream);
+int ff_group_norm_nhwc(const void* x, const float* add_nc, int64_t add_ld, const void* gamma, const void* beta, void* y,
+                       void* workspace, int32_t N, int32_t HW, int32_t C, int32_t G, float eps, int32_t silu, void* stream);
 
 /* out[m, c] = h[m, c] + bias[c] + res[m, c] : bf16 [M, C]; bias bf16 [C] or NULL, res bf16 [M, C] or NULL (conv
  * bias + skip connection of ResnetBlock2D / Down- / Upsample2D in one pass); out may alias h or res.            */

@@ -207,3 +207,21 @@ def test_fast_path_folds_residuals_into_the_projection_gemms(dev):
     rel = float((fast.float() - want).norm() / want.norm())
     print(f"rel-L2 vs fp32 with fused residual GEMMs: {rel:.3e}")
     assert rel < 3e-2, rel
+
+
+@pytest.mark.parametrize("shape", [(4, 320, 64, 64, 32), (3, 1280, 16, 16, 32), (2, 640, 32, 32, 32), (2, 1280, 8, 8, 32)])
+def test_group_norm_addend_as_column_block(dev, shape):
+    """add_nc handed over as a column block of a wider [N, sum C] matrix (row stride > C): every GroupNorm kernel form."""
+    from freefine_b200 import ops
+    n, c, h, w, G = shape
+    x = _nhwc(n, c, h, w, dev, 13, scale=1.3, shift=-0.2)
+    g = torch.Generator(device="cpu").manual_seed(6)
+    gamma = (1 + 0.3 * torch.randn(c, generator=g)).to(dev).bfloat16()
+    beta = (0.2 * torch.randn(c, generator=g)).to(dev).bfloat16()
+    wide = (0.8 * torch.randn(n, 3 * c + 40, generator=g)).to(dev)
+    add = wide[:, c + 8:2 * c + 8]
+    assert not add.is_contiguous() or n == 1
+    got = ops.group_norm_nhwc(x, gamma, beta, G, 1e-5, add_nc=add, silu=True)
+    want = ref_group_norm_nhwc(x, gamma, beta, G, 1e-5, add_nc=add.contiguous(), silu=True)
+    torch.testing.assert_close(got.float(), want.float(), rtol=RTOL, atol=ATOL)
+    assert torch.equal(got, ops.group_norm_nhwc(x, gamma, beta, G, 1e-5, add_nc=add.contiguous(), silu=True))

@@ -48,6 +48,8 @@ SIGNATURES = {
                                     C.c_int32, C.c_int32, C.c_void_p]),
     "ff_mask_downsample_pack": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                           C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "ff_upsample2x_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "ff_concat_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "ff_linear_bias_residual": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "ff_mask_prep": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 7 + [C.c_void_p] * 6),
     "ff_dilate_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),

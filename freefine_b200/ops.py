@@ -460,6 +460,30 @@ def bias_residual_nhwc(h, bias=None, res=None):
     return h
 
 
+def upsample2x_nhwc(x):
+    """Nearest 2x up-sampling of a channels_last bf16 [N,C,H,W] tensor -> channels_last [N,C,2H,2W].  See ff_upsample2x_nhwc."""
+    N, HW, Cc = _nhwc_view(x, "x")
+    H, W = x.shape[2], x.shape[3]
+    y = torch.empty((N, Cc, 2 * H, 2 * W), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    rc = _lib.load().ff_upsample2x_nhwc(_ptr(x), _ptr(y), N, H, W, Cc, _stream())
+    _lib.check(rc, "ff_upsample2x_nhwc")
+    _count("ff_upsample2x_nhwc")
+    return y
+
+
+def concat_nhwc(a, b):
+    """torch.cat([a, b], dim=1) of channels_last bf16 [N,C,H,W] tensors -> channels_last [N,Ca+Cb,H,W].  See ff_concat_nhwc."""
+    N, HW, Ca = _nhwc_view(a, "a")
+    Nb, HWb, Cb = _nhwc_view(b, "b")
+    if (N, HW) != (Nb, HWb) or a.shape[2:] != b.shape[2:]:
+        raise ValueError(f"concat_nhwc: shapes {tuple(a.shape)} and {tuple(b.shape)} differ outside the channel dimension")
+    out = torch.empty((N, Ca + Cb, a.shape[2], a.shape[3]), dtype=a.dtype, device=a.device, memory_format=torch.channels_last)
+    rc = _lib.load().ff_concat_nhwc(_ptr(a), _ptr(b), _ptr(out), N * HW, Ca, Cb, _stream())
+    _lib.check(rc, "ff_concat_nhwc")
+    _count("ff_concat_nhwc")
+    return out
+
+
 _LT_WS: dict = {}
 
 

@@ -116,6 +116,19 @@ def hbm_rooflines(dev, peak_gbs: float, with_eager: bool = False):
             rows.append(_row("ff_bias_residual_nhwc", 3 * xg.numel() * 2, ms, peak_gbs, size=f"{n}x{c}x{hh}x{ww} bf16"))
             del r2
         del xg
+    xu = _nhwc(32, 640, 32, 32, dev)
+    ms = _timeit(lambda: ops.upsample2x_nhwc(xu))
+    r = _row("ff_upsample2x_nhwc", 5 * xu.numel() * 2, ms, peak_gbs, size="32x640x32x32 -> 64x64 bf16")
+    if with_eager:
+        r["eager_ms"] = _timeit(lambda: F.interpolate(xu, scale_factor=2.0, mode="nearest"))
+    rows.append(r)
+    ca_, cb_ = _nhwc(32, 640, 64, 64, dev), _nhwc(32, 320, 64, 64, dev)
+    ms = _timeit(lambda: ops.concat_nhwc(ca_, cb_))
+    r = _row("ff_concat_nhwc", 2 * (ca_.numel() + cb_.numel()) * 2, ms, peak_gbs, size="32x(640+320)x64x64 bf16")
+    if with_eager:
+        r["eager_ms"] = _timeit(lambda: torch.cat([ca_, cb_], dim=1))
+    rows.append(r)
+    del xu, ca_, cb_
     hg = torch.randn(32, 4096, 2560, device=dev).bfloat16()
     ms = _timeit(lambda: ops.geglu(hg))
     r = _row("ff_geglu", hg.numel() * 2 * 3 // 2, ms, peak_gbs, size="32x4096x2560 bf16")

@@ -71,6 +71,13 @@ def _attn_res(attn, h, res, **kw):
     return out if attn.ff_residual_fused else out + res
 
 
+def _cat(a, b):
+    """torch.cat([a, b], dim=1); dense NHWC bf16 tensors go through the 128-bit copy kernel."""
+    if _fast(a) and a.shape[1] % 8 == 0 and b.shape[1] % 8 == 0:
+        return ops.concat_nhwc(a, b)
+    return torch.cat([a, b], dim=1)
+
+
 def _tokens(x):
     """channels_last [N,C,H,W] -> [N, H*W, C] view."""
     n, c, h, w = x.shape
@@ -254,6 +261,8 @@ class Upsample2D(nn.Module):
         self.conv = nn.Conv2d(ch, ch, 3, padding=1)
 
     def forward(self, x, output_size=None):
+        if _fast(x) and x.shape[1] % 8 == 0 and (output_size is None or tuple(output_size) == (2 * x.shape[2], 2 * x.shape[3])):
+            return _conv(ops.upsample2x_nhwc(x), self.conv)
         if output_size is None:
             x = F.interpolate(x, scale_factor=2.0, mode="nearest")
         else:
@@ -336,7 +345,7 @@ class UpBlock2D(nn.Module):
         for r in self.resnets:
             res = res_hidden_states_tuple[-1]
             res_hidden_states_tuple = res_hidden_states_tuple[:-1]
-            hidden_states = r(torch.cat([hidden_states, res], dim=1), temb)
+            hidden_states = r(_cat(hidden_states, res), temb)
         if self.upsamplers is not None:
             for u in self.upsamplers:
                 hidden_states = u(hidden_states, upsample_size)
@@ -362,7 +371,7 @@ class CrossAttnUpBlock2D(nn.Module):
         for r, a in zip(self.resnets, self.attentions):
             res = res_hidden_states_tuple[-1]
             res_hidden_states_tuple = res_hidden_states_tuple[:-1]
-            hidden_states = r(torch.cat([hidden_states, res], dim=1), temb)
+            hidden_states = r(_cat(hidden_states, res), temb)
             hidden_states = a(hidden_states, encoder_hidden_states=encoder_hidden_states)
         if self.upsamplers is not None:
             for u in self.upsamplers:

@@ -150,6 +150,12 @@ int ff_mask_prep(const uint8_t* shifted, const uint8_t* ori, const uint8_t* draw
  * (model.py:927-934, src/utils/vis_utils.py:340-347).  W % 4 == 0.                                                    */
 int ff_dilate_mask(const uint8_t* mask, uint8_t* out, int32_t N, int32_t H, int32_t W, int32_t k, void* stream);
 
+/* y[n, 2h+dy, 2w+dx, c] = x[n, h, w, c] (nearest 2x up-sampling, F.interpolate(scale_factor=2, mode="nearest") of diffusers'
+ * Upsample2D) and out[m, :] = [a[m, :Ca], b[m, :Cb]] (torch.cat([hidden_states, res], dim=1) of the up blocks) on dense bf16
+ * NHWC tensors, any 16-bit type really: pure 128-bit copies.  C, Ca, Cb % 8 == 0.                                          */
+int ff_upsample2x_nhwc(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
+int ff_concat_nhwc(const void* a, const void* b, void* out, int64_t M, int32_t Ca, int32_t Cb, void* stream);
+
 /* out[M,N] = x[M,K] . w[N,K]^T (+ bias[N]) (+ res[M,N]), bf16 row-major, fp32 accumulation, ONE cuBLASLt GEMM (bias epilogue +
  * beta * C): a plain library GEMM behind the C ABI.  Replaces `Linear(h) + hidden_states` at the end of every sub-block of
  * diffusers' BasicTransformerBlock / Transformer2DModel as walked by override_forward (src/utils/attention.py:13-223), i.e. the

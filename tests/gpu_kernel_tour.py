@@ -77,5 +77,10 @@ mm = lambda: ((torch.rand(2, 128, 128, device=dev) > 0.7).to(torch.uint8) * 255)
 ops.mask_prep(mm(), mm(), None, mm(), (16, 16), True, True)
 ops.mask_prep(mm(), mm(), mm(), mm(), (16, 16), False, True)
 ops.dilate_mask(mm(), 15)
+xu = torch.randn(2, 64, 5, 7, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+ops.upsample2x_nhwc(xu)
+ops.concat_nhwc(xu, torch.randn(2, 24, 5, 7, device=dev).bfloat16().contiguous(memory_format=torch.channels_last))
+ops.linear_bias_residual(torch.randn(33, 64, device=dev).bfloat16(), torch.randn(40, 64, device=dev).bfloat16(),
+                         torch.randn(40, device=dev).bfloat16(), torch.randn(33, 40, device=dev).bfloat16())
 torch.cuda.synchronize()
 print("kernel tour ok:", dict(ops.COUNTS))

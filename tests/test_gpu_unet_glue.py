@@ -225,3 +225,26 @@ def test_group_norm_addend_as_column_block(dev, shape):
     want = ref_group_norm_nhwc(x, gamma, beta, G, 1e-5, add_nc=add.contiguous(), silu=True)
     torch.testing.assert_close(got.float(), want.float(), rtol=RTOL, atol=ATOL)
     assert torch.equal(got, ops.group_norm_nhwc(x, gamma, beta, G, 1e-5, add_nc=add.contiguous(), silu=True))
+
+
+@pytest.mark.parametrize("shape", [(2, 640, 32, 32), (3, 1280, 8, 8), (1, 320, 5, 7), (2, 8, 3, 3)])
+def test_upsample2x_nhwc_bit_exact(dev, shape):
+    from freefine_b200 import ops
+    n, c, h, w = shape
+    x = _nhwc(n, c, h, w, dev, 51)
+    got = ops.upsample2x_nhwc(x)
+    want = F.interpolate(x, scale_factor=2.0, mode="nearest")
+    assert got.shape == (n, c, 2 * h, 2 * w) and got.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("shape", [(2, 1280, 640, 32, 32), (3, 320, 320, 64, 64), (1, 8, 16, 3, 5), (2, 1280, 1280, 8, 8)])
+def test_concat_nhwc_bit_exact(dev, shape):
+    from freefine_b200 import ops
+    n, ca, cb, h, w = shape
+    a, b = _nhwc(n, ca, h, w, dev, 52), _nhwc(n, cb, h, w, dev, 53)
+    got = ops.concat_nhwc(a, b)
+    assert got.shape == (n, ca + cb, h, w) and got.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(got, torch.cat([a, b], dim=1))
+    with pytest.raises(ValueError):
+        ops.concat_nhwc(a, _nhwc(n, cb, h + 1, w, dev, 54))

@@ -60,6 +60,17 @@ def ref_linear_bias_residual(x, weight, bias=None, res=None, out=None):
     return v.to(x.dtype)
 
 
+def ref_upsample2x_nhwc(x):
+    _dense_nhwc(x)
+    return F.interpolate(x, scale_factor=2.0, mode="nearest").contiguous(memory_format=torch.channels_last)
+
+
+def ref_concat_nhwc(a, b):
+    _dense_nhwc(a)
+    _dense_nhwc(b)
+    return torch.cat([a, b], dim=1).contiguous(memory_format=torch.channels_last)
+
+
 @pytest.fixture
 def forced_fast(monkeypatch):
     monkeypatch.setattr(standin, "_fast", lambda x: True)
@@ -68,6 +79,8 @@ def forced_fast(monkeypatch):
     monkeypatch.setattr(ops, "geglu", ref_geglu)
     monkeypatch.setattr(ops, "layer_norm", ref_layer_norm)
     monkeypatch.setattr(ops, "linear_bias_residual", ref_linear_bias_residual)
+    monkeypatch.setattr(ops, "upsample2x_nhwc", ref_upsample2x_nhwc)
+    monkeypatch.setattr(ops, "concat_nhwc", ref_concat_nhwc)
 
 
 def _inputs(parts, n=3, hw=16):

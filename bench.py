@@ -146,10 +146,10 @@ def run_reference(args):
 
 def ncu_traffic(sq, skv, d, B):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/r1_attn_ncu_summary.txt: the same launch shape, S=4096 d=40 32 streams, run alone by profiles/attn_case.py);
+    (profiles/r2b_attn_ncu_summary.txt: the same launch shape, S=4096 d=40 32 streams, run alone by profiles/attn_case.py);
     {} when the dominant launch of this run has another shape or the summary is absent."""
     here = os.path.dirname(os.path.abspath(__file__))
-    path = next((q for q in (os.path.join(here, "profiles", f) for f in ("r2_attn_ncu_summary.txt", "r1_attn_ncu_summary.txt"))
+    path = next((q for q in (os.path.join(here, "profiles", f) for f in ("r2b_attn_ncu_summary.txt", "r2_attn_ncu_summary.txt", "r1_attn_ncu_summary.txt"))
                  if os.path.exists(q)), None)
     if (sq, skv, d, B) != (4096, 4096, 40, 32) or path is None:
         return {}

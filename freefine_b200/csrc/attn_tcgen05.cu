@@ -58,6 +58,9 @@ template <bool HILO> constexpr float rescale_threshold() { return HILO ? 24.f : 
 #ifndef FF_POLY_PATTERN
 #define FF_POLY_PATTERN 0x92
 #endif
+#ifndef FF_SEP_P
+#define FF_SEP_P 0   // experiment switch (parity-green, slower: 2.55 vs 2.35 ms -- profiles/r2b_attn_experiments.txt)
+#endif
 #ifndef FF_SELF_ISSUE
 #define FF_SELF_ISSUE 0   // experiment switch (measured slower: 2.84 vs 2.35 ms, profiles/r2b_attn_experiments.txt)
 #endif
@@ -73,8 +76,13 @@ template <int DPAD, bool HILO> struct Cfg {
   static_assert(NSTAGE >= 2, "QK(t+1) is issued before PV(t): tile t+1 must fit beside tile t");
   // TMEM: S buffer 0 / 1 (= tile parity), then one O accumulator PER PARITY (each warpgroup runs its own online
   // softmax over its tiles; the two are merged at the end of a pass)
-  static constexpr int TMEM_S = 0, TMEM_O = 2 * BN;                     // O of parity b at TMEM_O + b * DPV
-  static constexpr int TMEM_USED = 2 * BN + 2 * DPV;
+  // SEP (d <= 40, fp16 P, -DFF_SEP_P): the packed P tile (32 columns) gets its OWN TMEM region, shared by the two
+  // warpgroups in turn, instead of overwriting the S columns it came from.  The S buffer of a tile is then free as soon as
+  // its scores have been read, QK(t+2) is issued UNDER the exp sweep of tile t, and the warpgroup's chain no longer
+  // contains  p_full -> PV(t), QK(t+2) -> s_full  (about a third of its period in the round-2 timelines).
+  static constexpr bool SEP = FF_SEP_P && DPAD == 48 && !HILO && NSTAGE == 4;
+  static constexpr int TMEM_S = 0, TMEM_P = 2 * BN, TMEM_O = 2 * BN + (SEP ? BN / 2 : 0);   // O of parity b at TMEM_O + b * DPV
+  static constexpr int TMEM_USED = TMEM_O + 2 * DPV;
   static constexpr int TMEM_COLS = TMEM_USED <= 256 ? 256 : 512;
   static constexpr int SMEM_Q = NKT * TILE_BYTES;
   static constexpr int SMEM_STAGE = 2 * NKT * KV_BYTES;                 // K tiles then V tiles
@@ -89,7 +97,7 @@ template <int DPAD, bool HILO> struct Cfg {
   // named barrier and its first warp issues PV(t) and QK(t+2) itself -- the p_full mbarrier round trip (arrive -> the
   // sleeping issuer warp resumes: ~330 cycles in the round-2 timelines, on the critical chain of every tile) is replaced
   // by a bar.sync among four warps, and nine warps instead of ten leave 112 instead of 96 registers per thread.
-  static constexpr bool SELF = FF_SELF_ISSUE && DPAD == 48 && !HILO && NSTAGE == 4;
+  static constexpr bool SELF = FF_SELF_ISSUE && !SEP && DPAD == 48 && !HILO && NSTAGE == 4;
   static constexpr int THREADS = SELF ? 32 * (NUM_SOFTMAX_WARPS + 1) : NUM_THREADS;
 };
 
@@ -160,8 +168,10 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
     }
   }
 #else
+  const long long t0 = clock64();
 #pragma unroll 1
-  for (uint32_t n = 0; n < (1u << 26); ++n) {
+  for (uint32_t n = 1;; ++n) {
+    if ((n & 15u) == 0 && clock64() - t0 > 4000000000LL) break;    // ~2 s (a sleeping try_wait returns after ~10 ms)
 #if FF_WAIT_FORM == 1
     if (mbar_try(bar, parity)) return;
 #else
@@ -652,6 +662,25 @@ __device__ __forceinline__ void lean_pv_qk48(uint32_t obuf, uint32_t sp, uint64_
   }
 }
 
+// SEP: O (+)= P V with P in its own region (K-step k at packed columns 8k), then the commits kv_empty and pv_done
+__device__ __forceinline__ void lean_pv48_sep(uint32_t obuf, uint32_t pbase, uint64_t vdesc, uint32_t idesc_pv, uint32_t acc0,
+                                              uint32_t bar_kve, uint32_t bar_o_) {
+  asm volatile(
+      "{\n\t.reg .pred e, p0, pt;\n\t.reg .b64 v1, v2, v3;\n\t.reg .b32 a1, a2, a3;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p0, %4, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+      "add.u64 v1, %2, 128;\n\tadd.u64 v2, %2, 256;\n\tadd.u64 v3, %2, 384;\n\t"
+      "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 16;\n\tadd.u32 a3, %1, 24;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], v1, %3, pt;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], v2, %3, pt;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], v3, %3, pt;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t}"
+      ::"r"(obuf), "r"(pbase), "l"(vdesc), "r"(idesc_pv), "r"(acc0), "r"(bar_kve), "r"(bar_o_)
+      : "memory");
+}
+
 template <int DPAD, bool P_HILO>
 __global__ void __launch_bounds__(Cfg<DPAD, P_HILO>::THREADS, Cfg<DPAD, P_HILO>::MIN_CTAS)
 attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -674,6 +703,12 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
   const uint32_t bar_s = bar_base + 16, bar_p = bar_base + 32;
   const uint32_t bar_kv_full = bar_base + 48, bar_kv_empty = bar_base + 48 + 8 * C::NSTAGE;
   const uint32_t tmem_slot = bar_base + 48 + 16 * C::NSTAGE;            // u32 written by tcgen05.alloc
+  // SEP: s_free[2] (the scores of a parity's tile have been read: 4 warp arrivals) and pv_done[2] (one completion per PV
+  // of that parity: PV(t) and every earlier MMA have completed; pv_done of the OTHER parity is also "the P region is free").
+  // A parity wait is exact only when the barrier is at most one completion behind what is waited for and cannot run
+  // ahead of it: see the notes at the two wait sites.
+  const uint32_t bar_f = bar_base + 192, bar_o = bar_base + 208;
+  static_assert(48 + 16 * C::NSTAGE + 8 <= 192, "barrier block layout");
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   float* const acc_smem = reinterpret_cast<float*>(gen_base + (sACC - smem_base));
   float* const mx_smem = reinterpret_cast<float*>(gen_base + (sMX - smem_base));
@@ -693,6 +728,10 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     mbar_init(bar_s + 8, 1);
     mbar_init(bar_p, NUM_SOFTMAX_WARPS / 2);    // one elected arrival per warp of the warpgroup that owns the parity
     mbar_init(bar_p + 8, NUM_SOFTMAX_WARPS / 2);
+    mbar_init(bar_f, NUM_SOFTMAX_WARPS / 2);
+    mbar_init(bar_f + 8, NUM_SOFTMAX_WARPS / 2);
+    mbar_init(bar_o, 1);
+    mbar_init(bar_o + 8, 1);
     for (int i = 0; i < C::NSTAGE; ++i) {
       mbar_init(bar_kv_full + 8 * i, 1);
       mbar_init(bar_kv_empty + 8 * i, 1);
@@ -815,7 +854,49 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       }
       FF_TRACE(0, 20);
       mbar_wait(bar_q, 0);
-      if constexpr (FF_LEAN_ISSUER && DPAD == 48 && !P_HILO && C::NSTAGE == 4) {
+      if constexpr (C::SEP) {
+        // Tile t = 4g + u: stage u, parity u & 1.  Per tile, in order:  [A] QK(t+2) as soon as the scores of tile t have
+        // been read (s_free) and K/V(t+2) has landed;  [B] PV(t) when P(t) is in the P region.  The warpgroups run about
+        // half a period apart, so waiting for p_full(t) before looking at s_free(t+1) costs the other parity nothing.
+        tc_fence_after();
+        if (n_total > 0) { lean_wait(bar_kv_full, 0); tc_fence_after(); lean_qk48(tmem + C::TMEM_S, qdesc0, kdesc0, idesc_qk, bar_s); }
+        if (n_total > 1) {
+          lean_wait(bar_kv_full + 8, 0);
+          tc_fence_after();
+          lean_qk48(tmem + C::TMEM_S + BN, qdesc0, kdesc0 + (uint64_t)(C::SMEM_STAGE >> 4), idesc_qk, bar_s + 8);
+        }
+        uint32_t gph = 0;
+        int t = 0;
+#pragma unroll 1
+        while (t < n_total) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (t < n_total) {
+              const int pstart = t >= pe2 ? pe2 : (t >= pe1 ? pe1 : (t >= pe0 ? pe0 : 0));
+              const uint32_t acc0 = (t - pstart < 2) ? 0u : 1u;      // the first tile of each parity in a pass starts O
+              FF_TL(1, t, 0);
+              if (t + 2 < n_total) {
+                lean_wait(bar_kv_full + 8 * ((u + 2) & 3), u < 2 ? gph : gph ^ 1u);
+                lean_wait(bar_f + 8 * (u & 1), (uint32_t)((u >> 1) & 1));
+                FF_TL(1, t, 1);
+                tc_fence_after();
+                lean_qk48(tmem + C::TMEM_S + BN * (u & 1), qdesc0, kdesc0 + (uint64_t)((((u + 2) & 3) * C::SMEM_STAGE) >> 4),
+                          idesc_qk, bar_s + 8 * (u & 1));
+              }
+              FF_TL(1, t, 2);
+              lean_wait(bar_p, (uint32_t)(u & 1));
+              FF_TL(1, t, 3);
+              tc_fence_after();
+              lean_pv48_sep(tmem + C::TMEM_O + C::DPV * (u & 1), tmem + C::TMEM_P, vdesc0 + (uint64_t)((u * C::SMEM_STAGE) >> 4),
+                            idesc_pv, acc0, bar_kv_empty + 8 * u, bar_o + 8 * (u & 1));
+              FF_TL(1, t, 4);
+              ++t;
+            }
+          }
+          gph ^= 1u;
+        }
+        __syncwarp();
+      } else if constexpr (FF_LEAN_ISSUER && DPAD == 48 && !P_HILO && C::NSTAGE == 4) {
         // Lean flat loop, unrolled over one turn of the four-stage K/V ring: tile t = 4g + u sits in stage u, its S/P
         // buffer and accumulator have parity u & 1, p_full(t) has phase (u >> 1) & 1, and the K/V stage of tile t + 2 is
         // (u + 2) & 3 with phase g (u < 2) or g + 1 -- everything but g is a compile-time constant.  kv_full(t + 2) is
@@ -1115,7 +1196,8 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
               m_used = mts;
               grow = true;
             }
-            if (__any_sync(0xffffffffu, grow)) {
+            const bool any_grow = __any_sync(0xffffffffu, grow);
+            auto rescale_o = [&]() {
 #pragma unroll
               for (int c = 0; c < C::DPV / 16; ++c) {      // (includes the denominator column)
                 float o[16];
@@ -1126,13 +1208,15 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                 for (int i = 0; i < 16; ++i) ob[i] = __float_as_uint(o[i] * alpha);
                 tmem_st16(tO + 16 * c, ob);
               }
-            }
+            };
+            // (SEP: s_full(itj) no longer implies PV(itj-2) -- the rescale waits for pv_done below, before P is stored)
+            if (!C::SEP && any_grow) rescale_o();
             FF_TL(0, itj, 3);
             // ---- p = 2^(s*scale*log2e - m), packed for the tensor core over the S columns of the same keys:
             // fp16: K-step ks -> packed columns 32*(ks/2) + 8*(ks%2) + [0,8); hi/lo bf16: hi at 16*ks + [0,8), lo at
             // 16*ks + [8,16).  Columns [32,64) first (still in registers), then [0,32) re-read.
             const float nb = (cls == TILE_MIX || row_ok_cls) ? -m_used : -INFINITY;   // -inf: p = 0 for the whole row
-            uint32_t pk[P_HILO ? 32 : 16];
+            uint32_t pk[(P_HILO || C::SEP) ? 32 : 16];     // SEP: [0,16) = keys 0..31, [16,32) = keys 32..63, stored at the end
 #pragma unroll
             for (int hb = 1; hb >= 0; --hb) {
               float sa[32];
@@ -1142,6 +1226,12 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
               if (hb == 0) {
                 tmem_ld32(tS, sa);
                 tmem_wait_ld32(sa);
+                if constexpr (C::SEP) {
+                  // every score of the tile is in registers: the S buffer may take QK(itj+2) now
+                  tc_fence_before();
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive(bar_f + 8 * wg);
+                }
               }
               const float* sv = hb ? sb : sa;
 #endif
@@ -1150,22 +1240,36 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 #pragma unroll
                 for (int jj = 0; jj < 2; ++jj) {
                   if constexpr (P_HILO) softmax_chunk_hilo<false>(sv + 16 * jj, pk + 16 * jj, sc, nb, 0u);
-                  else softmax_chunk_f16<false>(sv + 16 * jj, pk + 8 * jj, sc, nb, 0u);
+                  else softmax_chunk_f16<false>(sv + 16 * jj, pk + (C::SEP ? 16 * hb : 0) + 8 * jj, sc, nb, 0u);
                 }
               } else {
 #pragma unroll
                 for (int jj = 0; jj < 2; ++jj) {
                   const uint32_t bits = (kbits >> (16 * jj)) & 0xffffu;
                   if constexpr (P_HILO) softmax_chunk_hilo<true>(sv + 16 * jj, pk + 16 * jj, sc, nb, bits);
-                  else softmax_chunk_f16<true>(sv + 16 * jj, pk + 8 * jj, sc, nb, bits);
+                  else softmax_chunk_f16<true>(sv + 16 * jj, pk + (C::SEP ? 16 * hb : 0) + 8 * jj, sc, nb, bits);
                 }
               }
               if constexpr (P_HILO) {
                 tmem_st16(tS + 32 * hb, *reinterpret_cast<const uint32_t(*)[16]>(pk));
                 tmem_st16(tS + 32 * hb + 16, *reinterpret_cast<const uint32_t(*)[16]>(pk + 16));
-              } else {
+              } else if constexpr (!C::SEP) {
                 tmem_st16(tS + 32 * hb, *reinterpret_cast<const uint32_t(*)[16]>(pk));
               }
+            }
+            if constexpr (C::SEP) {
+              // the P region is shared with the other warpgroup: PV(itj-1) must have consumed P(itj-1); in-order
+              // completion then also covers PV(itj-2), the last writer of O_wg (rescale).  Exact: the previous completion
+              // of that barrier, PV(itj-3), is implied by s_full(itj) (QK(itj) was issued after it), and the next one,
+              // PV(itj+1), needs a P that is only stored after PV(itj), i.e. after the P this warpgroup is about to store.
+              if (itj >= 1) {
+                const uint32_t bo = bar_o + 8 * (wg ^ 1), po = (uint32_t)(((itj - 1) >> 1) & 1);
+                if (!mbar_test(bo, po)) mbar_wait(bo, po);
+              }
+              tc_fence_after();
+              if (any_grow) rescale_o();
+              tmem_st16(tlane + C::TMEM_P, *reinterpret_cast<const uint32_t(*)[16]>(pk));
+              tmem_st16(tlane + C::TMEM_P + 16, *reinterpret_cast<const uint32_t(*)[16]>(pk + 16));
             }
             FF_TL(0, itj, 4);
             tmem_wait_st();
@@ -1188,7 +1292,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
               }
             } else {
               __syncwarp();
-              if (lane == 0) mbar_arrive(bar_p + 8 * wg);
+              if (lane == 0) mbar_arrive(C::SEP ? bar_p : bar_p + 8 * wg);     // (SEP: one p_full barrier, phases in tile order)
             }
             FF_TL(0, itj, 6);
             FF_TRACE(itj, 34);
@@ -1201,7 +1305,14 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
       // ---- end of pass: merge the two partial softmaxes, acc += weight * roww / l * O.
       // (1) my last PV has landed: s_full(last_mine + 2) -- a real tile of the next pass or one of the two virtual commits
       FF_TRACE(it, 35);
-      if (n_mine > 0) mbar_wait_hot<0>(bar_s + 8 * wg, ((last_mine + 2) >> 1) & 1);
+      if constexpr (C::SEP) {
+        // every PV of the pass has completed <=> the PV of its last tile L = it - 1 has (in-order completion).  Exact: the
+        // previous completion of that barrier, PV(L-2), was implied by the last per-tile wait of either warpgroup (or by
+        // the previous end of pass), and PV(L+2) belongs to the next pass, which starts after this merge.
+        const int L = it - 1;
+        mbar_wait(bar_o + 8 * (L & 1), (uint32_t)((L >> 1) & 1));
+        tc_fence_after();
+      } else if (n_mine > 0) mbar_wait_hot<0>(bar_s + 8 * wg, ((last_mine + 2) >> 1) & 1);
       FF_TRACE(it, 36);
       // (2) exchange the reference points (row-wise, through shared memory)
       mx_smem[wg * BM + rloc] = n_mine > 0 ? m_used : -INFINITY;

@@ -4,7 +4,7 @@
 # usage: round2b_attn_ab.sh <tag> "<variants>" "<ring modes for the product lib>"
 mkdir -p gpurun_out
 T=${1:-ab}; VARS=${2:-""}; MODES=${3:-""}
-timeout 600 python -m pytest tests/test_gpu_attention.py tests/test_gpu_kernels.py -q -m gpu -x > gpurun_out/${T}_pytest.txt 2>&1; echo "product: $(tail -1 gpurun_out/${T}_pytest.txt)"
+timeout 300 python -m pytest tests/test_gpu_attention.py tests/test_gpu_kernels.py -q -m gpu -x --timeout 60 > gpurun_out/${T}_pytest.txt 2>&1; echo "product: $(tail -1 gpurun_out/${T}_pytest.txt)"
 echo "== product" > gpurun_out/${T}_attn_case.txt
 timeout 120 python profiles/attn_case.py 5 >> gpurun_out/${T}_attn_case.txt 2>&1
 for v in $VARS; do

@@ -42,6 +42,10 @@ for cta in range(2):
     print("softmax tile period (own tiles): mean %.0f  min %d  max %d" % (dt.mean(), dt.min(), dt.max()))
     seg = (sm[rows, 1:7] - sm[rows, 0:6]).astype(np.int64)
     print("mean phase durations: wait_s %.0f  load+max(h0) %.0f  load+max(h1) %.0f  exp %.0f  st_wait %.0f  arrive %.0f" % tuple(seg.mean(0)))
+    for i in range(8, 20):
+        a = [int(x - t0) if x else -1 for x in sm[i, :7]]
+        b = [int(x - t0) if x else -1 for x in mm[i, :5]]
+        print(f"tile {i:2d} S " + " ".join(f"{x:7d}" for x in a) + "  | M " + " ".join(f"{x:7d}" for x in b))
     mrows = [i for i in range(4, 60) if mm[i, 0] and mm[i, 4]]
     if mrows:
         md = np.diff(mm[mrows, 0].astype(np.int64))

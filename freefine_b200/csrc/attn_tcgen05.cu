@@ -58,6 +58,9 @@ template <bool HILO> constexpr float rescale_threshold() { return HILO ? 24.f : 
 #ifndef FF_POLY_PATTERN
 #define FF_POLY_PATTERN 0x92
 #endif
+#ifndef FF_T32_DEFAULT
+#define FF_T32_DEFAULT 0
+#endif
 #ifndef FF_SEP_P
 #define FF_SEP_P 0   // experiment switch (parity-green, slower: 2.55 vs 2.35 ms -- profiles/r2b_attn_experiments.txt)
 #endif
@@ -1408,6 +1411,7 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 }
 
 #include "attn_ring.cuh"        // ring-buffered kernel: the product kernel for fp16-P, 8 < head_dim <= 80
+#include "attn_t32.cuh"         // 32-key-tile kernel for head_dim <= 40 (FF_ATTN_T32)
 
 // ---------------------------------------------------------------------------------------------------------------
 // host side
@@ -1502,6 +1506,24 @@ int launch_ring(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
   return ff::check_launch("ff_attn_masked_kv (ring kernel)");
 }
 
+int launch_t32(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const KParams& kp, int n_streams, cudaStream_t st) {
+  static std::atomic<uint64_t> configured{0};
+  int rc = ensure_smem(attn_t32_kernel, T32::SMEM_BYTES, configured);
+  if (rc != FF_OK) return rc;
+  dim3 grid((kp.s_q + BM - 1) / BM, kp.heads, n_streams);
+  attn_t32_kernel<<<grid, NUM_THREADS, T32::SMEM_BYTES, st>>>(mq, mk, mv, kp);
+  return ff::check_launch("ff_attn_masked_kv (32-key tiles)");
+}
+
+int t32_mode() {      // FF_ATTN_T32 in the environment, read once: 1 = 32-key-tile kernel for 8 < head_dim <= 40 (fp16 P)
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("FF_ATTN_T32");
+    mode = e ? (atoi(e) != 0) : FF_T32_DEFAULT;
+  }
+  return mode;
+}
+
 // Kernel selection for the fp16-P path, 8 < head_dim <= 80 (FF_ATTN_RING in the environment, read once; experiments only):
 //   0 = legacy kernel; ring <DPAD, warpgroups, S/P buffers, exp token> for d<=40 / d<=80:
 //   1 = <48,1,3,0> (two CTAs per SM) / <80,2,3,0>    2 = <48,2,4,0> / <80,2,3,0>    3 = <48,3,5,0> / <80,2,3,0>
@@ -1578,12 +1600,14 @@ extern "C" int ff_attn_masked_kv(const FFAttnArgs* a, void* stream) {
   alignas(64) CUtensorMap mq, mk, mv;
   int rc;
   if ((rc = make_map(&mq, a->q, a->n_streams, a->s_q, a->heads, a->head_dim, BM)) != FF_OK) return rc;
-  if ((rc = make_map(&mk, a->k, a->n_kv_streams, a->s_kv, a->heads, a->head_dim, BN)) != FF_OK) return rc;
   const bool v_f16 = a->v_dtype == FF_DT_F16;
+  const bool use_t32 = v_f16 && a->head_dim > 8 && a->head_dim <= 40 && t32_mode() != 0;
+  const int kv_rows = use_t32 ? TBN : BN;                  // rows of a K / V box = keys per tile of the kernel that runs
+  if ((rc = make_map(&mk, a->k, a->n_kv_streams, a->s_kv, a->heads, a->head_dim, kv_rows)) != FF_OK) return rc;
   FF_REQUIRE(a->v_head_stride == ff_attn_v_head_stride(a->head_dim),
              "ff_attn_masked_kv: V must be staged by ff_kv_gather_cast (v_head_stride=%d, expected %d)",
              a->v_head_stride, ff_attn_v_head_stride(a->head_dim));
-  if ((rc = make_map(&mv, a->v, a->n_kv_streams, a->s_kv, a->heads, a->v_head_stride, BN, v_f16)) != FF_OK) return rc;
+  if ((rc = make_map(&mv, a->v, a->n_kv_streams, a->s_kv, a->heads, a->v_head_stride, kv_rows, v_f16)) != FF_OK) return rc;
 
   KParams kp;
   kp.plan = a->plan;
@@ -1605,6 +1629,7 @@ extern "C" int ff_attn_masked_kv(const FFAttnArgs* a, void* stream) {
   // thresholds leave room for the ones column at channel d inside DPV (see ff_attn_v_head_stride)
   if (v_f16) {
     if (d <= 8) return launch<16, false>(mq, mk, mv, kp, a->n_streams, st);
+    if (use_t32) return launch_t32(mq, mk, mv, kp, a->n_streams, st);
     const int rm = ring_mode();
     if (rm == 1 && d <= 40) return launch_ring<48, 1, 3, false>(mq, mk, mv, kp, a->n_streams, st);
     if (rm == 2 && d <= 40) return launch_ring<48, 2, 4, false>(mq, mk, mv, kp, a->n_streams, st);

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_traffic_is_read_from_the_committed_ncu_summary():
     t = bench.ncu_traffic(4096, 4096, 40, 32)
-    name = next(f for f in ("r2_attn_ncu_summary.txt", "r1_attn_ncu_summary.txt") if os.path.exists(os.path.join(ROOT, "profiles", f)))
+    name = next(f for f in ("r2b_attn_ncu_summary.txt", "r2_attn_ncu_summary.txt", "r1_attn_ncu_summary.txt") if os.path.exists(os.path.join(ROOT, "profiles", f)))
     lines = [l.split() for l in open(os.path.join(ROOT, "profiles", name))]
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     rd = next(float(f[1]) * unit[f[2]] for f in lines if f and f[0] == "dram__bytes_read.sum")

@@ -1136,6 +1136,9 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             {
               float sa[32];
               tmem_ld32(tS, sa);
+#ifdef FF_LD_BOTH     // both halves of the row in flight together: one tcgen05.ld round trip instead of two per tile
+              tmem_ld32(tS + 32, sb);
+#endif
               tmem_wait_ld32(sa);
               float m0, m1;
               if (cls != TILE_MIX) {
@@ -1161,7 +1164,9 @@ attn_masked_kv_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 #pragma unroll
               for (int i = 0; i < 32; ++i) sb[i] = mt + (float)i;
 #else
+#ifndef FF_LD_BOTH
               tmem_ld32(tS + 32, sb);
+#endif
               tmem_wait_ld32(sb);
 #endif
               float m0, m1;

@@ -35,7 +35,7 @@ def launches():
         lines.append("%9.3f ms %5.1f%%  x%4d  %s" % (ms, 100 * ms / total, c, name[:90]))
     ours = {k: (round(v[0], 3), v[1]) for k, v in tot.items() if any(s in k for s in ("attn_masked", "attn_ring", "gn_fused", "warp_affine", "ddim_", "mask_downsample", "cross_region", "kv_gather", "gn_stats", "gn_apply",
                                                                                       "geglu_kernel", "layer_norm_kernel", "layer_norm5_kernel", "bias_residual", "gn_small", "mask_prep",
-                                                                                      "dilate_kernel"))}
+                                                                                      "dilate_kernel", "upsample2x_nhwc", "concat_nhwc"))}
     lines.append("# our kernels (ms, launches): %s" % ours)
     lines.append("# share of our kernels: %.1f%%   share of all ff_attn_masked_kv launches: %.1f%%" % (
         100 * sum(v[0] for v in ours.values()) / total, 100 * sum(v[0] for k, v in ours.items() if "attn_masked" in k or "attn_ring" in k) / total))

@@ -27,6 +27,10 @@ reference's GeoBench-2D default skips the first 35 schedule steps (`--start-step
             this process on the UNet path that was timed, and on the fp32 UNet body.
 `secondary`: (N=1) short measurements of the GeoBench-2D default schedule (start_step 35), of 768^2 / start_step 15
             (BASELINE.json configs[4] shape) and of the fp32 UNet body (`--unet-dtype fp32` arm), same code path.
+`gpu_launches`: launches of OUR kernels inside the timed region (per C-ABI entry in `gpu_launches_by_entry`);
+            `library_gemm_launches_by_entry` lists apart the entries that launch library code (ff_linear_bias_residual = one
+            cuBLASLt GEMM with bias epilogue + beta*C).  `config.cudnn_benchmark`: torch.backends.cudnn.benchmark is on by
+            default (fixed convolution shapes, tuned inside the warm-up steps; `--no-cudnn-benchmark` for the A/B).
 `--sweep M`: BASELINE.json configs[2]: M edits sharded i mod W (DistributedSampler order, tail padding included), batches of
             `--edits`, final latents gathered over NCCL inside the timed region; strong scaling, reported as `sweep`.
 """

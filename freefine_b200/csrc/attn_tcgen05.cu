@@ -1599,7 +1599,14 @@ extern "C" int ff_attn_masked_kv(const FFAttnArgs* a, void* stream) {
   }
   int dev = 0, major = 0;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  {
+    static std::atomic<int> cached_major[64];          // per device, queried once (this runs once per attention launch)
+    major = cached_major[dev & 63].load(std::memory_order_relaxed);
+    if (major == 0) {
+      cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+      cached_major[dev & 63].store(major, std::memory_order_relaxed);
+    }
+  }
   if (major != 10) return ff::fail(FF_E_ARCH, "ff_attn_masked_kv: needs an sm_100 device (got sm_%d*)", major);
 
   alignas(64) CUtensorMap mq, mk, mv;

@@ -198,6 +198,11 @@ class FreeFinePipeline:
 
     def _unet(self, latents, t, text_embeddings):
         dt = self.unet.dtype if hasattr(self.unet, "dtype") else next(self.unet.parameters()).dtype
+        if latents.is_cuda and not (torch.is_tensor(t) and t.is_cuda):
+            # the timestep as a device tensor made by a fill kernel: an H2D copy from pageable memory (what
+            # `timesteps.to(device)` inside the UNet would do) synchronises the stream first, i.e. drains the launch queue
+            # once per UNet call
+            t = torch.full((), int(t), dtype=torch.int64, device=latents.device)
         with ops.nvtx_range(f"ff.unet streams={latents.shape[0]}"):
             out = self.unet(latents.to(dt), t, encoder_hidden_states=text_embeddings.to(dt))
         return out.float()

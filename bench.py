@@ -74,6 +74,9 @@ def parse():
                     help="fp32: UNet body in fp32 (TF32 off) -- the arm whose whole-edit parity meets the 1e-2 north-star")
     ap.add_argument("--sweep", type=int, default=0, help="config 3: that many edits sharded over the ranks + final gather")
     ap.add_argument("--no-extras", action="store_true", help="skip rooflines / parity / secondary measurements")
+    ap.add_argument("--active-frac-steps", type=int, default=4,
+                    help="schedule steps of the batch run under CUPTI for gpu_active_frac (4 = quick default; the batch "
+                         "boundaries weigh 12x more there than in the full 50-step schedule -- pass 50 for the real figure)")
     return ap.parse_args()
 
 
@@ -487,9 +490,11 @@ def run_ours(args):
         from freefine_b200 import roofline as RF, selfcheck
         t_x = time.perf_counter()
         try:
-            extras["gpu_active_frac"] = RF.gpu_active_frac(lambda: run_device(pipe, dev_batches[args.warmup], settings(args.num_step, max(args.start_step, args.num_step - 4))))
+            extras["gpu_active_frac"] = RF.gpu_active_frac(lambda: run_device(pipe, dev_batches[args.warmup], settings(args.num_step, max(args.start_step, args.num_step - args.active_frac_steps))))
             if extras["gpu_active_frac"]:
-                extras["gpu_active_frac"]["step"] = "one batch with the last 4 schedule steps (4 inversion + 4 sampling UNet calls)"
+                n_af = args.num_step - max(args.start_step, args.num_step - args.active_frac_steps)
+                extras["gpu_active_frac"]["step"] = (f"one batch with the last {n_af} schedule steps ({n_af} inversion + {n_af} sampling UNet "
+                                                     f"calls) incl. the per-batch coarse edit / mask prep / VAE boundaries")
         except Exception as e:
             extras["gpu_active_frac"] = {"frac": None, "error": str(e)[:200]}
         del dev_batches[:]

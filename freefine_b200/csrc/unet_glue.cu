@@ -40,13 +40,92 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// SiLU of eight values.  t * sigmoid(t) = t / (1 + 2^(-t * log2 e)): the straightforward form costs TWO MUFU operations per
+// element (EX2 + RCP); at 16 MUFU lanes per clock and SM that is 8 elements per clock -- 9 TB/s of algorithmic GroupNorm
+// traffic, the same order as the HBM peak -- while taking every reciprocal on the FMA pipe instead (bit-trick seed,
+// |rel err| <= 0.101, + three Newton steps as packed FFMA2 / FMUL2: 1.5e-7, fp32-exact for a bf16 result) makes the apply
+// loop issue-bound (8 instead of 5 instructions per element).  Measured on B200 (profiles/r2c_gn_kernels.txt, GroupNorm +
+// SiLU 32x320x64x64 / 32x1920x32x32): mode 0 = MUFU reciprocal everywhere 62.7 / 94.1 us, mode 2 = Newton everywhere 63.3 /
+// 94.8 us, mode 3 = HALF of the pairs each way (both pipes busy) 59.8 / 87.0 us -- the product.  Mode 1
+// (t * (0.5 + 0.5 * tanh.approx(t / 2)), one MUFU and 4 instructions: 54.2 / 76.3 us) is NOT used: its absolute error
+// |t| * 2.4e-4 is a 70 % relative error at t = -8, where the other modes are exact to fp32 rounding.
+#ifndef FF_SILU_MODE
+#define FF_SILU_MODE 3
+#endif
+__device__ __forceinline__ void silu8(float (&f)[8]) {
+#if FF_SILU_MODE == 0
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = __fdividef(f[j], 1.f + __expf(-f[j]));
+#elif FF_SILU_MODE == 1
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float th;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * f[j]));
+    f[j] = f[j] * fmaf(0.5f, th, 0.5f);
+  }
+#else
+#ifndef FF_SILU_NR
+#define FF_SILU_NR 3
+#endif
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    const float2 t = make_float2(f[j], f[j + 1]);
+    // Newton path: exponent argument clamped to 2^126 so that d = 1 + e stays finite (t < -87: silu(t) = -0 either way)
+    const float2 a = __fmul2_rn(t, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+    float2 e, r;
+#if FF_SILU_MODE == 3
+    if (j >= 4) {                                          // (compile-time after unrolling) half of the pairs: MUFU.RCP;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(a.x));      // rcp(1 + inf) = 0, no clamp needed here
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(a.y));
+      const float2 d = __fadd2_rn(e, make_float2(1.f, 1.f));
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(d.x));
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(d.y));
+    } else
+#endif
+    {
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(fminf(a.x, 126.f)));
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(fminf(a.y, 126.f)));
+      const float2 d = __fadd2_rn(e, make_float2(1.f, 1.f));
+      r = make_float2(__uint_as_float(0x7EF311C7u - __float_as_uint(d.x)), __uint_as_float(0x7EF311C7u - __float_as_uint(d.y)));
+      const float2 nd = make_float2(-d.x, -d.y), two = make_float2(2.f, 2.f);
+#pragma unroll
+      for (int it = 0; it < FF_SILU_NR; ++it) r = __fmul2_rn(r, __ffma2_rn(nd, r, two));
+    }
+    const float2 o = __fmul2_rn(t, r);
+    f[j] = o.x;
+    f[j + 1] = o.y;
+  }
+#endif
+}
+
+// thread-block cluster primitives (PTX; sm_90+): split barrier and a distributed-shared-memory load
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all() {
+  cluster_arrive_release();
+  cluster_wait_acquire();
+}
+__device__ __forceinline__ unsigned int cluster_nctarank() {
+  unsigned int v;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(v));
+  return v;
+}
+__device__ __forceinline__ float ld_dsmem_f32(const float* my_smem, unsigned int rank) {
+  const uint32_t local = static_cast<uint32_t>(__cvta_generic_to_shared(my_smem));
+  uint32_t remote;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 constexpr int GN_THREADS = 256;
 constexpr int GN_MAX_CHUNKS = 64;     // pixel chunks per image (partial statistics per chunk), two-kernel form
 constexpr int GN_MAX_CHUNKS_FUSED = 128;   // ... single-read form (the workspace is sized for this one)
 #ifndef FF_GN_MLP
-#define FF_GN_MLP 4
+#define FF_GN_MLP 8
 #endif
 constexpr int GN_MLP = FF_GN_MLP;     // independent 16-byte loads in flight per thread (statistics and apply loops)
 constexpr int GN_CHUNK_PX = 128;      // pixels per CTA, images of more than 1024 pixels
@@ -66,8 +145,20 @@ struct GnLayout {
   }
 };
 
-// partial[n][chunk][g] = (sum, sum of squares) of v = x + add over the pixels of the chunk and the channels of group g
-__global__ void __launch_bounds__(GN_THREADS)
+// bf16x8 -> four fp32 pairs (low half, high half of each word: channels 2i, 2i+1)
+__device__ __forceinline__ void unpack8_pairs(const uint4& q, float2 (&f)[4]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) f[i] = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+}
+
+// partial[n][chunk][g] = (sum, sum of squares) of v = x + add over the pixels of the chunk and the channels of group g.
+// Round 2 (third session): the loop accumulates the RAW sums of x as packed pairs (FADD2 / FFMA2: 16 instructions per
+// 16-byte vector with the unpack, was 40 with the per-element addend) and folds the per-(n, c) addend in afterwards
+// (sum(x + a) = sum(x) + k a,  sum((x + a)^2) = sum(x^2) + 2 a sum(x) + k a^2,  k = pixels this thread walked); full batches
+// of GN_MLP loads run without per-load predicates, the ragged end as one predicated batch.  ncu before: 89 executed
+// instructions per vector, issue slots 49 % busy on an HBM-bound kernel.
+__global__ void __launch_bounds__(GN_THREADS, 4)
 gn_stats_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_nc, long long add_ld, float2* __restrict__ partial,
                      int HW, int C, int G, int chunk_px, int n_chunks) {
   extern __shared__ float sm[];                 // [R][2][C] per-row-slot channel sums, then reduced into slot 0
@@ -79,41 +170,54 @@ gn_stats_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_
   const int p0 = chunk * chunk_px, p1 = min(HW, p0 + chunk_px);
   if (L.r < L.R) {
     for (int v = L.col; v < L.CV; v += L.cols) {
-      float a[8], s[8], ss[8];
+      float2 s2[4], q2[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        a[j] = add_nc ? __ldg(add_nc + (size_t)n * add_ld + 8 * v + j) : 0.f;
-        s[j] = ss[j] = 0.f;
-      }
+      for (int i = 0; i < 4; ++i) s2[i] = q2[i] = make_float2(0.f, 0.f);
       const uint4* px = x + ((size_t)n * HW + p0 + L.r) * L.CV + v;
       const size_t step = (size_t)L.R * L.CV;
-      // batches of GN_MLP independent loads, THEN the arithmetic: with a plain `#pragma unroll 4` ptxas kept two loads in
-      // flight per thread (each load sat next to its 32 dependent operations) and the pass ran at 2.5 TB/s
+      int p = p0 + L.r;
+      const int mine = p < p1 ? (p1 - p + L.R - 1) / L.R : 0;     // pixels of this thread
 #pragma unroll 1
-      for (int p = p0 + L.r; p < p1; p += GN_MLP * L.R, px += GN_MLP * step) {
-        uint4 raw[GN_MLP];
+      for (; p + (GN_MLP - 1) * L.R < p1; p += GN_MLP * L.R, px += GN_MLP * step) {
+        uint4 raw[GN_MLP];                                 // independent loads first, then the arithmetic
 #pragma unroll
-        for (int u = 0; u < GN_MLP; ++u)
-          raw[u] = (p + u * L.R < p1) ? __ldg(px + u * step) : make_uint4(0u, 0u, 0u, 0u);
+        for (int u = 0; u < GN_MLP; ++u) raw[u] = __ldg(px + u * step);
 #pragma unroll
         for (int u = 0; u < GN_MLP; ++u) {
-          if (p + u * L.R < p1) {
-            float f[8];
-            unpack8(raw[u], f);
+          float2 f[4];
+          unpack8_pairs(raw[u], f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float t = f[j] + a[j];
-              s[j] += t;
-              ss[j] = fmaf(t, t, ss[j]);
-            }
+          for (int i = 0; i < 4; ++i) {
+            s2[i] = __fadd2_rn(s2[i], f[i]);
+            q2[i] = __ffma2_rn(f[i], f[i], q2[i]);
+          }
+        }
+      }
+      if (p < p1) {                                        // ragged end: ONE predicated batch (zeros add nothing)
+        uint4 raw[GN_MLP];
+#pragma unroll
+        for (int u = 0; u < GN_MLP; ++u) raw[u] = (p + u * L.R < p1) ? __ldg(px + u * step) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int u = 0; u < GN_MLP; ++u) {
+          float2 f[4];
+          unpack8_pairs(raw[u], f);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            s2[i] = __fadd2_rn(s2[i], f[i]);
+            q2[i] = __ffma2_rn(f[i], f[i], q2[i]);
           }
         }
       }
       float* dst = sm + (size_t)L.r * 2 * C + 8 * v;
+      const float k = (float)mine;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        dst[j] = s[j];
-        dst[C + j] = ss[j];
+      for (int i = 0; i < 4; ++i) {
+        const float a0 = add_nc ? __ldg(add_nc + (size_t)n * add_ld + 8 * v + 2 * i) : 0.f;
+        const float a1 = add_nc ? __ldg(add_nc + (size_t)n * add_ld + 8 * v + 2 * i + 1) : 0.f;
+        dst[2 * i] = fmaf(k, a0, s2[i].x);
+        dst[2 * i + 1] = fmaf(k, a1, s2[i].y);
+        dst[C + 2 * i] = fmaf(a0, fmaf(k, a0, 2.f * s2[i].x), q2[i].x);
+        dst[C + 2 * i + 1] = fmaf(a1, fmaf(k, a1, 2.f * s2[i].y), q2[i].y);
       }
     }
   }
@@ -181,34 +285,52 @@ gn_apply_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_
   const int p0 = chunk * chunk_px, p1 = min(HW, p0 + chunk_px);
   for (int v = L.col; v < L.CV; v += L.cols) {
     float sc[8], sh[8];
+    {
+      int g = (8 * v) / cpg, rem = 8 * v - g * cpg;       // one division per vector; the group advances with the channel
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = 8 * v + j, g = c / cpg;
-      const float a = add_nc ? __ldg(add_nc + (size_t)n * add_ld + c) : 0.f;
-      sc[j] = rstd[g] * __bfloat162float(gamma[c]);
-      sh[j] = fmaf(a - mean[g], sc[j], __bfloat162float(beta[c]));     // y = (x + a - mean) * rstd * gamma + beta
+      for (int j = 0; j < 8; ++j) {
+        if (rem == cpg) {
+          rem = 0;
+          ++g;
+        }
+        ++rem;
+        const float a = add_nc ? __ldg(add_nc + (size_t)n * add_ld + 8 * v + j) : 0.f;
+        sc[j] = rstd[g] * __bfloat162float(gamma[8 * v + j]);
+        sh[j] = fmaf(a - mean[g], sc[j], __bfloat162float(beta[8 * v + j]));     // y = (x + a - mean) * rstd * gamma + beta
+      }
     }
     const size_t off = ((size_t)n * HW + p0 + L.r) * L.CV + v;
     const uint4* px = x + off;
     uint4* py = y + off;
     const size_t step = (size_t)L.R * L.CV;
+    int p = p0 + L.r;
 #pragma unroll 1
-    for (int p = p0 + L.r; p < p1; p += GN_MLP * L.R, px += GN_MLP * step, py += GN_MLP * step) {
+    for (; p + (GN_MLP - 1) * L.R < p1; p += GN_MLP * L.R, px += GN_MLP * step, py += GN_MLP * step) {
       uint4 raw[GN_MLP];                                   // (independent loads first: see the statistics kernel)
 #pragma unroll
-      for (int u = 0; u < GN_MLP; ++u)
-        raw[u] = (p + u * L.R < p1) ? __ldg(px + u * step) : make_uint4(0u, 0u, 0u, 0u);
+      for (int u = 0; u < GN_MLP; ++u) raw[u] = __ldg(px + u * step);
+#pragma unroll
+      for (int u = 0; u < GN_MLP; ++u) {
+        float f[8];
+        unpack8(raw[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+        if (SILU) silu8(f);
+        py[u * step] = pack8(f);
+      }
+    }
+    if (p < p1) {                                          // ragged end: one predicated batch
+      uint4 raw[GN_MLP];
+#pragma unroll
+      for (int u = 0; u < GN_MLP; ++u) raw[u] = (p + u * L.R < p1) ? __ldg(px + u * step) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
       for (int u = 0; u < GN_MLP; ++u) {
         if (p + u * L.R < p1) {
           float f[8];
           unpack8(raw[u], f);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float t = fmaf(f[j], sc[j], sh[j]);
-            if (SILU) t = __fdividef(t, 1.f + __expf(-t));     // 2 MUFU ops; the IEEE division made this kernel ALU-bound
-            f[j] = t;
-          }
+          for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+          if (SILU) silu8(f);
           py[u * step] = pack8(f);
         }
       }
@@ -224,16 +346,25 @@ gn_apply_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_
 // CHANNELS instead: one CTA per (image, bundle of B groups whose channels fill whole 16-byte vectors), all HW pixels of
 // those channels in registers (VPT vectors per thread, all loads in flight at once), statistics and apply in one pass --
 // x is read exactly once, there is no workspace traffic, and a 32 x 1280 x 16 x 16 launch has 1024 CTAs instead of 128.
-template <bool SILU, int VPT>
-__global__ void __launch_bounds__(GN_THREADS, VPT >= 24 ? 2 : 1)
+//
+// Cluster form (CL, experiment switch FF_GN_CLUSTER=1 -- see gn_small_plan): images too large for one CTA's registers (64 x 64 and up, and the wide 32 x 32 concatenations) are
+// split by PIXELS over a thread-block cluster of S <= 8 CTAs on top of the channel split; each CTA reduces its part, the
+// per-group sums are exchanged through distributed shared memory between two cluster barriers (every CTA adds the S
+// partials in rank order: identical statistics everywhere, bit-reproducible), and the apply runs from registers as before.
+// Still one read of x and no workspace; the only cross-CTA traffic is 2 * B floats per CTA.
+template <bool SILU, int VPT, bool CL>
+__global__ void __launch_bounds__(GN_THREADS, VPT >= 32 ? 1 : (VPT >= 12 ? 2 : 1))
 gn_small_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_nc, long long add_ld,
                      const __nv_bfloat16* __restrict__ gamma,
-                     const __nv_bfloat16* __restrict__ beta, uint4* __restrict__ y, int HW, int C, int G, int B, float eps) {
+                     const __nv_bfloat16* __restrict__ beta, uint4* __restrict__ y, int HW, int C, int G, int B, int P, float eps) {
   __shared__ float sm[GN_THREADS / 32 * 8 * 2 + 16];   // [warp][group][S, SS] partials, then [B] mean, [B] rstd
+  __shared__ float xch[16];                            // CL: this CTA's [group][S, SS], read by the cluster peers
   const int cpg = C / G, bch = B * cpg, BV = bch >> 3, CV = C >> 3;
   const int R = GN_THREADS / BV, col = threadIdx.x % BV, r = threadIdx.x / BV;
   const bool live = r < R;
   const int n = blockIdx.y, bundle = blockIdx.x;
+  const int pb = CL ? (int)blockIdx.z * P : 0;              // my pixel range [pb, pe)
+  const int pe = CL ? min(HW, pb + P) : HW;
   const int c0 = bundle * bch + 8 * col;        // my eight channels
   float* stat = sm + GN_THREADS / 32 * 8 * 2;
   float a[8];
@@ -243,15 +374,15 @@ gn_small_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_
   const uint4* px = x + ((size_t)n * HW) * CV + bundle * BV + col;
 #pragma unroll
   for (int k = 0; k < VPT; ++k) {
-    const int p = r + k * R;
-    raw[k] = (live && p < HW) ? __ldg(px + (size_t)p * CV) : make_uint4(0u, 0u, 0u, 0u);
+    const int p = pb + r + k * R;
+    raw[k] = (live && p < pe) ? __ldg(px + (size_t)p * CV) : make_uint4(0u, 0u, 0u, 0u);
   }
   float s[8], ss[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
 #pragma unroll
   for (int k = 0; k < VPT; ++k) {
-    if (live && r + k * R < HW) {
+    if (live && pb + r + k * R < pe) {
       float f[8];
       unpack8(raw[k], f);
 #pragma unroll
@@ -298,43 +429,104 @@ gn_small_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_
       S += sm[(w * 8 + threadIdx.x) * 2];
       SS += sm[(w * 8 + threadIdx.x) * 2 + 1];
     }
-    const float inv_cnt = 1.f / ((float)cpg * (float)HW);
-    const float m = S * inv_cnt;
-    const float var = fmaxf(SS * inv_cnt - m * m, 0.f);
-    stat[threadIdx.x] = m;
-    stat[B + threadIdx.x] = 1.f / sqrtf(var + eps);
-  }
-  __syncthreads();
-  if (!live) return;
-  float sc[8], sh[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int g = gid[j];
-    sc[j] = stat[B + g] * __bfloat162float(gamma[c0 + j]);
-    sh[j] = fmaf(a[j] - stat[g], sc[j], __bfloat162float(beta[c0 + j]));     // y = (x + a - mean) * rstd * gamma + beta
-  }
-  uint4* py = y + ((size_t)n * HW) * CV + bundle * BV + col;
-#pragma unroll
-  for (int k = 0; k < VPT; ++k) {
-    const int p = r + k * R;
-    if (p < HW) {
-      float f[8];
-      unpack8(raw[k], f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float t = fmaf(f[j], sc[j], sh[j]);
-        if (SILU) t = __fdividef(t, 1.f + __expf(-t));
-        f[j] = t;
-      }
-      py[(size_t)p * CV] = pack8(f);
+    if (CL) {
+      xch[2 * threadIdx.x] = S;
+      xch[2 * threadIdx.x + 1] = SS;
+    } else {
+      const float inv_cnt = 1.f / ((float)cpg * (float)HW);
+      const float m = S * inv_cnt;
+      const float var = fmaxf(SS * inv_cnt - m * m, 0.f);
+      stat[threadIdx.x] = m;
+      stat[B + threadIdx.x] = 1.f / sqrtf(var + eps);
     }
   }
+  if (CL) {
+    cluster_sync_all();                                     // partials of every CTA of the cluster are in place
+    if (threadIdx.x < B) {
+      float S = 0.f, SS = 0.f;
+      const unsigned int nr = cluster_nctarank();
+      for (unsigned int rk = 0; rk < nr; ++rk) {            // rank order: the same sum in every CTA
+        S += ld_dsmem_f32(&xch[2 * threadIdx.x], rk);
+        SS += ld_dsmem_f32(&xch[2 * threadIdx.x + 1], rk);
+      }
+      const float inv_cnt = 1.f / ((float)cpg * (float)HW);
+      const float m = S * inv_cnt;
+      const float var = fmaxf(SS * inv_cnt - m * m, 0.f);
+      stat[threadIdx.x] = m;
+      stat[B + threadIdx.x] = 1.f / sqrtf(var + eps);
+    }
+    cluster_arrive_release();                               // my reads of the peers are done (waited for at the exit)
+  }
+  __syncthreads();
+  if (live) {
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = gid[j];
+      sc[j] = stat[B + g] * __bfloat162float(gamma[c0 + j]);
+      sh[j] = fmaf(a[j] - stat[g], sc[j], __bfloat162float(beta[c0 + j]));     // y = (x + a - mean) * rstd * gamma + beta
+    }
+    uint4* py = y + ((size_t)n * HW) * CV + bundle * BV + col;
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const int p = pb + r + k * R;
+      if (p < pe) {
+        float f[8];
+        unpack8(raw[k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+        if (SILU) silu8(f);
+        py[(size_t)p * CV] = pack8(f);
+      }
+    }
+  }
+  if (CL) cluster_wait_acquire();                           // nobody leaves while a peer may still read its xch[]
 }
 
-// groups per bundle B (the smallest B dividing G whose B * cpg channels are whole 16-byte vectors), vectors per thread;
-// 0 = the shape does not fit the register-resident form
-int gn_small_plan(int HW, int C, int G, int* B_out, size_t* smem) {
+struct GnSmallArgs {
+  const uint4* x;
+  const float* add_nc;
+  long long add_ld;
+  const __nv_bfloat16 *gamma, *beta;
+  uint4* y;
+  int HW, C, G, B, P;
+  float eps;
+};
+
+// grid.z = cluster size (the cluster spans z only); CL launches go through cudaLaunchKernelEx with the cluster attribute
+template <int VPT, bool CL>
+cudaError_t gn_small_launch(const GnSmallArgs& a, dim3 grid, bool silu, cudaStream_t st) {
+  auto kern = silu ? gn_small_nhwc_kernel<true, VPT, CL> : gn_small_nhwc_kernel<false, VPT, CL>;
+  if (!CL) {
+    kern<<<grid, GN_THREADS, 0, st>>>(a.x, a.add_nc, a.add_ld, a.gamma, a.beta, a.y, a.HW, a.C, a.G, a.B, a.P, a.eps);
+    return cudaSuccess;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(GN_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = grid.z;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, a.x, a.add_nc, a.add_ld, a.gamma, a.beta, a.y, a.HW, a.C, a.G, a.B, a.P, a.eps);
+}
+
+// groups per bundle B (the smallest B dividing G whose B * cpg channels are whole 16-byte vectors), vectors per thread
+// and cluster size S (1 = plain launch); 0 = the shape does not fit the register-resident form
+int gn_small_plan(int HW, int C, int G, int* B_out, int* S_out, int* P_out) {
   static const bool off = [] { const char* e = getenv("FF_GN_SMALL"); return e && atoi(e) == 0; }();
+  // FF_GN_CLUSTER=1: cluster form for shapes beyond 24 vectors per thread -- an EXPERIMENT switch: measured on B200 it is
+  // parity-green but slower than the two-kernel form at every such shape (77 vs 65 us at 32x320x64x64, 226 vs 157 us at
+  // 32x960x64x64, 117 vs 85 us at 32x1920x32x32: with 2 CTAs of 128 registers per SM the load, reduce and apply phases
+  // run in lock-step and nothing overlaps them, profiles/r2c_gn_kernels.txt);  FF_GN_CLUSTER_VPT: vectors per thread the
+  // cluster split aims for (tuning knob)
+  static const bool cl_on = [] { const char* e = getenv("FF_GN_CLUSTER"); return e && atoi(e) != 0; }();
+  static const int cl_vpt = [] { const char* e = getenv("FF_GN_CLUSTER_VPT"); const int v = e ? atoi(e) : 0; return v >= 2 && v <= 32 ? v : 24; }();
   if (off) return 0;
   const int cpg = C / G;
   int B = 0;
@@ -343,11 +535,29 @@ int gn_small_plan(int HW, int C, int G, int* B_out, size_t* smem) {
   if (!B) return 0;
   const int BV = B * cpg / 8;
   if (BV > GN_THREADS) return 0;
-  const int R = GN_THREADS / BV, need = (HW + R - 1) / R;
-  if (need > 24) return 0;
+  const int R = GN_THREADS / BV;
+  auto bucket = [](int need) { return need <= 2 ? 2 : (need <= 4 ? 4 : (need <= 6 ? 6 : (need <= 12 ? 12 : (need <= 24 ? 24 : 32)))); };
+  int S = 1, P = HW, need = (HW + R - 1) / R;
+  if (need > 24) {
+    if (!cl_on) return 0;
+    int best = 0;
+    for (int sz = 2; sz <= 8; sz <<= 1) {
+      const int p = (HW + sz - 1) / sz, nd = (p + R - 1) / R;
+      if ((sz - 1) * p >= HW) continue;                      // (an empty last CTA: pointless split)
+      if (nd <= 32) {
+        best = sz;
+        if (nd <= cl_vpt) break;
+      }
+    }
+    if (!best) return 0;
+    S = best;
+    P = (HW + S - 1) / S;
+    need = (P + R - 1) / R;
+  }
   *B_out = B;
-  *smem = 0;                                                 // (static shared memory only)
-  return need <= 2 ? 2 : (need <= 4 ? 4 : (need <= 6 ? 6 : (need <= 12 ? 12 : 24)));
+  *S_out = S;
+  *P_out = P;
+  return bucket(need);
 }
 
 // ---- single-read GroupNorm (round 2) -----------------------------------------------------------------------------------
@@ -527,11 +737,8 @@ gn_fused_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_
       float f[8];
       unpack8(*pt, f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float t = fmaf(f[j], sc[j], sh[j]);
-        if (SILU) t = __fdividef(t, 1.f + __expf(-t));
-        f[j] = t;
-      }
+      for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+      if (SILU) silu8(f);
       *py = pack8(f);
     }
   }
@@ -567,45 +774,74 @@ bias_residual_kernel(const uint4* __restrict__ h, const __nv_bfloat16* __restric
 // gelu(g) = g * Phi(g), Phi from erfc(z) = t*(a1 + t*(a2 + t*(a3 + t*(a4 + t*a5)))) * exp(-z^2), t = 1/(1 + p z), z =
 // |g|/sqrt(2)  (Abramowitz & Stegun 7.1.26, absolute error 1.5e-7 -- four orders below the bf16 rounding of the result):
 // 2 MUFU ops + ~12 FMA-pipe ops per element instead of libdevice erff's ~30, which made the kernel ALU-bound.
-__device__ __forceinline__ float gelu_erf(float g) {
-  const float z = fabsf(g) * 0.70710678118654752440f;
-  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
-  float p = fmaf(t, 1.061405429f, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
-  const float half_erfc = 0.5f * p * t * e;                                      // 0.5 * erfc(|g|/sqrt 2)
-  return g * (g >= 0.f ? 1.f - half_erfc : half_erfc);
+// Round 2 (third session): the scalar form of this (one element at a time, x unpacked to fp32) executed ~26 instructions
+// per element and the kernel was ISSUE-bound (335 M elements x 26 / 32 lanes / 592 schedulers = 186 us of issue slots for
+// a launch that took 197 us; the HBM floor is 154 us).  gelu_erf_x_bf16x2 evaluates a PAIR of gates with packed FFMA2 / FMUL2 (0.5 folded into the polynomial,
+// gelu = g / 2 + |g| * (1/2 - erfc/2): no select), rounds the pair to bf16x2 and multiplies it with the still-packed x
+// pair by HMUL2.BF16 -- exact product, ONE rounding: what the eager bf16 multiply does -- so x is never
+// unpacked: ~12 instructions per element.  With two MUFU operations per element the MUFU pipe (16 lanes per clock and
+// SM) would then be the bound at 149 us, so every other pair takes its reciprocal on the FMA pipe (seed + 3 Newton steps,
+// see silu8).
+template <bool NEWTON>
+__device__ __forceinline__ uint32_t gelu_erf_x_bf16x2(uint32_t gate, uint32_t xw) {
+  const float2 g = make_float2(__uint_as_float(gate << 16), __uint_as_float(gate & 0xffff0000u));
+  const float2 ag = make_float2(fabsf(g.x), fabsf(g.y));
+  const float2 den = __ffma2_rn(ag, make_float2(0.23164189045f, 0.23164189045f), make_float2(1.f, 1.f));   // 1 + p |g| / sqrt 2
+  float2 t;
+  if (NEWTON) {
+    t = make_float2(__uint_as_float(0x7EF311C7u - __float_as_uint(den.x)), __uint_as_float(0x7EF311C7u - __float_as_uint(den.y)));
+    const float2 nd = make_float2(-den.x, -den.y), two = make_float2(2.f, 2.f);
+#pragma unroll
+    for (int it = 0; it < 3; ++it) t = __fmul2_rn(t, __ffma2_rn(nd, t, two));
+  } else {
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(den.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(den.y));
+  }
+  // p = erfc polynomial / 2 (Abramowitz & Stegun 7.1.26 coefficients halved)
+  float2 p = __ffma2_rn(t, make_float2(0.5307027145f, 0.5307027145f), make_float2(-0.7265760135f, -0.7265760135f));
+  p = __ffma2_rn(p, t, make_float2(0.7107068705f, 0.7107068705f));
+  p = __ffma2_rn(p, t, make_float2(-0.142248368f, -0.142248368f));
+  p = __ffma2_rn(p, t, make_float2(0.127414796f, 0.127414796f));
+  const float2 arg = __fmul2_rn(__fmul2_rn(g, g), make_float2(-0.7213475204444817f, -0.7213475204444817f));   // -z^2 log2 e
+  float2 e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(arg.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(arg.y));
+  const float2 h = __fmul2_rn(__fmul2_rn(p, t), e);                                       // erfc(|g| / sqrt 2) / 2
+  const float2 q = __fadd2_rn(make_float2(0.5f, 0.5f), make_float2(-h.x, -h.y));
+  const float2 ge = __ffma2_rn(ag, q, __fmul2_rn(g, make_float2(0.5f, 0.5f)));           // g/2 + |g| (1/2 - h) = g Phi(g)
+  const __nv_bfloat162 gb = __floats2bfloat162_rn(ge.x, ge.y);                            // the bf16 tensor F.gelu returns
+  const __nv_bfloat162 r = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&xw), gb);   // bf16 * bf16, one rounding
+  return *reinterpret_cast<const uint32_t*>(&r);
 }
 
+__device__ __forceinline__ uint4 geglu8(const uint4& qx, const uint4& qg) {
+  return make_uint4(gelu_erf_x_bf16x2<false>(qg.x, qx.x), gelu_erf_x_bf16x2<true>(qg.y, qx.y),
+                    gelu_erf_x_bf16x2<false>(qg.z, qx.z), gelu_erf_x_bf16x2<true>(qg.w, qx.w));
+}
+
+// (dm, dv) = (2 * stride) div / mod FV from the host: the (row, vector) pair advances without a 64-bit division per trip
 __global__ void __launch_bounds__(256)
-geglu_kernel(const uint4* __restrict__ h, uint4* __restrict__ out, long long total, int FV) {
+geglu_kernel(const uint4* __restrict__ h, uint4* __restrict__ out, long long total, int FV, long long dm, int dv) {
   // two output vectors per trip: four independent 16-byte loads in flight per thread before the erf arithmetic
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 2 * stride) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  long long m = i / FV, m2 = (i + stride) / FV;
+  int v = (int)(i - m * FV), v2 = (int)(i + stride - m2 * FV);
+  for (; i < total; i += 2 * stride) {
     const long long i2 = i + stride;
     const bool two = i2 < total;
-    const long long m = i / FV, m2 = two ? i2 / FV : m;
-    const int v = (int)(i - m * FV), v2 = two ? (int)(i2 - m2 * FV) : v;
     const uint4* row = h + m * 2 * FV;
-    const uint4* row2 = h + m2 * 2 * FV;
+    const uint4* row2 = h + (two ? m2 : m) * 2 * FV;
+    const int w2 = two ? v2 : v;
     const uint4 qx = __ldg(row + v), qg = __ldg(row + FV + v);
-    const uint4 qx2 = __ldg(row2 + v2), qg2 = __ldg(row2 + FV + v2);
-    float x[8], g[8];
-    unpack8(qx, x);
-    unpack8(qg, g);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] *= bf16_round(gelu_erf(g[j]));
-    out[i] = pack8(x);
-    if (two) {
-      unpack8(qx2, x);
-      unpack8(qg2, g);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] *= bf16_round(gelu_erf(g[j]));
-      out[i2] = pack8(x);
-    }
+    const uint4 qx2 = __ldg(row2 + w2), qg2 = __ldg(row2 + FV + w2);
+    out[i] = geglu8(qx, qg);
+    if (two) out[i2] = geglu8(qx2, qg2);
+    m += dm; v += dv;
+    if (v >= FV) { v -= FV; ++m; }
+    m2 += dm; v2 += dv;
+    if (v2 >= FV) { v2 -= FV; ++m2; }
   }
 }
 
@@ -867,26 +1103,25 @@ extern "C" int ff_group_norm_nhwc(const void* x, const float* add_nc, int64_t ad
   // load, reduce and store phases of the CTAs on an SM do not overlap enough (profiles/r2_gn_single_read.txt).
   static const bool two_kernel = [] { const char* e = getenv("FF_GN_SINGLE_READ"); return !(e && atoi(e) != 0); }();
   {
-    int B = 0;
-    size_t smem = 0;
-    const int vpt = gn_small_plan(HW, C, G, &B, &smem);
+    int B = 0, S = 1, P = HW;
+    const int vpt = gn_small_plan(HW, C, G, &B, &S, &P);
     if (vpt > 0) {
-      const dim3 grid(G / B, N);
-      const uint4* xp = static_cast<const uint4*>(x);
-      const __nv_bfloat16* gp = static_cast<const __nv_bfloat16*>(gamma);
-      const __nv_bfloat16* bp = static_cast<const __nv_bfloat16*>(beta);
-      uint4* yp = static_cast<uint4*>(y);
-#define FF_GN_SMALL_LAUNCH(V)                                                                                            \
-  do {                                                                                                                   \
-    if (silu) gn_small_nhwc_kernel<true, V><<<grid, GN_THREADS, smem, st>>>(xp, add_nc, add_ld, gp, bp, yp, HW, C, G, B, eps);    \
-    else gn_small_nhwc_kernel<false, V><<<grid, GN_THREADS, smem, st>>>(xp, add_nc, add_ld, gp, bp, yp, HW, C, G, B, eps);        \
-  } while (0)
-      if (vpt == 2) FF_GN_SMALL_LAUNCH(2);
-      else if (vpt == 4) FF_GN_SMALL_LAUNCH(4);
-      else if (vpt == 6) FF_GN_SMALL_LAUNCH(6);
-      else if (vpt == 12) FF_GN_SMALL_LAUNCH(12);
-      else FF_GN_SMALL_LAUNCH(24);
-#undef FF_GN_SMALL_LAUNCH
+      const GnSmallArgs a{static_cast<const uint4*>(x), add_nc, (long long)add_ld, static_cast<const __nv_bfloat16*>(gamma),
+                          static_cast<const __nv_bfloat16*>(beta), static_cast<uint4*>(y), HW, C, G, B, P, eps};
+      const dim3 grid(G / B, N, S);
+      cudaError_t e;
+      if (S > 1) {
+        if (vpt <= 12) e = gn_small_launch<12, true>(a, grid, silu != 0, st);
+        else if (vpt == 24) e = gn_small_launch<24, true>(a, grid, silu != 0, st);
+        else e = gn_small_launch<32, true>(a, grid, silu != 0, st);
+      } else {
+        if (vpt == 2) e = gn_small_launch<2, false>(a, grid, silu != 0, st);
+        else if (vpt == 4) e = gn_small_launch<4, false>(a, grid, silu != 0, st);
+        else if (vpt == 6) e = gn_small_launch<6, false>(a, grid, silu != 0, st);
+        else if (vpt == 12) e = gn_small_launch<12, false>(a, grid, silu != 0, st);
+        else e = gn_small_launch<24, false>(a, grid, silu != 0, st);
+      }
+      if (e != cudaSuccess) return ff::fail(FF_E_CUDA, "ff_group_norm_nhwc (register-resident): %s", cudaGetErrorString(e));
       return ff::check_launch("ff_group_norm_nhwc (register-resident)");
     }
   }
@@ -961,8 +1196,12 @@ extern "C" int ff_geglu(const void* h, void* out, int64_t M, int32_t F, void* st
   FF_REQUIRE(M > 0 && F > 0 && F % 8 == 0, "ff_geglu: F must be a positive multiple of 8");
   FF_REQUIRE(ff::aligned16(h) && ff::aligned16(out), "ff_geglu: pointers must be 16-byte aligned");
   const long long total = (long long)M * (F / 8);
-  geglu_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint4*>(h), static_cast<uint4*>(out), total, F / 8);
+  // (a persistent grid of 148 x {4, 6, 8, 12} CTAs measured the same or slower than the 148 x 16 cap: 192 / 230 / 192 / 191
+  // vs 190 us at 131072 x 1280 -- the launch sits at 5.3 TB/s of its two-reads-one-write traffic either way)
+  const int grid = grid_for(total), FV = F / 8;
+  const long long step2 = 2LL * grid * 256;
+  geglu_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(h), static_cast<uint4*>(out), total, FV, step2 / FV, (int)(step2 % FV));
   return ff::check_launch("ff_geglu");
 }
 

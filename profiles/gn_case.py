@@ -49,3 +49,22 @@ for (m, c) in ((32 * 4096, 320), (32 * 1024, 640), (32 * 256, 1280), (16 * 4096,
         best = min(best, e0.elapsed_time(e1) / 10)
     byt = 2 * x.numel() * 2
     print(f"layer_norm {m}x{c}: {best * 1e3:7.1f} us  {byt / best / 1e6:6.0f} GB/s algorithmic")
+
+# GEGLU at the feed-forward widths of a 32-stream call: h [M, 2F] -> [M, F]
+for (m, f) in ((32 * 4096, 1280), (32 * 1024, 2560), (32 * 256, 5120), (16 * 4096, 1280)):
+    h = torch.randn(1, m, 2 * f, device=dev).bfloat16()
+    fn = lambda: ops.geglu(h)
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(10):
+            fn()
+    best = 1e9
+    for _ in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / 10)
+    byt = 3 * m * f * 2
+    print(f"geglu {m}x{f}: {best * 1e3:7.1f} us  {byt / best / 1e6:6.0f} GB/s algorithmic")

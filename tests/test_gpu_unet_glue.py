@@ -42,7 +42,9 @@ GN_SHAPES = [
     # register-resident small-image kernel at the SD1.5 sizes (bundles of 1 / 2 / 4 groups, 2..24 vectors per thread)
     (2, 1280, 8, 8, 32), (2, 1280, 16, 16, 32), (2, 2560, 16, 16, 32), (2, 1920, 16, 16, 32), (2, 640, 32, 32, 32),
     (1, 1280, 32, 32, 32), (2, 320, 32, 32, 32), (2, 1280, 24, 24, 32),
-    (2, 960, 32, 32, 32),     # 61 vectors per thread would be needed: stays on the two-kernel form
+    (2, 960, 32, 32, 32),     # 61 vectors per thread in one CTA: two-kernel form (cluster form with FF_GN_CLUSTER=1)
+    # ragged pixel splits (odd image sizes; last CTA of the cluster shorter in the cluster form)
+    (1, 320, 72, 72, 32), (1, 640, 50, 50, 32), (1, 320, 47, 47, 32), (2, 1920, 32, 32, 32),
 ]
 
 
@@ -64,6 +66,30 @@ def test_group_norm_nhwc(dev, shape, silu, with_add):
     torch.testing.assert_close(got.float(), want.float(), rtol=RTOL, atol=ATOL)
     # bit-reproducible run to run (fixed summation order)
     assert torch.equal(got, ops.group_norm_nhwc(x, gamma, beta, G, 1e-5, add_nc=add, silu=silu))
+
+
+def test_group_norm_cluster_switch(dev):
+    """FF_GN_CLUSTER=1 (experiment switch, read once per process): the thread-block-cluster form of the register-resident
+    kernel -- pixel split over 2 / 4 / 8 CTAs, statistics exchanged through distributed shared memory -- in a child process."""
+    import os, subprocess, sys
+    code = (
+        "import sys, torch; sys.path.insert(0, 'tests')\n"
+        "from test_unet_fast_cpu import ref_group_norm_nhwc\n"
+        "from freefine_b200 import ops\n"
+        "dev = torch.device('cuda:0'); g = torch.Generator(device='cpu').manual_seed(3)\n"
+        "for (n, c, h, w) in ((2, 320, 64, 64), (1, 960, 64, 64), (2, 960, 32, 32), (1, 320, 47, 47), (1, 640, 50, 50), (1, 320, 96, 96)):\n"
+        "    x = (torch.randn(n, c, h, w, generator=g) * 1.7 + 0.4).to(dev).bfloat16().contiguous(memory_format=torch.channels_last)\n"
+        "    ga = (1 + 0.3 * torch.randn(c, generator=g)).to(dev).bfloat16(); be = (0.2 * torch.randn(c, generator=g)).to(dev).bfloat16()\n"
+        "    add = (0.8 * torch.randn(n, c, generator=g)).to(dev)\n"
+        "    got = ops.group_norm_nhwc(x, ga, be, 32, 1e-5, add_nc=add, silu=True)\n"
+        "    want = ref_group_norm_nhwc(x, ga, be, 32, 1e-5, add_nc=add, silu=True)\n"
+        "    torch.testing.assert_close(got.float(), want.float(), rtol=8e-3, atol=2e-3)\n"
+        "    assert torch.equal(got, ops.group_norm_nhwc(x, ga, be, 32, 1e-5, add_nc=add, silu=True))\n"
+        "print('cluster ok')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FF_GN_CLUSTER="1")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "cluster ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_group_norm_large_mean(dev):

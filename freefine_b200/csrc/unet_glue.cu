@@ -52,29 +52,29 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 #ifndef FF_SILU_MODE
 #define FF_SILU_MODE 3
 #endif
-__device__ __forceinline__ void silu8(float (&f)[8]) {
+__device__ __forceinline__ void silu_pairs(float2 (&f)[4]) {
 #if FF_SILU_MODE == 0
 #pragma unroll
-  for (int j = 0; j < 8; ++j) f[j] = __fdividef(f[j], 1.f + __expf(-f[j]));
+  for (int i = 0; i < 4; ++i) f[i] = make_float2(__fdividef(f[i].x, 1.f + __expf(-f[i].x)), __fdividef(f[i].y, 1.f + __expf(-f[i].y)));
 #elif FF_SILU_MODE == 1
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float th;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * f[j]));
-    f[j] = f[j] * fmaf(0.5f, th, 0.5f);
+  for (int i = 0; i < 4; ++i) {
+    float2 th;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th.x) : "f"(0.5f * f[i].x));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th.y) : "f"(0.5f * f[i].y));
+    f[i] = __fmul2_rn(f[i], __ffma2_rn(make_float2(0.5f, 0.5f), th, make_float2(0.5f, 0.5f)));
   }
 #else
 #ifndef FF_SILU_NR
 #define FF_SILU_NR 3
 #endif
 #pragma unroll
-  for (int j = 0; j < 8; j += 2) {
-    const float2 t = make_float2(f[j], f[j + 1]);
-    // Newton path: exponent argument clamped to 2^126 so that d = 1 + e stays finite (t < -87: silu(t) = -0 either way)
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = f[i];
     const float2 a = __fmul2_rn(t, make_float2(-1.4426950408889634f, -1.4426950408889634f));
     float2 e, r;
 #if FF_SILU_MODE == 3
-    if (j >= 4) {                                          // (compile-time after unrolling) half of the pairs: MUFU.RCP;
+    if (i >= 2) {                                          // (compile-time after unrolling) half of the pairs: MUFU.RCP;
       asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(a.x));      // rcp(1 + inf) = 0, no clamp needed here
       asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(a.y));
       const float2 d = __fadd2_rn(e, make_float2(1.f, 1.f));
@@ -83,6 +83,7 @@ __device__ __forceinline__ void silu8(float (&f)[8]) {
     } else
 #endif
     {
+      // Newton path: exponent argument clamped to 2^126 so that d = 1 + e stays finite (t < -87: silu(t) = -0 either way)
       asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(fminf(a.x, 126.f)));
       asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(fminf(a.y, 126.f)));
       const float2 d = __fadd2_rn(e, make_float2(1.f, 1.f));
@@ -91,11 +92,39 @@ __device__ __forceinline__ void silu8(float (&f)[8]) {
 #pragma unroll
       for (int it = 0; it < FF_SILU_NR; ++it) r = __fmul2_rn(r, __ffma2_rn(nd, r, two));
     }
-    const float2 o = __fmul2_rn(t, r);
-    f[j] = o.x;
-    f[j + 1] = o.y;
+    f[i] = __fmul2_rn(t, r);
   }
 #endif
+}
+
+__device__ __forceinline__ void silu8(float (&f)[8]) {
+  float2 q[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q[i] = make_float2(f[2 * i], f[2 * i + 1]);
+  silu_pairs(q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = q[i].x;
+    f[2 * i + 1] = q[i].y;
+  }
+}
+
+// y = act(x * sc + sh) of one bf16x8 vector, pairwise: unpack (shift / mask), FFMA2, SiLU on the pairs, pack
+template <bool SILU>
+__device__ __forceinline__ uint4 norm_act8(const uint4& raw, const float2 (&sc)[4], const float2 (&sh)[4]) {
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+  float2 f[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    f[i] = __ffma2_rn(make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u)), sc[i], sh[i]);
+  if (SILU) silu_pairs(f);
+  uint32_t o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 b = __floats2bfloat162_rn(f[i].x, f[i].y);
+    o[i] = *reinterpret_cast<const uint32_t*>(&b);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 // thread-block cluster primitives (PTX; sm_90+): split barrier and a distributed-shared-memory load
@@ -243,8 +272,11 @@ gn_stats_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_
   }
 }
 
+#ifndef FF_GN_APPLY_MINB
+#define FF_GN_APPLY_MINB 1
+#endif
 template <bool SILU>
-__global__ void __launch_bounds__(GN_THREADS)
+__global__ void __launch_bounds__(GN_THREADS, FF_GN_APPLY_MINB)
 gn_apply_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_nc, long long add_ld,
                      const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
                      const float2* __restrict__ partial, uint4* __restrict__ y, int HW, int C, int G, int chunk_px,
@@ -284,7 +316,7 @@ gn_apply_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_
   if (L.r >= L.R) return;
   const int p0 = chunk * chunk_px, p1 = min(HW, p0 + chunk_px);
   for (int v = L.col; v < L.CV; v += L.cols) {
-    float sc[8], sh[8];
+    float2 sc[4], sh[4];                                   // (channel pairs: the loop below is packed FFMA2)
     {
       int g = (8 * v) / cpg, rem = 8 * v - g * cpg;       // one division per vector; the group advances with the channel
 #pragma unroll
@@ -295,8 +327,15 @@ gn_apply_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_
         }
         ++rem;
         const float a = add_nc ? __ldg(add_nc + (size_t)n * add_ld + 8 * v + j) : 0.f;
-        sc[j] = rstd[g] * __bfloat162float(gamma[8 * v + j]);
-        sh[j] = fmaf(a - mean[g], sc[j], __bfloat162float(beta[8 * v + j]));     // y = (x + a - mean) * rstd * gamma + beta
+        const float scj = rstd[g] * __bfloat162float(gamma[8 * v + j]);
+        const float shj = fmaf(a - mean[g], scj, __bfloat162float(beta[8 * v + j]));     // y = (x + a - mean) * rstd * gamma + beta
+        if (j & 1) {
+          sc[j >> 1].y = scj;
+          sh[j >> 1].y = shj;
+        } else {
+          sc[j >> 1].x = scj;
+          sh[j >> 1].x = shj;
+        }
       }
     }
     const size_t off = ((size_t)n * HW + p0 + L.r) * L.CV + v;
@@ -310,14 +349,7 @@ gn_apply_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_
 #pragma unroll
       for (int u = 0; u < GN_MLP; ++u) raw[u] = __ldg(px + u * step);
 #pragma unroll
-      for (int u = 0; u < GN_MLP; ++u) {
-        float f[8];
-        unpack8(raw[u], f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
-        if (SILU) silu8(f);
-        py[u * step] = pack8(f);
-      }
+      for (int u = 0; u < GN_MLP; ++u) py[u * step] = norm_act8<SILU>(raw[u], sc, sh);
     }
     if (p < p1) {                                          // ragged end: one predicated batch
       uint4 raw[GN_MLP];
@@ -325,14 +357,7 @@ gn_apply_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_
       for (int u = 0; u < GN_MLP; ++u) raw[u] = (p + u * L.R < p1) ? __ldg(px + u * step) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
       for (int u = 0; u < GN_MLP; ++u) {
-        if (p + u * L.R < p1) {
-          float f[8];
-          unpack8(raw[u], f);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
-          if (SILU) silu8(f);
-          py[u * step] = pack8(f);
-        }
+        if (p + u * L.R < p1) py[u * step] = norm_act8<SILU>(raw[u], sc, sh);
       }
     }
   }

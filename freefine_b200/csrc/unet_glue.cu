@@ -187,7 +187,11 @@ __device__ __forceinline__ void unpack8_pairs(const uint4& q, float2 (&f)[4]) {
 // (sum(x + a) = sum(x) + k a,  sum((x + a)^2) = sum(x^2) + 2 a sum(x) + k a^2,  k = pixels this thread walked); full batches
 // of GN_MLP loads run without per-load predicates, the ragged end as one predicated batch.  ncu before: 89 executed
 // instructions per vector, issue slots 49 % busy on an HBM-bound kernel.
-__global__ void __launch_bounds__(GN_THREADS, 4)
+// (5 CTAs per SM measured the same, 6 slower: 58.4 / 60.9 vs 58.1 us at 32x320x64x64)
+#ifndef FF_GN_STATS_MINB
+#define FF_GN_STATS_MINB 4
+#endif
+__global__ void __launch_bounds__(GN_THREADS, FF_GN_STATS_MINB)
 gn_stats_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_nc, long long add_ld, float2* __restrict__ partial,
                      int HW, int C, int G, int chunk_px, int n_chunks) {
   extern __shared__ float sm[];                 // [R][2][C] per-row-slot channel sums, then reduced into slot 0
@@ -272,8 +276,9 @@ gn_stats_nhwc_kernel(const uint4* __restrict__ x, const float* __restrict__ add_
   }
 }
 
+// 4 CTAs per SM (64 registers, 24 bytes of spill) beat 3 (78 registers: 84 vs 58 us at 32x320x64x64) and 5 (66 us)
 #ifndef FF_GN_APPLY_MINB
-#define FF_GN_APPLY_MINB 1
+#define FF_GN_APPLY_MINB 4
 #endif
 template <bool SILU>
 __global__ void __launch_bounds__(GN_THREADS, FF_GN_APPLY_MINB)

@@ -43,6 +43,7 @@ SIGNATURES = {
     "ff_last_error": (C.c_char_p, []),
     "ff_attn_masked_kv": (C.c_int, [C.POINTER(FFAttnArgs), C.c_void_p]),
     "ff_attn_v_head_stride": (C.c_int, [C.c_int32]),
+    "ff_attn_plain_smallkv": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 5 + [C.c_float, C.c_int32, C.c_void_p]),
     "ff_debug_set_timeline": (C.c_int, [C.c_void_p]),
     "ff_kv_gather_cast": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
                                     C.c_int32, C.c_int32, C.c_void_p]),

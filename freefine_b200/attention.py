@@ -27,6 +27,8 @@ from __future__ import annotations
 import abc
 import math
 
+import os
+
 import torch
 
 from . import ops, plans
@@ -115,6 +117,9 @@ class Attention_Modulator(AttentionControl):
         # P operand of the P.V contraction: "f16" = V staged as fp16, one fp16 P operand (fast path, ~3e-4 max-abs);
         # "bf16x2" = V stays bf16, P as a hi+lo bf16 pair (2x PV tensor work, ~3e-5 max-abs)
         self.p_operand = "f16"
+        # plain attention over <= 128 keys (text cross-attention, 8 x 8 self-attention) through ff_attn_plain_smallkv;
+        # False (or FF_ATTN_SMALLKV=0) sends those layers through ff_attn_masked_kv like every other layer (A/B switch)
+        self.small_kv_kernel = os.environ.get("FF_ATTN_SMALLKV", "1") != "0"
         self._tables = {}                 # (kind, S) -> (signature, bits, popcount)
         self._plans = {}                  # key -> device plan bytes
 
@@ -231,6 +236,15 @@ class Attention_Modulator(AttentionControl):
         B = query.shape[0]
         if key.shape[0] != B:
             raise ValueError("plain attention needs one K/V stream per query stream")
+        d = query.shape[-1] // self.heads
+        if key.shape[1] <= ops.SMALLKV_MAX_KEYS and d in ops.SMALLKV_HEAD_DIMS and self.p_operand == "f16" and self.small_kv_kernel:
+            # short key sequences (the 77-key text cross-attention, 8 x 8 self-attention): K/V resident in shared memory,
+            # HBM-bound on Q in + O out; the tcgen05 kernel pays ~7 us of pipeline set-up per 128-row tile there
+            dt = query.dtype
+            if dt not in (torch.float32, torch.bfloat16):
+                query, key, value, dt = query.float(), key.float(), value.float(), torch.float32
+            return ops.attn_plain_smallkv(query.to(torch.bfloat16).contiguous(), key.to(torch.bfloat16).contiguous(),
+                                          value.to(torch.bfloat16).contiguous(), self.heads, self.scale, out_dtype=dt)
         plan = self._plan(("plain", B, self.heads), lambda: plans.plain_plan(B, self.heads))
         return self._attend(query, key, value, plan)
 

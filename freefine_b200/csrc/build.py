@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB_DIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIB_DIR, "libfreefine_b200.so")
-SOURCES = ["ff_api.cu", "ddim_step.cu", "mask_pack.cu", "mask_prep.cu", "warp_blend.cu", "cross_blend.cu", "kv_prepare.cu", "unet_glue.cu", "linear_fused.cu", "attn_tcgen05.cu"]
+SOURCES = ["ff_api.cu", "ddim_step.cu", "mask_pack.cu", "mask_prep.cu", "warp_blend.cu", "cross_blend.cu", "kv_prepare.cu", "unet_glue.cu", "linear_fused.cu", "attn_smallkv.cu", "attn_tcgen05.cu"]
 HEADERS = ["ff_common.cuh", "attn_ring.cuh", "attn_t32.cuh", os.path.join("..", "..", "include", "freefine_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr"]

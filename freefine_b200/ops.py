@@ -376,6 +376,29 @@ def attn_masked_kv(q, k, v, plan, heads, scale, bitmasks=None, popcount=None, ou
     return out
 
 
+SMALLKV_MAX_KEYS = 128
+SMALLKV_HEAD_DIMS = (8, 40, 80, 160)
+
+
+def attn_plain_smallkv(q, k, v, heads, scale, out_dtype=None):
+    """softmax(q k^T * scale) v, stream i over K/V stream i, for s_kv <= 128 and head_dim in SMALLKV_HEAD_DIMS: q [B,Sq,C],
+    k / v [B,Skv,C] bf16 (v unstaged).  Returns [B,Sq,C] in out_dtype (default bf16).  See ff_attn_plain_smallkv."""
+    _chk(q, torch.bfloat16, "q", 3)
+    _chk(k, torch.bfloat16, "k", 3)
+    _chk(v, torch.bfloat16, "v", 3)
+    B, Sq, Cc = q.shape
+    if k.shape[0] != B or k.shape[2] != Cc or v.shape != k.shape or Cc % heads:
+        raise ValueError(f"bad shapes q{tuple(q.shape)} k{tuple(k.shape)} v{tuple(v.shape)} heads={heads}")
+    out_dtype = torch.bfloat16 if out_dtype is None else out_dtype
+    out = torch.empty((B, Sq, Cc), dtype=out_dtype, device=q.device)
+    with nvtx_range(f"ff_attn_plain_smallkv S_q={Sq} S_kv={k.shape[1]} d={Cc // heads} streams={B}"):
+        rc = _lib.load().ff_attn_plain_smallkv(_ptr(q), _ptr(k), _ptr(v), _ptr(out), B, heads, Cc // heads, Sq, k.shape[1],
+                                               float(scale), _DT[out_dtype], _stream())
+    _lib.check(rc, "ff_attn_plain_smallkv")
+    _count("ff_attn_plain_smallkv")
+    return out
+
+
 def cross_region_blend(hs, bitmasks, region_ids):
     """hs [4E,S,C] (f32/bf16) in place: c_e <- region ? c_e : u_e, c_r <- u_r  (attention.py:1381-1383)."""
     if hs.dtype not in _DT:

@@ -319,3 +319,71 @@ def test_s9216_head_slices_vs_oracle(dev):
         ref = cg * ref_pass + (1 - cg) * self_pass
         err = float((sl(out, s, h) - ref).abs().max())
         assert err < TOL, (s, h, err)
+
+
+# ---- ff_attn_plain_smallkv: plain attention over <= 128 keys (text cross-attention, 8 x 8 self-attention) -------------------
+def _smallkv(dev, q, k, v, heads, scale, out_dtype=torch.float32):
+    from freefine_b200 import ops
+    out = ops.attn_plain_smallkv(q.to(dev).bfloat16().contiguous(), k.to(dev).bfloat16().contiguous(),
+                                 v.to(dev).bfloat16().contiguous(), heads, scale, out_dtype=out_dtype)
+    torch.cuda.synchronize()
+    return out.float().cpu()
+
+
+def test_smallkv_golden(dev, golden):
+    """The reference's own plain / 77-key cross-attention outputs (tests/golden/attention.npz) through the short-key kernel."""
+    if P_OPERAND != "f16":
+        pytest.skip("ff_attn_plain_smallkv has one operand path (fp16 P.V)")
+    g = golden["attention"]
+    T = lambda k: torch.from_numpy(g[k])
+    sc = 8 ** -0.5
+    assert T("cross/k").shape[1] == 77
+    hs = _smallkv(dev, T("cross/q"), T("cross/k"), T("cross/v"), 8, sc)
+    assert float((hs - _run(dev, T("cross/q"), T("cross/k"), T("cross/v"), plans.plain_plan(4, 8), 8, sc)).abs().max()) < 1e-3
+    from freefine_b200 import ops
+    reg = O.process_mask_before_attention(T("cross/region"), 64).numpy()
+    bits = torch.from_numpy(O.pack_bits(reg).view(np.int32))[None].to(dev)
+    hs = ops.cross_region_blend(hs.to(dev), bits, torch.zeros(1, dtype=torch.int32, device=dev)).cpu()
+    assert float((hs - T("cross/out")).abs().max()) < TOL
+    if T("plain/k").shape[1] <= 128:
+        out = _smallkv(dev, T("plain/q"), T("plain/k"), T("plain/v"), 8, sc)
+        assert float((out - T("plain/out")).abs().max()) < TOL
+
+
+@pytest.mark.parametrize("B,heads,d,s_q,s_kv", [(2, 8, 40, 4096, 77), (2, 8, 80, 1024, 77), (3, 8, 160, 256, 77), (2, 8, 160, 64, 64),
+                                                (1, 2, 40, 200, 77), (1, 2, 80, 70, 128), (2, 2, 160, 17, 1), (1, 3, 40, 333, 81),
+                                                (1, 2, 8, 100, 5)])
+def test_smallkv_vs_oracle(dev, B, heads, d, s_q, s_kv):
+    """Seeded inputs on the bf16 grid against the CPU oracle's plain attention: SD1.5 shapes (64^2 / 32^2 / 16^2 cross-attention,
+    8^2 self-attention), ragged row counts (not multiples of 16 / 64 / 256), 1 / 81 / 128 keys, f32 and bf16 outputs."""
+    if P_OPERAND != "f16":
+        pytest.skip("ff_attn_plain_smallkv has one operand path (fp16 P.V)")
+    g = torch.Generator().manual_seed(1000 * d + s_q + s_kv)
+    C = heads * d
+    q = torch.randn(B, s_q, C, generator=g).bfloat16().float()
+    k = torch.randn(B, s_kv, C, generator=g).bfloat16().float()
+    v = (2.0 * torch.randn(B, s_kv, C, generator=g)).bfloat16().float()
+    sc = d ** -0.5
+    want = O.plain_attention(q, k, v, heads, sc)
+    got = _smallkv(dev, q, k, v, heads, sc)
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) < TOL
+    got16 = _smallkv(dev, q, k, v, heads, sc, out_dtype=torch.bfloat16)
+    assert float((got16 - want).abs().max()) < TOL + 2.0 ** -8 * float(want.abs().max())
+    # peaked rows: one dominant key per query (large logits), the softmax must not overflow or lose the row
+    k2 = k.clone()
+    k2[:, 0] = 30.0 * q[:, 0, :].sign()
+    want2 = O.plain_attention(q, k2, v, heads, sc)
+    got2 = _smallkv(dev, q, k2, v, heads, sc)
+    assert torch.isfinite(got2).all() and float((got2 - want2).abs().max()) < 2 * TOL
+
+
+def test_smallkv_error_paths(dev):
+    from freefine_b200 import ops
+    q = torch.zeros(1, 32, 80, device=dev, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="s_kv"):
+        ops.attn_plain_smallkv(q, torch.zeros(1, 129, 80, device=dev, dtype=torch.bfloat16), torch.zeros(1, 129, 80, device=dev, dtype=torch.bfloat16), 2, 0.1)
+    with pytest.raises(RuntimeError, match="head_dim"):
+        ops.attn_plain_smallkv(q, torch.zeros(1, 8, 80, device=dev, dtype=torch.bfloat16), torch.zeros(1, 8, 80, device=dev, dtype=torch.bfloat16), 5, 0.1)
+    with pytest.raises(ValueError):
+        ops.attn_plain_smallkv(q, torch.zeros(2, 8, 80, device=dev, dtype=torch.bfloat16), torch.zeros(2, 8, 80, device=dev, dtype=torch.bfloat16), 2, 0.1)

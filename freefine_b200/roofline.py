@@ -137,6 +137,15 @@ def hbm_rooflines(dev, peak_gbs: float, with_eager: bool = False):
         r["eager_ms"] = _timeit(lambda: xa * F.gelu(ga2))
     rows.append(r)
     del hg
+    # text cross-attention of a 32-stream call (77 keys): HBM-bound on Q in + O out (K/V stay in shared memory)
+    for (bq, sq, dq) in ((32, 4096, 40), (32, 1024, 80), (32, 256, 160)):
+        qq = torch.randn(bq, sq, 8 * dq, device=dev).bfloat16()
+        kq_ = torch.randn(bq, 77, 8 * dq, device=dev).bfloat16()
+        vq_ = torch.randn(bq, 77, 8 * dq, device=dev).bfloat16()
+        ms = _timeit(lambda: ops.attn_plain_smallkv(qq, kq_, vq_, 8, dq ** -0.5))
+        rows.append(_row("ff_attn_plain_smallkv", 2 * qq.numel() * 2 + 2 * kq_.numel() * 2, ms, peak_gbs,
+                         size=f"{bq} streams x {sq} queries x 77 keys, 8 heads, d={dq}, bf16"))
+        del qq, kq_, vq_
     xl = torch.randn(32, 4096, 320, device=dev).bfloat16()
     ga, be = torch.ones(320, device=dev).bfloat16(), torch.zeros(320, device=dev).bfloat16()
     ms = _timeit(lambda: ops.layer_norm(xl, ga, be, 1e-5))

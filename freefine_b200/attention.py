@@ -117,7 +117,7 @@ class Attention_Modulator(AttentionControl):
         # P operand of the P.V contraction: "f16" = V staged as fp16, one fp16 P operand (fast path, ~3e-4 max-abs);
         # "bf16x2" = V stays bf16, P as a hi+lo bf16 pair (2x PV tensor work, ~3e-5 max-abs)
         self.p_operand = "f16"
-        # plain attention over <= 128 keys (text cross-attention, 8 x 8 self-attention) through ff_attn_plain_smallkv;
+        # plain attention over <= 256 keys (text cross-attention, 8 x 8 / 16 x 16 self-attention) through ff_attn_plain_smallkv;
         # False (or FF_ATTN_SMALLKV=0) sends those layers through ff_attn_masked_kv like every other layer (A/B switch)
         self.small_kv_kernel = os.environ.get("FF_ATTN_SMALLKV", "1") != "0"
         self._tables = {}                 # (kind, S) -> (signature, bits, popcount)
@@ -237,8 +237,9 @@ class Attention_Modulator(AttentionControl):
         if key.shape[0] != B:
             raise ValueError("plain attention needs one K/V stream per query stream")
         d = query.shape[-1] // self.heads
-        if key.shape[1] <= ops.SMALLKV_MAX_KEYS and d in ops.SMALLKV_HEAD_DIMS and self.p_operand == "f16" and self.small_kv_kernel:
-            # short key sequences (the 77-key text cross-attention, 8 x 8 self-attention): K/V resident in shared memory,
+        if (key.shape[1] <= (128 if d == 8 else ops.SMALLKV_MAX_KEYS) and d in ops.SMALLKV_HEAD_DIMS and self.p_operand == "f16"
+                and self.small_kv_kernel):
+            # short key sequences (the 77-key text cross-attention, 8 x 8 / 16 x 16 self-attention): K/V resident in shared memory,
             # HBM-bound on Q in + O out; the tcgen05 kernel pays ~7 us of pipeline set-up per 128-row tile there
             dt = query.dtype
             if dt not in (torch.float32, torch.bfloat16):

@@ -69,9 +69,9 @@ struct SkCfg {
   static constexpr int DV = D / 8;                 // 16-byte vectors per row / n8 tiles of O
 };
 
-// shared memory: K [KT16*16][LDS] bf16 | V [KT16*16][LDS] fp16 | Q [2][64][LDS] bf16
-template <int D, int KT16>
-constexpr size_t sk_smem_bytes() { return (size_t)(2 * KT16 * 16 + 2 * SK_ROWS) * SkCfg<D>::LDS * 2; }
+// shared memory: K [NBLK*KT16*16][LDS] bf16 | V [NBLK*KT16*16][LDS] fp16 | Q [2][64][LDS] bf16
+template <int D, int KT16, int NBLK>
+constexpr size_t sk_smem_bytes() { return (size_t)(2 * KT16 * 16 * NBLK + 2 * SK_ROWS) * SkCfg<D>::LDS * 2; }
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
@@ -81,19 +81,21 @@ constexpr int sk_pow2_at_least(int v) { return v <= 1 ? 1 : (v <= 2 ? 2 : (v <= 
 
 // All shared-memory addressing is "per-lane base computed once + compile-time offset" (the first version recomputed
 // row * LDS + column per ldmatrix: 121 IMAD per 16-row step, ncu), the key-padding mask is applied to the boundary tile only.
-template <int D, int KT16, bool OUT_F32>
-__global__ void __launch_bounds__(SK_THREADS, D <= 40 ? 6 : (D <= 80 ? 4 : 2))
+// NBLK > 1: key sequences of up to NBLK * 128 keys (the plain 16 x 16 self-attention: 256 keys) as NBLK blocks of KT16 * 16
+// keys under one online softmax (running maximum / sum, O rescaled between the blocks); all K / V still resident.
+template <int D, int KT16, int NBLK, bool OUT_F32>
+__global__ void __launch_bounds__(SK_THREADS, NBLK > 1 ? (D <= 80 ? 2 : 1) : (D <= 40 ? 6 : (D <= 80 ? 4 : 2)))
 attn_smallkv_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
                     void* __restrict__ out, int s_q, int s_kv, int heads, float scale_log2e) {
   using Cfg = SkCfg<D>;
-  constexpr int LDS = Cfg::LDS, DP = Cfg::DP, DV = Cfg::DV, KP = KT16 * 16, NT = KT16 * 2;
+  constexpr int LDS = Cfg::LDS, DP = Cfg::DP, DV = Cfg::DV, KP = KT16 * 16, NT = KT16 * 2, KPT = KP * NBLK;
   constexpr int TPR = sk_pow2_at_least(DP / 8);          // threads side by side over the 16-byte vectors of a row (loads)
   constexpr int TPW = sk_pow2_at_least(DV);              // ... of an output row (stores, per warp)
   constexpr uint32_t SLOT = SK_ROWS * LDS * 2;           // bytes of one Q slot
   extern __shared__ __align__(16) unsigned char sk_smem[];
   __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(sk_smem);
-  __half* Vs = reinterpret_cast<__half*>(Ks + KP * LDS);
-  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(Vs + KP * LDS);
+  __half* Vs = reinterpret_cast<__half*>(Ks + KPT * LDS);
+  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(Vs + KPT * LDS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int head = blockIdx.y, stream = blockIdx.z;
   const int C = heads * D;
@@ -119,27 +121,35 @@ attn_smallkv_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
       src += (size_t)(SK_THREADS / TPR) * C;
     }
   };
+  // K and V of this (stream, head): every 16-byte vector goes out as a cp.async at once (rows >= s_kv and the K padding
+  // columns zero-filled), together with the first Q tile -- ONE exposed memory latency for the whole prologue (the first
+  // version walked the rows with load -> convert -> store per trip: 64 dependent trips for 256 keys x d=160).  V lands as
+  // bf16 and is converted to fp16 (saturating) in place by the thread that copied it, before the CTA-wide barrier.
   load_q(0);
-  cp_async_commit();
-  // K (bf16 copy) and V (bf16 -> fp16, saturating) of this (stream, head); rows >= s_kv and K columns >= D are zeros
   if (ld_on) {
-    for (int r = ld_r; r < KP; r += SK_THREADS / TPR) {
-      uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = make_uint4(0u, 0u, 0u, 0u);
-      if (r < s_kv && ld_data) {
-        kv = __ldg(reinterpret_cast<const uint4*>(kg + (size_t)r * C + 8 * ld_c));
-        const uint4 vb = __ldg(reinterpret_cast<const uint4*>(vg + (size_t)r * C + 8 * ld_c));
-        const uint32_t w[4] = {vb.x, vb.y, vb.z, vb.w};
-        uint32_t o[4];
+    const uint32_t ks_u32 = smem_u32(Ks) + (ld_r * LDS + 8 * ld_c) * 2, vs_u32 = smem_u32(Vs) + (ld_r * LDS + 8 * ld_c) * 2;
+    for (int r = ld_r; r < KPT; r += SK_THREADS / TPR) {
+      const bool ok = ld_data && r < s_kv;
+      const uint32_t off = (uint32_t)(r - ld_r) * LDS * 2;
+      cp_async16(ks_u32 + off, ok ? static_cast<const void*>(kg + (size_t)r * C + 8 * ld_c) : static_cast<const void*>(kg), ok);
+      cp_async16(vs_u32 + off, ok ? static_cast<const void*>(vg + (size_t)r * C + 8 * ld_c) : static_cast<const void*>(vg), ok);
+    }
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  if (ld_data) {
+    for (int r = ld_r; r < min(KPT, s_kv); r += SK_THREADS / TPR) {
+      uint4* pv = reinterpret_cast<uint4*>(Vs + r * LDS + 8 * ld_c);
+      const uint4 vb = *pv;
+      const uint32_t w[4] = {vb.x, vb.y, vb.z, vb.w};
+      uint32_t o[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float lo = fminf(fmaxf(__uint_as_float(w[j] << 16), -65504.f), 65504.f);
-          const float hi = fminf(fmaxf(__uint_as_float(w[j] & 0xffff0000u), -65504.f), 65504.f);
-          o[j] = pack_f16(lo, hi);
-        }
-        vv = make_uint4(o[0], o[1], o[2], o[3]);
+      for (int j = 0; j < 4; ++j) {
+        const float lo = fminf(fmaxf(__uint_as_float(w[j] << 16), -65504.f), 65504.f);
+        const float hi = fminf(fmaxf(__uint_as_float(w[j] & 0xffff0000u), -65504.f), 65504.f);
+        o[j] = pack_f16(lo, hi);
       }
-      *reinterpret_cast<uint4*>(Ks + r * LDS + 8 * ld_c) = kv;
-      *reinterpret_cast<uint4*>(Vs + r * LDS + 8 * ld_c) = vv;
+      *pv = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
   // per-lane ldmatrix bases (bytes)
@@ -160,74 +170,99 @@ attn_smallkv_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
     __syncthreads();                 // ... for every thread's copies; also covers the K / V stores before the first step
     const uint32_t slot = qs_u32 + (st & 1) * SLOT;
 
-    // ---- S = Q K^T: NT n8 tiles of 16 x 8 scores, fp32
-    float s[NT][4];
+    float o[DV][4];
 #pragma unroll
-    for (int t = 0; t < NT; ++t) s[t][0] = s[t][1] = s[t][2] = s[t][3] = 0.f;
+    for (int n = 0; n < DV; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+    float mr0 = -INFINITY, mr1 = -INFINITY, l0 = 0.f, l1 = 0.f;      // running row maxima; per-thread partial row sums
+#pragma unroll 1                     // (NBLK = 2 unrolled let ptxas interleave the two blocks: 255 registers)
+    for (int blk = 0; blk < NBLK; ++blk) {
+      constexpr uint32_t BLK = KP * LDS * 2;                          // bytes of one key block in Ks / Vs
+      // ---- S = Q K^T: NT n8 tiles of 16 x 8 scores, fp32
+      float s[NT][4];
 #pragma unroll
-    for (int kb = 0; kb < DP / 16; ++kb) {
-      uint32_t a[4];
-      ldsm_x4(slot + q_lane + kb * 32, a);
+      for (int t = 0; t < NT; ++t) s[t][0] = s[t][1] = s[t][2] = s[t][3] = 0.f;
 #pragma unroll
-      for (int t = 0; t < NT; t += 2) {
-        uint32_t b0, b1, b2, b3;   // keys 8t..8t+7 (k 0-7, k 8-15), keys 8t+8..8t+15 (k 0-7, k 8-15)
-        ldsm_x4(k_base + (uint32_t)((t * 8 * LDS + kb * 16) * 2), b0, b1, b2, b3);
-        mma_bf16(s[t], a, b0, b1);
-        mma_bf16(s[t + 1], a, b2, b3);
+      for (int kb = 0; kb < DP / 16; ++kb) {
+        uint32_t a[4];
+        ldsm_x4(slot + q_lane + kb * 32, a);
+#pragma unroll
+        for (int t = 0; t < NT; t += 2) {
+          uint32_t b0, b1, b2, b3;   // keys 8t..8t+7 (k 0-7, k 8-15), keys 8t+8..8t+15 (k 0-7, k 8-15)
+          ldsm_x4(k_base + blk * BLK + (uint32_t)((t * 8 * LDS + kb * 16) * 2), b0, b1, b2, b3);
+          mma_bf16(s[t], a, b0, b1);
+          mma_bf16(s[t + 1], a, b2, b3);
+        }
+      }
+      // ---- softmax over the block (rows lane/4 and lane/4 + 8; a row lives in the 4 lanes of a quad)
+      float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        if (blk * KP + t * 8 + 8 > s_kv) {        // (warp-uniform) tile with padding keys
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (blk * KP + t * 8 + kq + (e & 1) >= s_kv) s[t][e] = -INFINITY;
+        }
+        m0 = fmaxf(m0, fmaxf(s[t][0], s[t][1]));
+        m1 = fmaxf(m1, fmaxf(s[t][2], s[t][3]));
+      }
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+      if (NBLK > 1 && blk > 0) {
+        // online softmax: every block holds at least one real key (the host picks NBLK = ceil(s_kv / 128)), so the maxima
+        // are finite from the first block on
+        const float n0 = fmaxf(mr0, m0), n1 = fmaxf(mr1, m1);
+        const float al0 = ex2((mr0 - n0) * scale_log2e), al1 = ex2((mr1 - n1) * scale_log2e);
+        l0 *= al0;
+        l1 *= al1;
+#pragma unroll
+        for (int n = 0; n < DV; ++n) {
+          o[n][0] *= al0;
+          o[n][1] *= al0;
+          o[n][2] *= al1;
+          o[n][3] *= al1;
+        }
+        mr0 = n0;
+        mr1 = n1;
+      } else {
+        mr0 = m0;
+        mr1 = m1;
+      }
+      const float nb0 = -mr0 * scale_log2e, nb1 = -mr1 * scale_log2e;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        s[t][0] = ex2(fmaf(s[t][0], scale_log2e, nb0));
+        s[t][1] = ex2(fmaf(s[t][1], scale_log2e, nb0));
+        s[t][2] = ex2(fmaf(s[t][2], scale_log2e, nb1));
+        s[t][3] = ex2(fmaf(s[t][3], scale_log2e, nb1));
+        l0 += s[t][0] + s[t][1];
+        l1 += s[t][2] + s[t][3];
+      }
+      // ---- O += P V: P straight from the score registers (two n8 tiles = one k16 A fragment), fp16
+#pragma unroll
+      for (int j = 0; j < KT16; ++j) {
+        const uint32_t a[4] = {pack_f16(s[2 * j][0], s[2 * j][1]), pack_f16(s[2 * j][2], s[2 * j][3]),
+                               pack_f16(s[2 * j + 1][0], s[2 * j + 1][1]), pack_f16(s[2 * j + 1][2], s[2 * j + 1][3])};
+#pragma unroll
+        for (int n = 0; n + 1 < DV; n += 2) {
+          uint32_t b[4];           // channels 8n..8n+7 (keys 0-7, 8-15 of the block), channels 8n+8..8n+15 (same)
+          ldsm_x4_t(v_base + blk * BLK + (uint32_t)((j * 16 * LDS + n * 8) * 2), b);
+          mma_f16(o[n], a, b[0], b[1]);
+          mma_f16(o[n + 1], a, b[2], b[3]);
+        }
+        if (DV & 1) {
+          uint32_t b[2];
+          ldsm_x2_t(v_base1 + blk * BLK + (uint32_t)(j * 16 * LDS * 2), b);
+          mma_f16(o[DV - 1], a, b[0], b[1]);
+        }
       }
     }
-    // ---- softmax over the whole row (rows lane/4 and lane/4 + 8; a row lives in the 4 lanes of a quad)
-    float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-    for (int t = 0; t < NT; ++t) {
-      if (t * 8 + 8 > s_kv) {        // (warp-uniform) tile with padding keys
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (t * 8 + kq + (e & 1) >= s_kv) s[t][e] = -INFINITY;
-      }
-      m0 = fmaxf(m0, fmaxf(s[t][0], s[t][1]));
-      m1 = fmaxf(m1, fmaxf(s[t][2], s[t][3]));
-    }
-    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
-    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
-    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-    const float nb0 = -m0 * scale_log2e, nb1 = -m1 * scale_log2e;
-    float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-    for (int t = 0; t < NT; ++t) {
-      s[t][0] = ex2(fmaf(s[t][0], scale_log2e, nb0));
-      s[t][1] = ex2(fmaf(s[t][1], scale_log2e, nb0));
-      s[t][2] = ex2(fmaf(s[t][2], scale_log2e, nb1));
-      s[t][3] = ex2(fmaf(s[t][3], scale_log2e, nb1));
-      l0 += s[t][0] + s[t][1];
-      l1 += s[t][2] + s[t][3];
-    }
+    // row sums: the partials of the four lanes of a quad (their rescale factors were identical)
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
     l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    // ---- O = P V: P straight from the score registers (two n8 tiles = one k16 A fragment), fp16
-    float o[DV][4];
-#pragma unroll
-    for (int n = 0; n < DV; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
-#pragma unroll
-    for (int j = 0; j < KT16; ++j) {
-      const uint32_t a[4] = {pack_f16(s[2 * j][0], s[2 * j][1]), pack_f16(s[2 * j][2], s[2 * j][3]),
-                             pack_f16(s[2 * j + 1][0], s[2 * j + 1][1]), pack_f16(s[2 * j + 1][2], s[2 * j + 1][3])};
-#pragma unroll
-      for (int n = 0; n + 1 < DV; n += 2) {
-        uint32_t b[4];           // channels 8n..8n+7 (keys 0-7, 8-15 of the block), channels 8n+8..8n+15 (same)
-        ldsm_x4_t(v_base + (uint32_t)((j * 16 * LDS + n * 8) * 2), b);
-        mma_f16(o[n], a, b[0], b[1]);
-        mma_f16(o[n + 1], a, b[2], b[3]);
-      }
-      if (DV & 1) {
-        uint32_t b[2];
-        ldsm_x2_t(v_base1 + (uint32_t)(j * 16 * LDS * 2), b);
-        mma_f16(o[DV - 1], a, b[0], b[1]);
-      }
-    }
     const float r0 = 1.f / l0, r1 = 1.f / l1;
     const int grow = row0 + st * SK_ROWS + warp * 16;      // first global row of my warp
     if (OUT_F32) {
@@ -263,12 +298,12 @@ attn_smallkv_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
   cp_async_wait<0>();
 }
 
-template <int D, int KT16>
+template <int D, int KT16, int NBLK>
 int sk_launch(const void* q, const void* k, const void* v, void* out, int n_streams, int heads, int s_q, int s_kv, float scale,
               int out_dtype, cudaStream_t st) {
-  constexpr size_t smem = sk_smem_bytes<D, KT16>();
-  auto kf = attn_smallkv_kernel<D, KT16, true>;
-  auto kb = attn_smallkv_kernel<D, KT16, false>;
+  constexpr size_t smem = sk_smem_bytes<D, KT16, NBLK>();
+  auto kf = attn_smallkv_kernel<D, KT16, NBLK, true>;
+  auto kb = attn_smallkv_kernel<D, KT16, NBLK, false>;
   if (smem > 48 * 1024) {
     static bool configured[64] = {};
     int dev = 0;
@@ -299,20 +334,26 @@ extern "C" int ff_attn_plain_smallkv(const void* q, const void* k, const void* v
   FF_REQUIRE(q && k && v && out, "ff_attn_plain_smallkv: null pointer");
   FF_REQUIRE(n_streams > 0 && heads > 0 && s_q > 0 && s_kv > 0, "ff_attn_plain_smallkv: bad shape");
   FF_REQUIRE(n_streams <= 65535 && heads <= 65535, "ff_attn_plain_smallkv: n_streams / heads must be <= 65535");
-  FF_REQUIRE(s_kv <= 128, "ff_attn_plain_smallkv: s_kv=%d must be <= 128 (longer key sequences: ff_attn_masked_kv)", s_kv);
+  FF_REQUIRE(s_kv <= (head_dim == 8 ? 128 : 256),
+             "ff_attn_plain_smallkv: s_kv=%d must be <= 256 (128 for head_dim 8); longer key sequences: ff_attn_masked_kv", s_kv);
   FF_REQUIRE(head_dim == 8 || head_dim == 40 || head_dim == 80 || head_dim == 160,
              "ff_attn_plain_smallkv: head_dim=%d must be 40, 80, 160 (SD1.5) or 8 (the reference's golden vectors)", head_dim);
   FF_REQUIRE(out_dtype == FF_DT_BF16 || out_dtype == FF_DT_F32, "ff_attn_plain_smallkv: out_dtype must be bf16 or f32");
   FF_REQUIRE(scale > 0.f, "ff_attn_plain_smallkv: scale must be positive");
   FF_REQUIRE(ff::aligned16(q) && ff::aligned16(k) && ff::aligned16(v) && ff::aligned16(out), "ff_attn_plain_smallkv: pointers must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool small = s_kv <= 80;
-#define FF_SK(Dv)                                                                                              \
-  return small ? sk_launch<Dv, 5>(q, k, v, out, n_streams, heads, s_q, s_kv, scale, out_dtype, st)               \
-               : sk_launch<Dv, 8>(q, k, v, out, n_streams, heads, s_q, s_kv, scale, out_dtype, st)
-  if (head_dim == 8) { FF_SK(8); }
-  if (head_dim == 40) { FF_SK(40); }
-  if (head_dim == 80) { FF_SK(80); }
+#define FF_SK(Dv)                                                                                                 \
+  do {                                                                                                            \
+    if (s_kv <= 80) return sk_launch<Dv, 5, 1>(q, k, v, out, n_streams, heads, s_q, s_kv, scale, out_dtype, st);  \
+    if (s_kv <= 128) return sk_launch<Dv, 8, 1>(q, k, v, out, n_streams, heads, s_q, s_kv, scale, out_dtype, st); \
+    return sk_launch<Dv, 8, 2>(q, k, v, out, n_streams, heads, s_q, s_kv, scale, out_dtype, st);                  \
+  } while (0)
+  if (head_dim == 8) {
+    if (s_kv <= 80) return sk_launch<8, 5, 1>(q, k, v, out, n_streams, heads, s_q, s_kv, scale, out_dtype, st);
+    return sk_launch<8, 8, 1>(q, k, v, out, n_streams, heads, s_q, s_kv, scale, out_dtype, st);
+  }
+  if (head_dim == 40) FF_SK(40);
+  if (head_dim == 80) FF_SK(80);
   FF_SK(160);
 #undef FF_SK
 }

@@ -376,12 +376,12 @@ def attn_masked_kv(q, k, v, plan, heads, scale, bitmasks=None, popcount=None, ou
     return out
 
 
-SMALLKV_MAX_KEYS = 128
+SMALLKV_MAX_KEYS = 256      # (128 for head_dim 8)
 SMALLKV_HEAD_DIMS = (8, 40, 80, 160)
 
 
 def attn_plain_smallkv(q, k, v, heads, scale, out_dtype=None):
-    """softmax(q k^T * scale) v, stream i over K/V stream i, for s_kv <= 128 and head_dim in SMALLKV_HEAD_DIMS: q [B,Sq,C],
+    """softmax(q k^T * scale) v, stream i over K/V stream i, for s_kv <= 256 and head_dim in SMALLKV_HEAD_DIMS: q [B,Sq,C],
     k / v [B,Skv,C] bf16 (v unstaged).  Returns [B,Sq,C] in out_dtype (default bf16).  See ff_attn_plain_smallkv."""
     _chk(q, torch.bfloat16, "q", 3)
     _chk(k, torch.bfloat16, "k", 3)

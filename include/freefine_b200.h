@@ -115,13 +115,13 @@ int ff_attn_masked_kv(const FFAttnArgs* h_args, void* stream);
 
 /* Plain attention out = softmax(q k^T * scale) v for SHORT key sequences: the plain branch of ca_forward
  * (src/utils/attention.py:395-404) as it runs for the text cross-attention of every transformer block (77 keys) and the
- * plain 8 x 8 self-attention (64 keys).  q [n_streams, s_q, heads*head_dim], k / v [n_streams, s_kv, heads*head_dim] bf16
- * (the un-split projections, stream i attends to K/V stream i; v is read as is -- no ff_kv_gather_cast staging),
- * out [n_streams, s_q, heads*head_dim] bf16 or f32.  s_kv <= 128, head_dim in {40, 80, 160} (and 8: the reference's golden
- * vectors), scale > 0.  K and V of a
- * (stream, head) stay in shared memory while Q streams through: the launch is HBM-bound on Q in + O out, where the tcgen05
- * kernel below pays ~7 us of per-CTA pipeline set-up per 128-row tile (csrc/attn_smallkv.cu).  Numerics as
- * ff_attn_masked_kv with v_dtype = FF_DT_F16 (P and V fp16 tensor-core operands, |v| >= 65504 saturates).               */
+ * plain 8 x 8 / 16 x 16 self-attention (64 / 256 keys).  q [n_streams, s_q, heads*head_dim], k / v [n_streams, s_kv,
+ * heads*head_dim] bf16 (the un-split projections, stream i attends to K/V stream i; v is read as is -- no
+ * ff_kv_gather_cast staging), out [n_streams, s_q, heads*head_dim] bf16 or f32.  s_kv <= 256, head_dim in {40, 80, 160}
+ * (and 8 with s_kv <= 128: the reference's golden vectors), scale > 0.  K and V of a (stream, head) stay in shared memory
+ * while Q streams through: the launch is bound by Q in + O out, where the tcgen05 kernel below pays ~7 us of per-CTA
+ * pipeline set-up per 128-row tile (csrc/attn_smallkv.cu).  Numerics as ff_attn_masked_kv with v_dtype = FF_DT_F16 (P and V
+ * fp16 tensor-core operands, |v| >= 65504 saturates).                                                                  */
 int ff_attn_plain_smallkv(const void* q, const void* k, const void* v, void* out, int32_t n_streams, int32_t heads,
                           int32_t head_dim, int32_t s_q, int32_t s_kv, float scale, int32_t out_dtype, void* stream);
 

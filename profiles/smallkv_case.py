@@ -26,7 +26,7 @@ def timed(fn):
 
 
 for (B, s_q, s_kv, d) in ((32, 4096, 77, 40), (16, 4096, 77, 40), (32, 1024, 77, 80), (16, 1024, 77, 80), (32, 256, 77, 160),
-                          (32, 64, 77, 160), (16, 64, 64, 160), (16, 9216, 77, 40)):
+                          (32, 64, 77, 160), (16, 64, 64, 160), (16, 9216, 77, 40), (32, 256, 256, 160), (16, 256, 256, 160)):
     heads = 8
     C = heads * d
     q = torch.randn(B, s_q, C, device=dev).bfloat16()

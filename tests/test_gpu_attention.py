@@ -352,10 +352,12 @@ def test_smallkv_golden(dev, golden):
 
 @pytest.mark.parametrize("B,heads,d,s_q,s_kv", [(2, 8, 40, 4096, 77), (2, 8, 80, 1024, 77), (3, 8, 160, 256, 77), (2, 8, 160, 64, 64),
                                                 (1, 2, 40, 200, 77), (1, 2, 80, 70, 128), (2, 2, 160, 17, 1), (1, 3, 40, 333, 81),
-                                                (1, 2, 8, 100, 5)])
+                                                (1, 2, 8, 100, 5),
+                                                # two key blocks under one online softmax: the plain 16 x 16 self-attention (256 keys), ragged 129 / 200
+                                                (2, 8, 160, 256, 256), (1, 2, 40, 100, 200), (1, 2, 80, 130, 129), (1, 2, 160, 77, 255)])
 def test_smallkv_vs_oracle(dev, B, heads, d, s_q, s_kv):
     """Seeded inputs on the bf16 grid against the CPU oracle's plain attention: SD1.5 shapes (64^2 / 32^2 / 16^2 cross-attention,
-    8^2 self-attention), ragged row counts (not multiples of 16 / 64 / 256), 1 / 81 / 128 keys, f32 and bf16 outputs."""
+    8^2 / 16^2 self-attention), ragged row counts (not multiples of 16 / 64 / 256), 1 / 81 / 128 / 129 / 256 keys, f32 and bf16 outputs."""
     if P_OPERAND != "f16":
         pytest.skip("ff_attn_plain_smallkv has one operand path (fp16 P.V)")
     g = torch.Generator().manual_seed(1000 * d + s_q + s_kv)
@@ -382,7 +384,7 @@ def test_smallkv_error_paths(dev):
     from freefine_b200 import ops
     q = torch.zeros(1, 32, 80, device=dev, dtype=torch.bfloat16)
     with pytest.raises(RuntimeError, match="s_kv"):
-        ops.attn_plain_smallkv(q, torch.zeros(1, 129, 80, device=dev, dtype=torch.bfloat16), torch.zeros(1, 129, 80, device=dev, dtype=torch.bfloat16), 2, 0.1)
+        ops.attn_plain_smallkv(q, torch.zeros(1, 257, 80, device=dev, dtype=torch.bfloat16), torch.zeros(1, 257, 80, device=dev, dtype=torch.bfloat16), 2, 0.1)
     with pytest.raises(RuntimeError, match="head_dim"):
         ops.attn_plain_smallkv(q, torch.zeros(1, 8, 80, device=dev, dtype=torch.bfloat16), torch.zeros(1, 8, 80, device=dev, dtype=torch.bfloat16), 5, 0.1)
     with pytest.raises(ValueError):

@@ -82,9 +82,10 @@ ops.upsample2x_nhwc(xu)
 ops.concat_nhwc(xu, torch.randn(2, 24, 5, 7, device=dev).bfloat16().contiguous(memory_format=torch.channels_last))
 ops.linear_bias_residual(torch.randn(33, 64, device=dev).bfloat16(), torch.randn(40, 64, device=dev).bfloat16(),
                          torch.randn(40, device=dev).bfloat16(), torch.randn(33, 40, device=dev).bfloat16())
-# round 2 (third session): short-key plain attention (ragged rows, 77 / 128 / 3 keys, every head width, both output types)
+# round 2 (third session): short-key plain attention (ragged rows, 77 / 128 / 3 keys, two key blocks: 200 / 256 keys, every head
+# width, both output types)
 for (b_, hd_, d_, sq_, sk_, dt_) in ((2, 2, 40, 300, 77, torch.bfloat16), (1, 3, 80, 70, 128, torch.float32), (2, 2, 160, 17, 3, torch.bfloat16),
-                                     (1, 2, 8, 33, 77, torch.float32)):
+                                     (1, 2, 8, 33, 77, torch.float32), (1, 2, 160, 40, 200, torch.bfloat16), (1, 2, 40, 70, 256, torch.float32)):
     ops.attn_plain_smallkv(torch.randn(b_, sq_, hd_ * d_, device=dev).bfloat16(), torch.randn(b_, sk_, hd_ * d_, device=dev).bfloat16(),
                            torch.randn(b_, sk_, hd_ * d_, device=dev).bfloat16(), hd_, d_ ** -0.5, out_dtype=dt_)
 torch.cuda.synchronize()

@@ -20,7 +20,8 @@ def launches():
         name = re.sub(r"\(.*", "", r[ki]).replace("void ", "").replace("<unnamed>::", "")
         name = re.sub(r"(attn_masked_kv_kernel<[^>]*>).*", r"\1", name)
         name = re.sub(r"(attn_ring_kernel<[^>]*>).*", r"\1", name)
-        name = name if "attn_masked" in name or "attn_ring" in name or "warp_affine" in name else re.sub(r"<.*", "", name)
+        name = re.sub(r"(attn_smallkv_kernel<[^>]*>).*", r"\1", name)
+        name = name if "attn_masked" in name or "attn_ring" in name or "attn_smallkv" in name or "warp_affine" in name else re.sub(r"<.*", "", name)
         name = "at::layer_norm (eager)" if name.startswith("at::") and "layer_norm" in name else name
         tot[name][0] += v
         tot[name][1] += 1
@@ -33,12 +34,13 @@ def launches():
              "# total %.1f ms over %d launches" % (total, n)]
     for name, (ms, c) in sorted(tot.items(), key=lambda kv: -kv[1][0])[:24]:
         lines.append("%9.3f ms %5.1f%%  x%4d  %s" % (ms, 100 * ms / total, c, name[:90]))
-    ours = {k: (round(v[0], 3), v[1]) for k, v in tot.items() if any(s in k for s in ("attn_masked", "attn_ring", "gn_fused", "warp_affine", "ddim_", "mask_downsample", "cross_region", "kv_gather", "gn_stats", "gn_apply",
+    ours = {k: (round(v[0], 3), v[1]) for k, v in tot.items() if any(s in k for s in ("attn_masked", "attn_ring", "attn_smallkv", "gn_fused", "warp_affine", "ddim_", "mask_downsample", "cross_region", "kv_gather", "gn_stats", "gn_apply",
                                                                                       "geglu_kernel", "layer_norm_kernel", "layer_norm5_kernel", "bias_residual", "gn_small", "mask_prep",
                                                                                       "dilate_kernel", "upsample2x_nhwc", "concat_nhwc"))}
     lines.append("# our kernels (ms, launches): %s" % ours)
-    lines.append("# share of our kernels: %.1f%%   share of all ff_attn_masked_kv launches: %.1f%%" % (
-        100 * sum(v[0] for v in ours.values()) / total, 100 * sum(v[0] for k, v in ours.items() if "attn_masked" in k or "attn_ring" in k) / total))
+    lines.append("# share of our kernels: %.1f%%   share of all ff_attn_masked_kv launches: %.1f%%   ff_attn_plain_smallkv launches: %.1f%%" % (
+        100 * sum(v[0] for v in ours.values()) / total, 100 * sum(v[0] for k, v in ours.items() if "attn_masked" in k or "attn_ring" in k) / total,
+        100 * sum(v[0] for k, v in ours.items() if "attn_smallkv" in k) / total))
     open(os.path.join(OUT, TAG + "_launches_summary.txt"), "w").write("\n".join(lines) + "\n")
     os.replace(PRE + "launches_bench.csv", os.path.join(OUT, TAG + "_launches_bench.csv")) if False else None
     print("\n".join(lines[:14]))

@@ -45,6 +45,17 @@ __device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], u
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// first product of an accumulator: C = 0 comes from RZ, the accumulator registers need no zeroing moves (60 per 16-row step)
+__device__ __forceinline__ void mma_bf16_z(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+               : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
+}
+__device__ __forceinline__ void mma_f16_z(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+               : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
   const int n = valid ? 16 : 0;      // src-size 0: the 16 bytes are zero-filled
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
@@ -171,16 +182,16 @@ attn_smallkv_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
     const uint32_t slot = qs_u32 + (st & 1) * SLOT;
 
     float o[DV][4];
+    if (NBLK > 1) {                  // (one key block: the first P V product writes the accumulators)
 #pragma unroll
-    for (int n = 0; n < DV; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+      for (int n = 0; n < DV; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+    }
     float mr0 = -INFINITY, mr1 = -INFINITY, l0 = 0.f, l1 = 0.f;      // running row maxima; per-thread partial row sums
 #pragma unroll 1                     // (NBLK = 2 unrolled let ptxas interleave the two blocks: 255 registers)
     for (int blk = 0; blk < NBLK; ++blk) {
       constexpr uint32_t BLK = KP * LDS * 2;                          // bytes of one key block in Ks / Vs
       // ---- S = Q K^T: NT n8 tiles of 16 x 8 scores, fp32
       float s[NT][4];
-#pragma unroll
-      for (int t = 0; t < NT; ++t) s[t][0] = s[t][1] = s[t][2] = s[t][3] = 0.f;
 #pragma unroll
       for (int kb = 0; kb < DP / 16; ++kb) {
         uint32_t a[4];
@@ -189,8 +200,13 @@ attn_smallkv_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
         for (int t = 0; t < NT; t += 2) {
           uint32_t b0, b1, b2, b3;   // keys 8t..8t+7 (k 0-7, k 8-15), keys 8t+8..8t+15 (k 0-7, k 8-15)
           ldsm_x4(k_base + blk * BLK + (uint32_t)((t * 8 * LDS + kb * 16) * 2), b0, b1, b2, b3);
-          mma_bf16(s[t], a, b0, b1);
-          mma_bf16(s[t + 1], a, b2, b3);
+          if (kb == 0) {
+            mma_bf16_z(s[t], a, b0, b1);
+            mma_bf16_z(s[t + 1], a, b2, b3);
+          } else {
+            mma_bf16(s[t], a, b0, b1);
+            mma_bf16(s[t + 1], a, b2, b3);
+          }
         }
       }
       // ---- softmax over the block (rows lane/4 and lane/4 + 8; a row lives in the 4 lanes of a quad)
@@ -248,13 +264,19 @@ attn_smallkv_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
         for (int n = 0; n + 1 < DV; n += 2) {
           uint32_t b[4];           // channels 8n..8n+7 (keys 0-7, 8-15 of the block), channels 8n+8..8n+15 (same)
           ldsm_x4_t(v_base + blk * BLK + (uint32_t)((j * 16 * LDS + n * 8) * 2), b);
-          mma_f16(o[n], a, b[0], b[1]);
-          mma_f16(o[n + 1], a, b[2], b[3]);
+          if (NBLK == 1 && j == 0) {
+            mma_f16_z(o[n], a, b[0], b[1]);
+            mma_f16_z(o[n + 1], a, b[2], b[3]);
+          } else {
+            mma_f16(o[n], a, b[0], b[1]);
+            mma_f16(o[n + 1], a, b[2], b[3]);
+          }
         }
         if (DV & 1) {
           uint32_t b[2];
           ldsm_x2_t(v_base1 + blk * BLK + (uint32_t)(j * 16 * LDS * 2), b);
-          mma_f16(o[DV - 1], a, b[0], b[1]);
+          if (NBLK == 1 && j == 0) mma_f16_z(o[DV - 1], a, b[0], b[1]);
+          else mma_f16(o[DV - 1], a, b[0], b[1]);
         }
       }
     }

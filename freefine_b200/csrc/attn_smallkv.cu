@@ -118,7 +118,29 @@ attn_smallkv_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
   const bool ld_on = ld_c < DP / 8, ld_data = ld_c < DV;
   const uint32_t qs_u32 = smem_u32(Qs);
 
-  // Q tile of step `st` -> slot st & 1 (rows past s_q and the padding columns D..DP are zero-filled)
+  // Q tile of step `st` -> slot st & 1 (rows past s_q and the padding columns D..DP are zero-filled).  FF_SK_WP (default):
+  // every warp copies ITS OWN 16 rows, so the step loop needs no CTA-wide barrier (cp.async wait + __syncwarp) and the
+  // four warps of a CTA drift apart instead of meeting twice per step.
+#ifndef FF_SK_WP
+#define FF_SK_WP 1
+#endif
+#if FF_SK_WP
+  constexpr int TPQ = sk_pow2_at_least(DP / 8);            // lanes side by side over the vectors of a row (<= 32)
+  const int wq_r = lane / TPQ, wq_c = lane % TPQ;
+  auto load_q = [&](int st) {
+    if (wq_c >= DP / 8) return;
+    const int base = row0 + st * SK_ROWS + warp * 16;
+    uint32_t dst = qs_u32 + (st & 1) * SLOT + ((warp * 16 + wq_r) * LDS + 8 * wq_c) * 2;
+    const __nv_bfloat16* src = qg + (size_t)(base + wq_r) * C + 8 * wq_c;
+#pragma unroll
+    for (int r = 0; r < 16; r += 32 / TPQ) {
+      const bool ok = wq_c < DV && base + wq_r + r < s_q;
+      cp_async16(dst, ok ? static_cast<const void*>(src) : static_cast<const void*>(qg), ok);
+      dst += (32 / TPQ) * LDS * 2;
+      src += (size_t)(32 / TPQ) * C;
+    }
+  };
+#else
   auto load_q = [&](int st) {
     if (!ld_on) return;
     const int base = row0 + st * SK_ROWS;
@@ -132,6 +154,7 @@ attn_smallkv_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
       src += (size_t)(SK_THREADS / TPR) * C;
     }
   };
+#endif
   // K and V of this (stream, head): every 16-byte vector goes out as a cp.async at once (rows >= s_kv and the K padding
   // columns zero-filled), together with the first Q tile -- ONE exposed memory latency for the whole prologue (the first
   // version walked the rows with load -> convert -> store per trip: 64 dependent trips for 256 keys x d=160).  V lands as
@@ -163,6 +186,9 @@ attn_smallkv_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
       *pv = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
+#if FF_SK_WP
+  __syncthreads();                   // K / V of the CTA are in place (the step loop itself has no CTA-wide barrier)
+#endif
   // per-lane ldmatrix bases (bytes)
   const uint32_t q_lane = (uint32_t)(((warp * 16 + (lane & 15)) * LDS + (lane >> 4) * 8) * 2);
   const uint32_t k_base = smem_u32(Ks) + (uint32_t)((((lane >> 4) * 8 + (lane & 7)) * LDS + ((lane >> 3) & 1) * 8) * 2);
@@ -178,7 +204,11 @@ attn_smallkv_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
     if (st + 1 < n_steps) load_q(st + 1);
     cp_async_commit();
     cp_async_wait<1>();              // the tile of this step has landed (the one just issued may still fly)
+#if FF_SK_WP
+    __syncwarp();                    // ... for every lane's copies of my warp's rows
+#else
     __syncthreads();                 // ... for every thread's copies; also covers the K / V stores before the first step
+#endif
     const uint32_t slot = qs_u32 + (st & 1) * SLOT;
 
     float o[DV][4];
@@ -315,7 +345,11 @@ attn_smallkv_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
         }
       }
     }
+#if FF_SK_WP
+    __syncwarp();                    // my rows of the slot are free for the tile of step st + 2
+#else
     __syncthreads();                 // the slot is free for the tile of step st + 2
+#endif
   }
   cp_async_wait<0>();
 }

@@ -809,9 +809,16 @@ bias_residual_kernel(const uint4* __restrict__ h, const __nv_bfloat16* __restric
 // a launch that took 197 us; the HBM floor is 154 us).  gelu_erf_x_bf16x2 evaluates a PAIR of gates with packed FFMA2 / FMUL2 (0.5 folded into the polynomial,
 // gelu = g / 2 + |g| * (1/2 - erfc/2): no select), rounds the pair to bf16x2 and multiplies it with the still-packed x
 // pair by HMUL2.BF16 -- exact product, ONE rounding: what the eager bf16 multiply does -- so x is never
-// unpacked: ~12 instructions per element.  With two MUFU operations per element the MUFU pipe (16 lanes per clock and
-// SM) would then be the bound at 149 us, so every other pair takes its reciprocal on the FMA pipe (seed + 3 Newton steps,
-// see silu8).
+// unpacked: ~12 instructions per element.  The launch is then bound by PIPE throughput, not issue slots: per element 10.5
+// fp32 FMA-pipe operations (128 lanes per clock and SM; FFMA2 saves issue slots, not lanes) + 2 MUFU operations (16 lanes)
+// = 95 / 149 us for 335 M elements against an HBM floor of 154 us; a Newton reciprocal (seed + 3 steps, see silu8) moves
+// one MUFU operation to six FMA ones.  Measured at 131072 x 1280 with 0 / 1 / 2 pairs in four on the FMA pipe: 178.2 / 188.1 /
+// 189.6 us -- every FMA-pipe operation added costs more than the MUFU operation it replaces, so all reciprocals stay on
+// the MUFU pipe (FF_GEGLU_NR_PAIRS = 0).
+// pairs per 16-byte vector (of 4) whose reciprocal runs on the FMA pipe -- see the balance below
+#ifndef FF_GEGLU_NR_PAIRS
+#define FF_GEGLU_NR_PAIRS 0
+#endif
 template <bool NEWTON>
 __device__ __forceinline__ uint32_t gelu_erf_x_bf16x2(uint32_t gate, uint32_t xw) {
   const float2 g = make_float2(__uint_as_float(gate << 16), __uint_as_float(gate & 0xffff0000u));
@@ -837,16 +844,44 @@ __device__ __forceinline__ uint32_t gelu_erf_x_bf16x2(uint32_t gate, uint32_t xw
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(arg.x));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(arg.y));
   const float2 h = __fmul2_rn(__fmul2_rn(p, t), e);                                       // erfc(|g| / sqrt 2) / 2
-  const float2 q = __fadd2_rn(make_float2(0.5f, 0.5f), make_float2(-h.x, -h.y));
-  const float2 ge = __ffma2_rn(ag, q, __fmul2_rn(g, make_float2(0.5f, 0.5f)));           // g/2 + |g| (1/2 - h) = g Phi(g)
+  // g Phi(g) = relu(g) - |g| h  (g >= 0: g (1 - h); g < 0: g h): the relu is an ALU-pipe FMNMX, ONE FMA-pipe operation left
+  const float2 ge = __ffma2_rn(make_float2(-ag.x, -ag.y), h, make_float2(fmaxf(g.x, 0.f), fmaxf(g.y, 0.f)));
   const __nv_bfloat162 gb = __floats2bfloat162_rn(ge.x, ge.y);                            // the bf16 tensor F.gelu returns
   const __nv_bfloat162 r = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&xw), gb);   // bf16 * bf16, one rounding
   return *reinterpret_cast<const uint32_t*>(&r);
 }
 
 __device__ __forceinline__ uint4 geglu8(const uint4& qx, const uint4& qg) {
-  return make_uint4(gelu_erf_x_bf16x2<false>(qg.x, qx.x), gelu_erf_x_bf16x2<true>(qg.y, qx.y),
-                    gelu_erf_x_bf16x2<false>(qg.z, qx.z), gelu_erf_x_bf16x2<true>(qg.w, qx.w));
+  return make_uint4(gelu_erf_x_bf16x2<false>(qg.x, qx.x), gelu_erf_x_bf16x2<FF_GEGLU_NR_PAIRS >= 1>(qg.y, qx.y),
+                    gelu_erf_x_bf16x2<false>(qg.z, qx.z), gelu_erf_x_bf16x2<FF_GEGLU_NR_PAIRS >= 2>(qg.w, qx.w));
+}
+
+// One warp per row of h, lanes over its 16-byte vectors, GEGLU_U vectors of x and of the gate in flight per lane: the
+// flat-index kernel below spends ~100 of its ~200 instructions per trip on 64-bit (row, vector) arithmetic and selects
+// (cuobjdump), here a vector costs one add.  Rows of F = 1280 / 2560 / 5120 channels are 160 / 320 / 640 vectors: whole
+// trips of 32 x 5 lanes-vectors, no idle lanes.
+constexpr int GEGLU_U = 5;
+__global__ void __launch_bounds__(256)
+geglu_rows_kernel(const uint4* __restrict__ h, uint4* __restrict__ out, long long M, int FV) {
+  const int lane = threadIdx.x & 31;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long m = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < M; m += nwarps) {
+    const uint4* row = h + m * 2 * FV + lane;
+    uint4* orow = out + m * FV + lane;
+    for (int v0 = 0; v0 < FV; v0 += 32 * GEGLU_U) {
+      uint4 qx[GEGLU_U], qg[GEGLU_U];
+#pragma unroll
+      for (int u = 0; u < GEGLU_U; ++u) {
+        if (v0 + 32 * u + lane < FV) {
+          qx[u] = __ldg(row + v0 + 32 * u);
+          qg[u] = __ldg(row + FV + v0 + 32 * u);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < GEGLU_U; ++u)
+        if (v0 + 32 * u + lane < FV) orow[v0 + 32 * u] = geglu8(qx[u], qg[u]);
+    }
+  }
 }
 
 // (dm, dv) = (2 * stride) div / mod FV from the host: the (row, vector) pair advances without a 64-bit division per trip
@@ -1228,7 +1263,15 @@ extern "C" int ff_geglu(const void* h, void* out, int64_t M, int32_t F, void* st
   const long long total = (long long)M * (F / 8);
   // (a persistent grid of 148 x {4, 6, 8, 12} CTAs measured the same or slower than the 148 x 16 cap: 192 / 230 / 192 / 191
   // vs 190 us at 131072 x 1280 -- the launch sits at 5.3 TB/s of its two-reads-one-write traffic either way)
-  const int grid = grid_for(total), FV = F / 8;
+  const int FV = F / 8;
+  static const bool rows_off = [] { const char* e = getenv("FF_GEGLU_ROWS"); return e && atoi(e) == 0; }();
+  if (FV >= 32 && !rows_off) {            // one warp per row (FF_GEGLU_ROWS=0: the flat-index kernel, A/B switch)
+    long long blocks = (M + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    geglu_rows_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(h), static_cast<uint4*>(out), M, FV);
+    return ff::check_launch("ff_geglu");
+  }
+  const int grid = grid_for(total);
   const long long step2 = 2LL * grid * 256;
   geglu_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(h), static_cast<uint4*>(out), total, FV, step2 / FV, (int)(step2 % FV));

@@ -1027,19 +1027,29 @@ concat_nhwc_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uin
 // LayerNorm for C = 40 * LPR channels (320 / 640 / 1280: every transformer width of SD1.5): LPR = 8 / 16 / 32 lanes share a
 // row, FIVE 16-byte vectors per lane -- no idle lanes (the generic kernel above gives a 320-channel row to a whole warp:
 // 40 vectors over 32 lanes = two rounds with 24 lanes idle in the second, and a five-step butterfly where three suffice).
-// gamma / beta stay packed in registers across the rows a warp walks.
+// Round 2 (third session): the row stays PACKED (20 registers) and is unpacked again in each of the three passes (sum,
+// centred variance, output) instead of living as 40 fp32 registers -- 80 registers, three CTAs per SM instead of two, i.e.
+// 61 KB of loads in flight per SM instead of 41 KB (the kernel is latency-bound: ~10 instructions per element); the
+// arithmetic runs on channel pairs (FADD2 / FFMA2).
+#ifndef FF_LN5_MINB
+#define FF_LN5_MINB 3
+#endif
+__device__ __forceinline__ uint4 ld_nc_volatile(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+// optimisation barrier: the four words are "modified", so a later unpack is recomputed from them instead of being kept
+__device__ __forceinline__ void keep_packed(uint4& q) { asm volatile("" : "+r"(q.x), "+r"(q.y), "+r"(q.z), "+r"(q.w)); }
+
 template <int LPR>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, FF_LN5_MINB)
 layer_norm5_kernel(const uint4* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
                    const __nv_bfloat16* __restrict__ beta, uint4* __restrict__ y, long long M, float eps) {
   constexpr int RPW = 32 / LPR, CV = 5 * LPR;
   const int lane = threadIdx.x & 31, sub = lane % LPR, rsel = lane / LPR;
-  uint4 gq[5], bq[5];
-#pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    gq[k] = __ldg(reinterpret_cast<const uint4*>(gamma) + sub + LPR * k);
-    bq[k] = __ldg(reinterpret_cast<const uint4*>(beta) + sub + LPR * k);
-  }
+  const uint4* g4 = reinterpret_cast<const uint4*>(gamma) + sub;
+  const uint4* b4 = reinterpret_cast<const uint4*>(beta) + sub;
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const float inv_c = 1.f / (float)(8 * CV);
   for (long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW; row0 < M; row0 += nwarps * RPW) {
@@ -1048,39 +1058,55 @@ layer_norm5_kernel(const uint4* __restrict__ x, const __nv_bfloat16* __restrict_
     uint4 raw[5];
 #pragma unroll
     for (int k = 0; k < 5; ++k) raw[k] = valid ? __ldg(x + row * CV + sub + LPR * k) : make_uint4(0u, 0u, 0u, 0u);
-    float f[5][8];
-    float s = 0.f;
+    float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
-      unpack8(raw[k], f[k]);
+      float2 f[4];
+      unpack8_pairs(raw[k], f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s += f[k][j];
+      for (int i = 0; i < 4; ++i) s2 = __fadd2_rn(s2, f[i]);
     }
+    float s = s2.x + s2.y;
 #pragma unroll
     for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float mean = s * inv_c;
-    float ss = 0.f;
+    const float2 nm = make_float2(-mean, -mean);
+    float2 q2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
+      float2 f[4];
+      keep_packed(raw[k]);             // (without it the compiler keeps the 40 unpacked values of the first pass alive)
+      unpack8_pairs(raw[k], f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = f[k][j] - mean;
-        ss = fmaf(d, d, ss);
+      for (int i = 0; i < 4; ++i) {
+        const float2 d = __fadd2_rn(f[i], nm);
+        q2 = __ffma2_rn(d, d, q2);
       }
     }
+    float ss = q2.x + q2.y;
 #pragma unroll
     for (int o = LPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     const float rstd = 1.f / sqrtf(ss * inv_c + eps);
     if (valid) {
+      const float2 r2 = make_float2(rstd, rstd);
       uint4* py = y + row * CV + sub;
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        float ga[8], be[8], o[8];
-        unpack8(gq[k], ga);
-        unpack8(bq[k], be);
+        float2 f[4], ga[4], be[4];
+        keep_packed(raw[k]);
+        // gamma / beta come from L1 every row (volatile loads: hoisted out of the row loop they cost 40 registers packed,
+        // 80 unpacked -- the occupancy this version is about)
+        unpack8_pairs(ld_nc_volatile(g4 + LPR * k), ga);
+        unpack8_pairs(ld_nc_volatile(b4 + LPR * k), be);
+        unpack8_pairs(raw[k], f);
+        uint32_t w[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = fmaf((f[k][j] - mean) * rstd, ga[j], be[j]);
-        py[LPR * k] = pack8(o);
+        for (int i = 0; i < 4; ++i) {
+          const float2 o = __ffma2_rn(__fmul2_rn(__fadd2_rn(f[i], nm), r2), ga[i], be[i]);
+          const __nv_bfloat162 b = __floats2bfloat162_rn(o.x, o.y);
+          w[i] = *reinterpret_cast<const uint32_t*>(&b);
+        }
+        py[LPR * k] = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
   }
@@ -1296,8 +1322,10 @@ extern "C" int ff_layer_norm(const void* x, const void* gamma, const void* beta,
   FF_REQUIRE(blocks <= 2147483647LL, "ff_layer_norm: too many rows");
   if (CV == 40 || CV == 80 || CV == 160) {                    // C = 320 / 640 / 1280: sub-warp rows, five vectors per lane
     const int lpr = CV / 5, rpw = 32 / lpr;
-    long long nb = (M + 8LL * rpw * 4 - 1) / (8LL * rpw * 4);   // about four row groups per warp
-    if (nb > 148 * 16) nb = 148 * 16;
+    long long nb = (M + 8LL * rpw * 4 - 1) / (8LL * rpw * 4);   // about four row groups per warp ...
+    // ... but at most what is resident at once (3 CTAs per SM): a persistent grid, no partial last wave.  FF_LN5_CTAS: knob.
+    static const int cap = [] { const char* e = getenv("FF_LN5_CTAS"); const int v = e ? atoi(e) : 0; return v >= 1 ? v : 148 * FF_LN5_MINB; }();
+    if (nb > cap) nb = cap;
     if (lpr == 8) layer_norm5_kernel<8><<<(int)nb, 256, 0, st>>>(xp, gp, bp, yp, M, eps);
     else if (lpr == 16) layer_norm5_kernel<16><<<(int)nb, 256, 0, st>>>(xp, gp, bp, yp, M, eps);
     else layer_norm5_kernel<32><<<(int)nb, 256, 0, st>>>(xp, gp, bp, yp, M, eps);

@@ -505,7 +505,9 @@ def run_ours(args):
             extras["rooflines"] = RF.hbm_rooflines(dev, hbm_peak) + RF.attention_rooflines(dev, burst)
             extras["rooflines_note"] = ("each kernel alone after the timed region: HBM-bound kernels on L2-exceeding batches (CUDA-graph "
                                         "replays, 3 warm-ups, best of 5) vs the measured copy peak; attention per layer shape vs the "
-                                        "BURST bf16 peak (kernel timed in isolation); in-run attention rows (`rooflines_in_run`) vs the sustained peak")
+                                        "BURST bf16 peak (kernel timed in isolation); in-run attention rows (`rooflines_in_run`) vs the sustained peak; the HBM "
+                                        "denominator is the measured COPY bandwidth (1 read : 1 write), so a read-heavy kernel at the HBM limit "
+                                        "(ff_geglu: 2 reads : 1 write) can show a fraction slightly above 1")
         except Exception as e:
             extras["rooflines"] = [{"error": str(e)[:300]}]
         # ---- parity of whole edits against the reference goldens, on the timed UNet path and on the fp32 body

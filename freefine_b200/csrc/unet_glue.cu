@@ -1052,61 +1052,75 @@ layer_norm5_kernel(const uint4* __restrict__ x, const __nv_bfloat16* __restrict_
   const uint4* b4 = reinterpret_cast<const uint4*>(beta) + sub;
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const float inv_c = 1.f / (float)(8 * CV);
-  for (long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW; row0 < M; row0 += nwarps * RPW) {
-    const long long row = row0 + rsel;
-    const bool valid = row < M;
-    uint4 raw[5];
+  // FF_LN5_GROUPS row groups per trip, their loads all issued before the first reduction: 2 groups (10 x 16 bytes in flight
+  // per lane) measured SLOWER than 1 (35.9 vs 29.9 us at 131072 x 320: 140 bytes of spills at 80 registers), so 1 it is
+#ifndef FF_LN5_GROUPS
+#define FF_LN5_GROUPS 1
+#endif
+  constexpr int NG = FF_LN5_GROUPS;
+  for (long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW; row0 < M; row0 += NG * nwarps * RPW) {
+    uint4 raw[NG][5];
+    bool valid[NG];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) raw[k] = valid ? __ldg(x + row * CV + sub + LPR * k) : make_uint4(0u, 0u, 0u, 0u);
-    float2 s2 = make_float2(0.f, 0.f);
+    for (int g = 0; g < NG; ++g) {
+      const long long row = row0 + g * nwarps * RPW + rsel;
+      valid[g] = row < M;
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      float2 f[4];
-      unpack8_pairs(raw[k], f);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) s2 = __fadd2_rn(s2, f[i]);
+      for (int k = 0; k < 5; ++k) raw[g][k] = valid[g] ? __ldg(x + row * CV + sub + LPR * k) : make_uint4(0u, 0u, 0u, 0u);
     }
-    float s = s2.x + s2.y;
 #pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s * inv_c;
-    const float2 nm = make_float2(-mean, -mean);
-    float2 q2 = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      float2 f[4];
-      keep_packed(raw[k]);             // (without it the compiler keeps the 40 unpacked values of the first pass alive)
-      unpack8_pairs(raw[k], f);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 d = __fadd2_rn(f[i], nm);
-        q2 = __ffma2_rn(d, d, q2);
-      }
-    }
-    float ss = q2.x + q2.y;
-#pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float rstd = 1.f / sqrtf(ss * inv_c + eps);
-    if (valid) {
-      const float2 r2 = make_float2(rstd, rstd);
-      uint4* py = y + row * CV + sub;
+    for (int g = 0; g < NG; ++g) {
+      const long long row = row0 + g * nwarps * RPW + rsel;
+      float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        float2 f[4], ga[4], be[4];
-        keep_packed(raw[k]);
-        // gamma / beta come from L1 every row (volatile loads: hoisted out of the row loop they cost 40 registers packed,
-        // 80 unpacked -- the occupancy this version is about)
-        unpack8_pairs(ld_nc_volatile(g4 + LPR * k), ga);
-        unpack8_pairs(ld_nc_volatile(b4 + LPR * k), be);
-        unpack8_pairs(raw[k], f);
-        uint32_t w[4];
+        float2 f[4];
+        unpack8_pairs(raw[g][k], f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s2 = __fadd2_rn(s2, f[i]);
+      }
+      float s = s2.x + s2.y;
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s * inv_c;
+      const float2 nm = make_float2(-mean, -mean);
+      float2 q2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        float2 f[4];
+        keep_packed(raw[g][k]);          // (without it the compiler keeps the 40 unpacked values of the first pass alive)
+        unpack8_pairs(raw[g][k], f);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float2 o = __ffma2_rn(__fmul2_rn(__fadd2_rn(f[i], nm), r2), ga[i], be[i]);
-          const __nv_bfloat162 b = __floats2bfloat162_rn(o.x, o.y);
-          w[i] = *reinterpret_cast<const uint32_t*>(&b);
+          const float2 d = __fadd2_rn(f[i], nm);
+          q2 = __ffma2_rn(d, d, q2);
         }
-        py[LPR * k] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      float ss = q2.x + q2.y;
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float rstd = 1.f / sqrtf(ss * inv_c + eps);
+      if (valid[g]) {
+        const float2 r2 = make_float2(rstd, rstd);
+        uint4* py = y + row * CV + sub;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          float2 f[4], ga[4], be[4];
+          keep_packed(raw[g][k]);
+          // gamma / beta come from L1 every row (volatile loads: hoisted out of the row loop they cost 40 registers packed,
+          // 80 unpacked -- the occupancy this version is about)
+          unpack8_pairs(ld_nc_volatile(g4 + LPR * k), ga);
+          unpack8_pairs(ld_nc_volatile(b4 + LPR * k), be);
+          unpack8_pairs(raw[g][k], f);
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 o = __ffma2_rn(__fmul2_rn(__fadd2_rn(f[i], nm), r2), ga[i], be[i]);
+            const __nv_bfloat162 b = __floats2bfloat162_rn(o.x, o.y);
+            w[i] = *reinterpret_cast<const uint32_t*>(&b);
+          }
+          py[LPR * k] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
       }
     }
   }

@@ -117,7 +117,7 @@ def test_bias_residual_nhwc(dev, shape, with_bias, with_res):
     torch.testing.assert_close(got.float(), want.float(), rtol=RTOL, atol=ATOL)
 
 
-@pytest.mark.parametrize("M,Fdim", [(77, 320), (4096, 1280), (231, 640), (64, 5120), (3, 8)])
+@pytest.mark.parametrize("M,Fdim", [(77, 320), (4096, 1280), (231, 640), (64, 5120), (3, 8), (5, 2000), (9, 248)])
 def test_geglu(dev, M, Fdim):
     from freefine_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(31)

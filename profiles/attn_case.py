@@ -22,6 +22,9 @@ for S, d in ((4096, 40), (1024, 80)):
     bits, pop = ops.mask_downsample_pack(torch.from_numpy(np.stack(masks)).to(dev), hw, hw)
     prefix = os.environ.get("FF_PREFIX", "1") == "1"       # the controller's default: keys sorted "source first"
     plan_np = plans.tca_plan(E, heads, "tca", 0.5, lambda e: 2 * e, lambda e: 2 * e + 1, prefix=prefix)
+    plain = os.environ.get("FF_PLAIN", "0") == "1"         # the plain self-attention layers (outside the TCA scope / inversion)
+    if plain:
+        plan_np, prefix = plans.plain_plan(4 * E, heads), False
     plan = ops.to_device_bytes(plan_np, dev)
     idx = None
     if prefix:
@@ -39,5 +42,5 @@ for S, d in ((4096, 40), (1024, 80)):
         ev[i + 1].record()
     torch.cuda.synchronize()
     ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(reps)]
-    print(f"S={S} d={d} streams={4*E} prefix={prefix} P={os.environ.get('FF_P', 'f16')}: {min(ms):.3f} ms best / {sum(ms)/len(ms):.3f} ms avg, algorithmic {flops/1e9:.1f} GFLOP -> "
+    print(f"S={S} d={d} streams={4*E} {'PLAIN ' if plain else ''}prefix={prefix} P={os.environ.get('FF_P', 'f16')}: {min(ms):.3f} ms best / {sum(ms)/len(ms):.3f} ms avg, algorithmic {flops/1e9:.1f} GFLOP -> "
           f"{flops / (min(ms) * 1e-3) / 1e12:.1f} TFLOP/s (dense-equivalent {7*4*S*S*d*heads*E/1e9:.1f} GFLOP)")

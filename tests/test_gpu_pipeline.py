@@ -43,7 +43,7 @@ NORTH_STAR_TOL = 1e-2
 # The bf16 channels-last UNet body (the path bench.py times; SURVEY.md 8d prescribes bf16 weights for the new path) is a
 # different NETWORK PRECISION from the fp32 reference: one forward of the tiny stand-in differs by 1.3e-2 rel-L2 already,
 # and an edit feeds 20-100 forwards back into its own input.  Measured on B200 (round 2, tests/gpu_diag_parity.py):
-# final latents 0.03 (config 1) / 0.10-0.14 (15+15 calls) / 0.20-0.23 (50+50 calls) rel-L2, moving by ~0.03 from build to build (any
+# final latents 0.03-0.04 (config 1) / 0.06-0.14 (15+15 calls) / 0.17-0.23 (50+50 calls) rel-L2 across the builds of round 2 (any
 # change of rounding is amplified by the schedule).  The bound below is a regression guard for that path, NOT the north-star tolerance
 # -- that one is checked, and met (2e-4 - 1.5e-3), with the fp32 UNet body and the same sm_100a kernels.
 BF16_BODY_BOUND = 0.35
